@@ -1,0 +1,118 @@
+/*
+ * rayuela_b200.h -- C ABI of librayuela_b200.so: the B200 (sm_100a) implementation of Rayuela.jl's two
+ * data-parallel hot paths.  Plain pointers and sizes only; every entry point cites the reference
+ * interface it replaces (paths relative to the Rayuela.jl tree).
+ *
+ * Array layouts are the memory images Julia's ccall passes (column-major):
+ *   X   d-by-n  float32  -> X[l*d + t]
+ *   C   d-by-(m*h) float32 (hcat(C...)) -> C[(j*h + c)*d + t]
+ *   B   m-by-n  uint8, 0-based -> B[l*m + k]
+ *   dists / idx  k-by-nq -> out[q*k + r]
+ * There is no CPU fallback anywhere in this library: every call needs a CUDA device and fails with
+ * RAYUELA_ERR_CUDA (or aborts, for the void compat symbols) when there is none.
+ */
+#ifndef RAYUELA_B200_H_
+#define RAYUELA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status ------------------------------------------------------------------------------------- */
+#define RAYUELA_OK 0
+#define RAYUELA_ERR_ARG (-1)   /* bad shape / unsupported parameter (e.g. h != 256, src/LSQ.jl:173-175) */
+#define RAYUELA_ERR_CUDA (-2)  /* CUDA runtime error (incl. no device) */
+#define RAYUELA_ERR_OOM (-3)
+
+/* flags */
+#define RAYUELA_DEVICE_PTRS 1u /* all array arguments are device pointers on the current device */
+
+/* Last error message of the calling thread ("" if none). The reference has no error channel at all
+ * (void symbols, deps/src/*.cpp extern blocks); Julia-side checks are error() strings. */
+const char* rayuela_last_error(void);
+
+/* Select the CUDA device used by subsequent calls from this thread (default: current device).
+ * The reference hard-codes device 0 (src/LSQ_GPU.jl:41,45). */
+int rayuela_set_device(int device);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
+uint64_t rayuela_launch_count(void);
+
+/* ---- path (1): LSQ / LSQ++ ICM-ILS encoding ------------------------------------------------------ */
+
+/* Replaces encode_icm_fully! (src/LSQ.jl:152-252) together with its callee loop
+ * iterated_conditional_modes_cpp! (src/LSQ.jl:42-80) / `condition` (deps/src/encode_icm.cpp:3-61), i.e.
+ * everything encoding_icm (src/LSQ.jl:272-294) and encode_icm_cuda_single (src/LSQ_GPU.jl:4-216) do:
+ * unaries, pairwise tables, ilsiter x {perturb, icmiter x m conditioning steps, cost, strict-< accept}.
+ *   B          in/out: initial codes, overwritten with the result (oldB semantics, src/LSQ.jl:248)
+ *   g0         global index of the first vector (RNG is keyed on the global index, so any sharding of
+ *              the base set across calls / GPUs gives identical codes)
+ *   orders     ilsiter-by-m visiting orders (0-based, host memory) or NULL: randord ? Philox randperm(seed)
+ *              : identity  (src/LSQ.jl:218-221)
+ *   snap_iters n_snap ILS iteration counts (1-based, host memory) at which B is copied to B_snap[s] and
+ *              qerror to objs[s] (host memory) -- encode_icm_cuda's `ilsiters` (src/LSQ_GPU.jl:193-204)
+ *   cost_out   n floats or NULL: final veccost per vector
+ *   stats      2*ilsiter ints (host memory) or NULL: (#equal, #better) per ILS iteration, the figures
+ *              the reference prints at src/LSQ.jl:243-245
+ */
+int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
+                       int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
+                       const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
+                       float* cost_out, int* stats, unsigned flags, void* stream);
+
+/* Replaces veccost (src/qerrors.jl:36-66).  mean_out (host double, may be NULL) receives qerror
+ * (src/qerrors.jl:69-74). cost may be NULL when only the mean is wanted. */
+int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,
+                    float* cost, double* mean_out, unsigned flags, void* stream);
+
+/* Exact-signature replacement of the reference symbol `condition` (deps/src/encode_icm.cpp:157-168), called
+ * at src/LSQ.jl:71-75.  Host pointers.  Kept for drop-in completeness; it is the wrong granularity for a
+ * GPU (one call per codebook step with an n*256 float host scratch) -- use rayuela_encode_icm. */
+void condition(unsigned char* B, float* ub, float* binaries, float* binaries_t, int* cbpair2binaryidx,
+               int* to_condition, int j, int n, int m);
+
+/* ---- path (2): asymmetric-distance linear scan --------------------------------------------------- */
+
+/* Exact-signature replacements of the reference symbols (host pointers, synchronous):
+ *   linscan_aqd_query                deps/src/linscan_aqd.cpp:107-113, called at src/Linscan.jl:19-23 (PQ/OPQ; 0-based ids)
+ *   linscan_aqd_query_extra_byte     deps/src/linscan_aqd_pairwise_byte.cpp:181-188, src/Linscan.jl:135-141 (LSQ; 1-based ids)
+ *   linscan_aqd_cq_query_extra_byte  deps/src/linscan_aqd_pairwise_byte.cpp:190-197, src/Linscan.jl:173-179 (CQ; 1-based ids) */
+void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, float* centers, float* queries,
+                       int N, unsigned int NQ, int B, int K, int dim1codes, int dim1queries, int subdim);
+void linscan_aqd_query_extra_byte(float* dists, int* idx, unsigned char* codes, float* queries,
+                                  float* codebooks, float* dbnorms, int nqueries, int ncodes, int m, int h,
+                                  int d, int nn);
+void linscan_aqd_cq_query_extra_byte(float* dists, int* idx, unsigned char* codes, float* queries,
+                                     float* codebooks, int nqueries, int ncodes, int m, int h, int d, int nn);
+
+/* Handle API: the encoded base set is uploaded / re-laid-out once and scanned many times. */
+#define RAYUELA_SCAN_LSQ 0 /* lut = -2<q,c>,  + dbnorms[i], ids 1-based (pairwise_byte.cpp:14-94) */
+#define RAYUELA_SCAN_CQ 1  /* lut = ||q-c||^2, ids 1-based            (pairwise_byte.cpp:97-176) */
+#define RAYUELA_SCAN_PQ 2  /* lut = per-subspace ||c-q||^2, ids 0-based (linscan_aqd.cpp:37-102) */
+typedef struct rayuela_index rayuela_index;
+
+/* id_offset is added to every returned id (global ids for a base shard of a multi-GPU index). */
+int rayuela_index_create(rayuela_index** out, int kind, const uint8_t* codes, const float* dbnorms, int64_t n,
+                         int m, int h, int64_t id_offset, unsigned flags, void* stream);
+/* codebooks: d-by-(m*h) (LSQ/CQ) or sub-by-h-by-m (PQ, d = m*sub).  dists/idx: k-by-nq. */
+int rayuela_index_search(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d, int k,
+                         float* dists, int32_t* idx, unsigned flags, void* stream);
+int rayuela_index_free(rayuela_index* ix);
+
+/* Merge S per-shard result lists (each k-by-nq, sorted by (dist, id)) into the global top-k by the same
+ * total order std::partial_sort uses on pair<float,int> (pairwise_byte.cpp:82).  Used after the all-gather
+ * of per-GPU results; in/out layouts [S][nq][k] and [nq][k]. */
+int rayuela_topk_merge(const float* dists_in, const int32_t* idx_in, int S, int nq, int k, float* dists_out,
+                       int32_t* idx_out, unsigned flags, void* stream);
+
+/* ---- PQ / OPQ encode ------------------------------------------------------------------------------ */
+/* Replaces quantize_pq (src/PQ.jl:18-48); quantize_opq (src/OPQ.jl:19-27) is this on R'X.
+ * Cpq: sub-by-h-by-m (cat(C..., dims=3)); B out m-by-n uint8 0-based. */
+int rayuela_quantize_pq(const float* X, const float* Cpq, int64_t n, int d, int m, int h, uint8_t* B,
+                        unsigned flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAYUELA_B200_H_ */

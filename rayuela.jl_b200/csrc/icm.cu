@@ -1,0 +1,614 @@
+// icm.cu -- path (1): LSQ / LSQ++ ICM-ILS encoding on B200.
+//   K0 sqnorm_kernel     ||c||^2 of every codebook entry
+//   K1 unary_kernel      U[l][j][c] = -2<C_j[:,c], x_l> + ||C_j[:,c]||^2     (src/utils.jl:121-149)
+//   K2 tables_kernel     T[j][k][b][c] = 2<C_j[:,c], C_k[:,b]>, both orientations (src/utils.jl:152-171,
+//                        src/LSQ.jl:180-183), so every conditioning row is 1 KB contiguous
+//   K3 icm_warp_kernel   the whole ILS loop of encode_icm_fully! (src/LSQ.jl:199-249) fused on device:
+//                        perturb -> icmiter x m conditioning steps (deps/src/encode_icm.cpp:26-59) -> cost ->
+//                        strict-< accept; one warp per vector
+//   veccost_kernel       src/qerrors.jl:36-66
+//   condition_kernel     exact-signature compat for deps/src/encode_icm.cpp:157-168
+// Arithmetic orders are the oracle's (DESIGN.md "Arithmetic contract"): sequential-t fmaf chains for the
+// dot products, ascending-k fp32 adds for the conditioning, sequential unfused sums for the cost.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ryl {
+
+static constexpr int kH = 256;
+
+// ---- K0 ---------------------------------------------------------------------------------------------
+__global__ void sqnorm_kernel(const float* __restrict__ C, int d, int mh, float* __restrict__ nrm) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= mh) return;
+  const float* c = C + (size_t)e * d;
+  float s = 0.f;
+  for (int t = 0; t < d; t++) s = fmaf(c[t], c[t], s);
+  nrm[e] = s;
+}
+
+// ---- K1: fp32 SIMT GEMM, 128 entries x 128 vectors per block, 8x8 per thread, BK = 8 --------------------
+// Each output is ONE sequential-t fmaf chain (no split-K), so it is bit-identical to the oracle's dot_seq.
+template <bool VEC4>
+__global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C, const float* __restrict__ X,
+                                                    const float* __restrict__ nrm, float* __restrict__ U, int64_t n,
+                                                    int d, int mh) {
+  constexpr int BM = 128, BN = 128, BK = 8;
+  __shared__ __align__(16) float As[BK][BM];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int e0 = blockIdx.x * BM;
+  const int64_t l0 = (int64_t)blockIdx.y * BN;
+  const int lr = tid >> 1, lk = (tid & 1) * 4;  // loader: row, k-quad
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < d; k0 += BK) {
+    float a[4], b[4];
+    const float* ap = C + (size_t)(e0 + lr) * d + k0 + lk;
+    const int64_t lv = l0 + lr;
+    const float* bp = X + (size_t)(lv < n ? lv : n - 1) * d + k0 + lk;
+    if (VEC4) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
+      if (k0 + lk < d) {  // d % 4 == 0: a quad is entirely inside or entirely outside
+        av = *reinterpret_cast<const float4*>(ap);
+        bv = *reinterpret_cast<const float4*>(bp);
+      }
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        bool ok = k0 + lk + i < d;
+        a[i] = ok ? ap[i] : 0.f;
+        b[i] = ok ? bp[i] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      As[lk + i][lr] = a[i];
+      Bs[lk + i][lr] = b[i];
+    }
+    __syncthreads();
+    const int kmax = min(BK, d - k0);  // the chain is exactly d long, like the oracle's dot_seq
+    for (int kk = 0; kk < kmax; kk++) {
+      float av[8], bv[8];
+      *reinterpret_cast<float4*>(&av[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      *reinterpret_cast<float4*>(&av[4]) = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      *reinterpret_cast<float4*>(&bv[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+      *reinterpret_cast<float4*>(&bv[4]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float nr[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) nr[i] = nrm[e0 + ty * 8 + i];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    int64_t l = l0 + tx * 8 + j;
+    if (l < n) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] = fmaf(-2.0f, acc[i][j], nr[i]);  // -2*dot exact, one rounding
+      float* dst = U + (size_t)l * mh + e0 + ty * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// ---- K2: pairwise tables, both orientations ------------------------------------------------------------
+// T[((j*m + k)*256 + b)*256 + c] = 2 * <C_j[:,c], C_k[:,b]>; the product is commutative inside fmaf, so
+// T[j][k][b][c] == T[k][j][c][b] bit for bit, i.e. this is binaries / binaries_t of the reference.
+__global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ C, float* __restrict__ T, int d, int m) {
+  constexpr int CH = 64;
+  __shared__ float cs[32][CH + 1];
+  __shared__ float bs[32][CH];
+  const int j = blockIdx.z / m, k = blockIdx.z % m;
+  if (j == k) return;
+  const int c0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+  const int c = threadIdx.x & 31, bg = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int base = 0; base < d; base += CH) {
+    const int chunk = min(CH, d - base);
+    for (int i = threadIdx.x; i < 32 * CH; i += 256) {
+      int r = i / CH, t = i % CH;
+      if (t < chunk) {
+        cs[r][t] = C[((size_t)j * kH + c0 + r) * d + base + t];
+        bs[r][t] = C[((size_t)k * kH + b0 + r) * d + base + t];
+      }
+    }
+    __syncthreads();
+    for (int t = 0; t < chunk; t++) {
+      float cv = cs[c][t];
+#pragma unroll
+      for (int i = 0; i < 4; i++) acc[i] = fmaf(cv, bs[bg + 8 * i][t], acc[i]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int b = b0 + bg + 8 * i;
+    T[(((size_t)j * m + k) * kH + b) * kH + c0 + c] = 2.0f * acc[i];
+  }
+}
+
+// ---- helpers for codes held in two 64-bit registers (m <= 16) -------------------------------------------
+struct Code {
+  uint64_t lo, hi;
+  __device__ __forceinline__ uint32_t get(int k) const {
+    return (uint32_t)((k < 8 ? lo >> (8 * k) : hi >> (8 * (k - 8))) & 0xFFu);
+  }
+  __device__ __forceinline__ void set(int k, uint32_t v) {
+    if (k < 8) lo = (lo & ~(0xFFull << (8 * k))) | ((uint64_t)v << (8 * k));
+    else hi = (hi & ~(0xFFull << (8 * (k - 8)))) | ((uint64_t)v << (8 * (k - 8)));
+  }
+};
+
+template <int M>
+__device__ __forceinline__ Code load_code(const uint8_t* b) {
+  Code c{0, 0};
+#pragma unroll
+  for (int k = 0; k < M; k++) c.set(k, b[k]);
+  return c;
+}
+
+// perturb_codes! (src/LSQ.jl:5-39, with replacement); identical draws to the oracle (DESIGN.md "RNG").
+template <int M>
+__device__ __forceinline__ void perturb(Code& c, int npert, uint64_t seed, int it, uint64_t g) {
+  for (int jb = 0; jb * 4 < npert; jb++) {
+    uint32_t pw[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)it, (uint32_t)jb};
+    uint32_t vw[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)it, 0x80000000u | (uint32_t)jb};
+    philox4x32_10(pw, (uint32_t)seed, (uint32_t)(seed >> 32));
+    philox4x32_10(vw, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+      if (jb * 4 + t < npert) c.set((int)mulhi32(pw[t], (uint32_t)M), mulhi32(vw[t], (uint32_t)kH));
+  }
+}
+
+// veccost for one vector, cooperatively by one warp; result uniform across the warp.
+// cb = ((0 + C_0[t,b_0]) + C_1[t,b_1]) + ... ; cost = sequential sum over t of (cb - x[t])^2, unfused.
+template <int M>
+__device__ __forceinline__ float warp_cost(const float* __restrict__ x, const float* __restrict__ C, const Code& code,
+                                           int d, float* sq, int lane) {
+  for (int t = lane; t < d; t += 32) {
+    float cb = 0.f;
+#pragma unroll
+    for (int k = 0; k < M; k++) cb = __fadd_rn(cb, __ldg(C + ((size_t)k * kH + code.get(k)) * d + t));
+    float df = __fsub_rn(cb, __ldg(x + t));
+    sq[t] = __fmul_rn(df, df);
+  }
+  __syncwarp();
+  float acc = 0.f;
+  for (int t = 0; t < d; t++) acc = __fadd_rn(acc, sq[t]);
+  __syncwarp();
+  return acc;
+}
+
+struct IcmParams {
+  const float* U;       // [nc][m][256]  unaries of this chunk
+  const float* T;       // [m][m][256][256]
+  const float* X;       // [nc][d]
+  const float* C;       // [m*256][d]
+  uint8_t* B;           // [nc][m] in/out
+  float* cost;          // [nc] or null
+  const int* orders;    // [ilsiter][m]
+  const int* snap_iters;  // [n_snap] (1-based ILS iteration counts)
+  uint8_t* B_snap;      // [n_snap][n_total][m], already offset to this chunk's first vector
+  int* stats;           // [ilsiter][2] (#equal, #better)
+  int64_t nc, n_total, g0;
+  uint64_t seed;
+  int d, ilsiter, icmiter, npert, n_snap;
+};
+
+// ---- K3: one warp per vector, all ILS iterations of that vector back to back ----------------------------
+// Lane owns candidates c = r*128 + lane*4 + e (r<2, e<4): every 1 KB row (unary or pairwise) is two
+// coalesced 512 B float4 loads per warp.  Unaries are re-read per step but a vector's 8 KB stay L2-resident
+// for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
+template <int M>
+__global__ void __launch_bounds__(256) icm_warp_kernel(IcmParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.d;
+  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * p.d);
+  for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
+  __syncthreads();
+
+  const int64_t wstride = (int64_t)gridDim.x * nwarps;
+  for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < p.nc; l += wstride) {
+    const float* x = p.X + (size_t)l * p.d;
+    Code cur = load_code<M>(p.B + (size_t)l * M);
+    float curcost = warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
+    const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
+
+    for (int it = 0; it < p.ilsiter; it++) {
+      Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
+      perturb<M>(nb, p.npert, p.seed, it, (uint64_t)(p.g0 + l));  // src/LSQ.jl:225
+      const int* order = p.orders + it * M;
+      for (int sweep = 0; sweep < p.icmiter; sweep++) {
+        for (int s = 0; s < M; s++) {
+          const int j = __ldg(order + s);
+          float4 a0 = __ldg(Ul + j * 64 + lane);
+          float4 a1 = __ldg(Ul + j * 64 + 32 + lane);
+#pragma unroll
+          for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j, encode_icm.cpp:28-45
+            const int k = kk + (kk >= j);
+            const float4* row =
+                reinterpret_cast<const float4*>(p.T + (((size_t)j * M + k) * kH + nb.get(k)) * kH);
+            float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
+            a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
+            a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
+            a1.x = __fadd_rn(a1.x, r1.x); a1.y = __fadd_rn(a1.y, r1.y);
+            a1.z = __fadd_rn(a1.z, r1.z); a1.w = __fadd_rn(a1.w, r1.w);
+          }
+          // first-minimum argmin (encode_icm.cpp:47-58): ascending c inside the lane, then a
+          // (value, index)-lexicographic butterfly across lanes
+          float bv = a0.x;
+          int bc = lane * 4;
+          if (a0.y < bv) { bv = a0.y; bc = lane * 4 + 1; }
+          if (a0.z < bv) { bv = a0.z; bc = lane * 4 + 2; }
+          if (a0.w < bv) { bv = a0.w; bc = lane * 4 + 3; }
+          if (a1.x < bv) { bv = a1.x; bc = 128 + lane * 4; }
+          if (a1.y < bv) { bv = a1.y; bc = 128 + lane * 4 + 1; }
+          if (a1.z < bv) { bv = a1.z; bc = 128 + lane * 4 + 2; }
+          if (a1.w < bv) { bv = a1.w; bc = 128 + lane * 4 + 3; }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+          }
+          nb.set(j, (uint32_t)bc);
+        }
+      }
+      const float newcost = warp_cost<M>(x, p.C, nb, p.d, sq, lane);  // src/LSQ.jl:237
+      if (lane == 0) {
+        if (newcost == curcost) atomicAdd(&stats_s[2 * it], 1);
+        if (newcost < curcost) atomicAdd(&stats_s[2 * it + 1], 1);
+      }
+      if (newcost < curcost) {                                   // strict <, src/LSQ.jl:242-247
+        cur = nb;
+        curcost = newcost;
+      }
+      for (int sidx = 0; sidx < p.n_snap; sidx++)                // ilsiters snapshots, src/LSQ_GPU.jl:193-204
+        if (__ldg(p.snap_iters + sidx) == it + 1 && lane < M)
+          p.B_snap[((size_t)sidx * p.n_total + l) * M + lane] = (uint8_t)cur.get(lane);
+    }
+    if (lane < M) p.B[(size_t)l * M + lane] = (uint8_t)cur.get(lane);
+    if (p.cost && lane == 0) p.cost[l] = curcost;
+  }
+  __syncthreads();
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x)
+      if (stats_s[i]) atomicAdd(p.stats + i, stats_s[i]);
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) veccost_kernel(const float* __restrict__ X, const uint8_t* __restrict__ B,
+                                                      const float* __restrict__ C, int64_t n, int d,
+                                                      float* __restrict__ cost) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * d;
+  for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < n; l += (int64_t)gridDim.x * nwarps) {
+    Code c = load_code<M>(B + (size_t)l * M);
+    float v = warp_cost<M>(X + (size_t)l * d, C, c, d, sq, lane);
+    if (lane == 0) cost[l] = v;
+  }
+}
+
+// deterministic two-stage sum in double (qerror = mean(veccost), src/qerrors.jl:69-74)
+__global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ v, int64_t n, double* __restrict__ partial) {
+  __shared__ double sh[256];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t b = (int64_t)blockIdx.x * per, e = min(n, b + per);
+  double s = 0;
+  for (int64_t i = b + threadIdx.x; i < e; i += 256) s += (double)v[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// compat: one conditioning step with the reference's own argument layout (deps/src/encode_icm.cpp:3-61)
+__global__ void __launch_bounds__(256) condition_kernel(uint8_t* __restrict__ B, float* __restrict__ ub,
+                                                        const float* __restrict__ binaries,
+                                                        const float* __restrict__ binaries_t,
+                                                        const int* __restrict__ pair2idx,
+                                                        const int* __restrict__ to_condition, int j, int n, int m) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t l = w; l < n; l += nw) {
+    float4* u4 = reinterpret_cast<float4*>(ub + (size_t)l * kH);
+    float4 a0 = u4[lane], a1 = u4[32 + lane];
+    for (int kidx = 0; kidx < m - 1; kidx++) {
+      const int k = to_condition[kidx];
+      const int bidx = pair2idx[j * m + k];
+      const float* bb = (j < k ? binaries : binaries_t) + (size_t)kH * kH * bidx;
+      const float4* row = reinterpret_cast<const float4*>(bb + (size_t)B[(size_t)l * m + k] * kH);
+      float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
+      a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
+      a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
+      a1.x = __fadd_rn(a1.x, r1.x); a1.y = __fadd_rn(a1.y, r1.y);
+      a1.z = __fadd_rn(a1.z, r1.z); a1.w = __fadd_rn(a1.w, r1.w);
+    }
+    u4[lane] = a0;
+    u4[32 + lane] = a1;
+    float bv = a0.x;
+    int bc = lane * 4;
+    if (a0.y < bv) { bv = a0.y; bc = lane * 4 + 1; }
+    if (a0.z < bv) { bv = a0.z; bc = lane * 4 + 2; }
+    if (a0.w < bv) { bv = a0.w; bc = lane * 4 + 3; }
+    if (a1.x < bv) { bv = a1.x; bc = 128 + lane * 4; }
+    if (a1.y < bv) { bv = a1.y; bc = 128 + lane * 4 + 1; }
+    if (a1.z < bv) { bv = a1.z; bc = 128 + lane * 4 + 2; }
+    if (a1.w < bv) { bv = a1.w; bc = 128 + lane * 4 + 3; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+      if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+    }
+    __syncwarp();
+    if (lane == 0) B[(size_t)l * m + j] = (uint8_t)bc;
+    __syncwarp();
+  }
+}
+
+}  // namespace ryl
+
+// ======================================================================================================
+// host side
+// ======================================================================================================
+using namespace ryl;
+
+template <int M>
+static int launch_icm(const IcmParams& p, cudaStream_t s) {
+  const int warps = 8;
+  size_t smem = (size_t)warps * p.d * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
+  RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
+  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t need = (p.nc + warps - 1) / warps;
+  int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);
+  RYL_LAUNCH(icm_warp_kernel<M>, grid, warps * 32, smem, s, p);
+  return RAYUELA_OK;
+}
+
+template <int M>
+static int launch_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, float* cost,
+                          cudaStream_t s) {
+  const int warps = 8;
+  size_t smem = (size_t)warps * d * sizeof(float);
+  RYL_ARG(smem <= 200 * 1024, "veccost: d too large for shared memory");
+  RYL_CUDA(cudaFuncSetAttribute(veccost_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)std::min<int64_t>((n + warps - 1) / warps, (int64_t)sm_count() * 8);
+  RYL_LAUNCH(veccost_kernel<M>, grid, warps * 32, smem, s, X, B, C, n, d, cost);
+  return RAYUELA_OK;
+}
+
+#define RYL_M_SWITCH(m, CALL)                                                                     \
+  switch (m) {                                                                                    \
+    case 1: CALL(1); break;  case 2: CALL(2); break;  case 3: CALL(3); break;  case 4: CALL(4); break;    \
+    case 5: CALL(5); break;  case 6: CALL(6); break;  case 7: CALL(7); break;  case 8: CALL(8); break;    \
+    case 9: CALL(9); break;  case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break; \
+    case 13: CALL(13); break; case 14: CALL(14); break; case 15: CALL(15); break; case 16: CALL(16); break; \
+    default: return fail(RAYUELA_ERR_ARG, "m must be in 1..16");                                  \
+  }
+
+static int device_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, float* cost,
+                          cudaStream_t s) {
+  int rc = RAYUELA_OK;
+#define CALL(M) rc = launch_veccost<M>(X, B, C, n, d, cost, s)
+  RYL_M_SWITCH(m, CALL)
+#undef CALL
+  return rc;
+}
+
+// mean of a device float array, deterministic; synchronises the stream
+static int device_mean(const float* v, int64_t n, double* out, cudaStream_t s) {
+  const int blocks = 256;
+  DevBuf part;
+  RYL_TRY(part.alloc(blocks * sizeof(double), s));
+  RYL_LAUNCH(sum_kernel, blocks, 256, 0, s, v, n, part.as<double>());
+  double h[blocks];
+  RYL_CUDA(cudaMemcpyAsync(h, part.p, sizeof h, cudaMemcpyDeviceToHost, s));
+  RYL_CUDA(cudaStreamSynchronize(s));
+  double t = 0;
+  for (int i = 0; i < blocks; i++) t += h[i];
+  *out = t / (double)n;
+  return RAYUELA_OK;
+}
+
+static size_t unary_budget_bytes() {
+  const char* e = getenv("RAYUELA_B200_UNARY_BYTES");
+  if (e && *e) return (size_t)strtoull(e, nullptr, 10);
+  return (size_t)16 << 30;
+}
+
+extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
+                                  int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
+                                  const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap,
+                                  float* objs, float* cost_out, int* stats, unsigned flags, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  RYL_ARG(h == kH, "encode_icm: only codebooks with 256 entries are supported (src/LSQ.jl:173-175)");
+  RYL_ARG(m >= 1 && m <= 16, "encode_icm: m must be in 1..16");
+  RYL_ARG(n >= 0 && d >= 1, "encode_icm: bad n or d");
+  RYL_ARG(ilsiter >= 0 && icmiter >= 0 && npert >= 0, "encode_icm: negative iteration count");
+  RYL_ARG(n_snap >= 0 && (n_snap == 0 || snap_iters), "encode_icm: snap_iters missing");
+  RYL_ARG(X && C && B, "encode_icm: null array");
+  if (n == 0) return RAYUELA_OK;
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  const int mh = m * kH;
+
+  InArg<float> x_in, c_in;
+  RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)mh * d, dev, s));
+  OutArg<uint8_t> b_io, snap_out;
+  RYL_TRY(b_io.bind(B, (size_t)n * m, dev, s, /*copy_in=*/true));
+  RYL_TRY(snap_out.bind(n_snap ? B_snap : nullptr, (size_t)n_snap * n * m, dev, s));
+  DevBuf snap_tmp;  // objs wanted without B_snap: keep the snapshots on the device only
+  if (n_snap && !snap_out.d && objs) {
+    RYL_TRY(snap_tmp.alloc((size_t)n_snap * n * m, s));
+    snap_out.d = snap_tmp.as<uint8_t>();
+  }
+  OutArg<float> cost_o;
+  RYL_TRY(cost_o.bind(cost_out, (size_t)n, dev, s));
+
+  // visiting orders (src/LSQ.jl:210-221), snapshot list, stats
+  std::vector<int> ord((size_t)std::max(ilsiter, 1) * m);
+  for (int it = 0; it < ilsiter; it++) {
+    if (orders) memcpy(&ord[(size_t)it * m], orders + (size_t)it * m, sizeof(int) * m);
+    else if (randord) philox_randperm(seed, it, m, &ord[(size_t)it * m]);
+    else for (int i = 0; i < m; i++) ord[(size_t)it * m + i] = i;
+    for (int i = 0; i < m; i++)
+      RYL_ARG(ord[(size_t)it * m + i] >= 0 && ord[(size_t)it * m + i] < m, "encode_icm: order entry out of range");
+  }
+  DevBuf ord_d, snapit_d, stats_d, nrm_d, T_d;
+  RYL_TRY(ord_d.alloc(ord.size() * sizeof(int), s));
+  RYL_CUDA(cudaMemcpyAsync(ord_d.p, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  RYL_TRY(snapit_d.alloc((size_t)std::max(n_snap, 1) * sizeof(int), s));
+  if (n_snap) RYL_CUDA(cudaMemcpyAsync(snapit_d.p, snap_iters, n_snap * sizeof(int), cudaMemcpyHostToDevice, s));
+  RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int), s));
+  RYL_CUDA(cudaMemsetAsync(stats_d.p, 0, stats_d.bytes, s));
+
+  // K0 + K2: ||c||^2 and the pairwise tables (get_binaries + binaries_t, src/LSQ.jl:288,180-183)
+  RYL_TRY(nrm_d.alloc((size_t)mh * sizeof(float), s));
+  RYL_LAUNCH(sqnorm_kernel, (mh + 255) / 256, 256, 0, s, c_in.d, d, mh, nrm_d.as<float>());
+  RYL_TRY(T_d.alloc((size_t)m * m * kH * kH * sizeof(float), s));
+  if (m > 1) RYL_LAUNCH(tables_kernel, dim3(kH / 32, kH / 32, m * m), 256, 0, s, c_in.d, T_d.as<float>(), d, m);
+
+  // chunk the base set so the unary buffer (m KB per vector) stays within budget (nsplits of
+  // src/LSQ_GPU.jl:226-255, done in space on one device instead of by the caller)
+  const int64_t per_vec = (int64_t)mh * sizeof(float);
+  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
+  DevBuf U_d;
+  RYL_TRY(U_d.alloc((size_t)std::min(chunk, n) * per_vec, s));
+  for (int64_t l0 = 0; l0 < n; l0 += chunk) {
+    const int64_t nc = std::min(chunk, n - l0);
+    dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
+    if (d % 4 == 0)
+      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
+                 U_d.as<float>(), nc, d, mh);
+    else
+      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
+                 U_d.as<float>(), nc, d, mh);
+    IcmParams p;
+    p.U = U_d.as<float>();
+    p.T = T_d.as<float>();
+    p.X = x_in.d + (size_t)l0 * d;
+    p.C = c_in.d;
+    p.B = b_io.d + (size_t)l0 * m;
+    p.cost = cost_o.d ? cost_o.d + l0 : nullptr;
+    p.orders = ord_d.as<int>();
+    p.snap_iters = snapit_d.as<int>();
+    p.B_snap = snap_out.d ? snap_out.d + (size_t)l0 * m : nullptr;
+    p.stats = stats_d.as<int>();
+    p.nc = nc;
+    p.n_total = n;
+    p.g0 = g0 + l0;
+    p.seed = seed;
+    p.d = d;
+    p.ilsiter = ilsiter;
+    p.icmiter = icmiter;
+    p.npert = npert;
+    p.n_snap = snap_out.d ? n_snap : 0;
+    int rc = RAYUELA_OK;
+#define CALL(M) rc = launch_icm<M>(p, s)
+    RYL_M_SWITCH(m, CALL)
+#undef CALL
+    RYL_TRY(rc);
+  }
+
+  // objective at each snapshot: qerror(RX, B, C), src/LSQ_GPU.jl:197
+  if (n_snap && objs && snap_out.d) {
+    DevBuf tmp;
+    RYL_TRY(tmp.alloc((size_t)n * sizeof(float), s));
+    for (int si = 0; si < n_snap; si++) {
+      RYL_TRY(device_veccost(x_in.d, snap_out.d + (size_t)si * n * m, c_in.d, n, d, m, tmp.as<float>(), s));
+      double mean = 0;
+      RYL_TRY(device_mean(tmp.as<float>(), n, &mean, s));
+      objs[si] = (float)mean;
+    }
+  }
+  RYL_TRY(b_io.flush(s));
+  RYL_TRY(snap_out.flush(s));
+  RYL_TRY(cost_o.flush(s));
+  if (stats) {
+    RYL_CUDA(cudaMemcpyAsync(stats, stats_d.p, (size_t)ilsiter * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaStreamSynchronize(s));
+  }
+  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  return RAYUELA_OK;
+}
+
+extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,
+                               float* cost, double* mean_out, unsigned flags, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  RYL_ARG(h == kH && m >= 1 && m <= 16 && n >= 1 && d >= 1, "veccost: bad shape (h must be 256, m in 1..16)");
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  InArg<float> x_in, c_in;
+  InArg<uint8_t> b_in;
+  RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)m * kH * d, dev, s));
+  RYL_TRY(b_in.bind(B, (size_t)n * m, dev, s));
+  OutArg<float> cost_o;
+  DevBuf tmp;
+  float* cd = nullptr;
+  if (cost) {
+    RYL_TRY(cost_o.bind(cost, (size_t)n, dev, s));
+    cd = cost_o.d;
+  } else {
+    RYL_TRY(tmp.alloc((size_t)n * sizeof(float), s));
+    cd = tmp.as<float>();
+  }
+  RYL_TRY(device_veccost(x_in.d, b_in.d, c_in.d, n, d, m, cd, s));
+  if (mean_out) RYL_TRY(device_mean(cd, n, mean_out, s));
+  RYL_TRY(cost_o.flush(s));
+  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  return RAYUELA_OK;
+}
+
+extern "C" void condition(unsigned char* B, float* ub, float* binaries, float* binaries_t, int* cbpair2binaryidx,
+                          int* to_condition, int j, int n, int m) {
+  auto body = [&]() -> int {
+    cudaStream_t s = nullptr;
+    RYL_ARG(m >= 2 && n >= 1 && j >= 0 && j < m, "condition: bad shape");
+    const size_t ncbi = (size_t)m * (m - 1) / 2;
+    InArg<float> bin, bin_t;
+    InArg<int> p2i, tc;
+    OutArg<uint8_t> b_io;
+    OutArg<float> ub_io;
+    RYL_TRY(bin.bind(binaries, ncbi * kH * kH, false, s));
+    RYL_TRY(bin_t.bind(binaries_t, ncbi * kH * kH, false, s));
+    RYL_TRY(p2i.bind(cbpair2binaryidx, (size_t)m * m, false, s));
+    RYL_TRY(tc.bind(to_condition, (size_t)m - 1, false, s));
+    RYL_TRY(b_io.bind(B, (size_t)n * m, false, s, true));
+    RYL_TRY(ub_io.bind(ub, (size_t)n * kH, false, s, true));
+    int grid = (int)std::min<int64_t>(((int64_t)n + 7) / 8, (int64_t)sm_count() * 8);
+    RYL_LAUNCH(condition_kernel, grid, 256, 0, s, b_io.d, ub_io.d, bin.d, bin_t.d, p2i.d, tc.d, j, n, m);
+    RYL_TRY(b_io.flush(s));
+    RYL_TRY(ub_io.flush(s));
+    RYL_CUDA(cudaStreamSynchronize(s));
+    return RAYUELA_OK;
+  };
+  int rc = body();
+  if (rc != RAYUELA_OK) {
+    fprintf(stderr, "librayuela_b200: condition failed (%d): %s\n", rc, rayuela_last_error());
+    abort();
+  }
+}

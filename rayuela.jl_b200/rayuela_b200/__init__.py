@@ -1,0 +1,13 @@
+"""rayuela_b200 -- B200 (sm_100a) implementation of Rayuela.jl's ICM/ILS encoding and ADC linear scan.
+
+    rayuela_b200.core       memory-image API over librayuela_b200.so (numpy host arrays or torch CUDA tensors)
+    rayuela_b200.julia_api  mirror of the Julia package's function names / shapes / index bases
+    rayuela_b200.dist       one-process-per-GPU sharding (torch.distributed) of both paths
+
+No CPU fallback exists: importing is cheap, but every call needs the built library and a CUDA device.
+"""
+from . import core, julia_api  # noqa: F401
+from ._lib import LIB_PATH, RayuelaError, launch_count  # noqa: F401
+from .julia_api import (SR_C_perturb, SR_D_perturb, apply_schedule, encode_icm_cuda, encoding_icm,  # noqa: F401
+                        eval_recall, linscan_cq, linscan_lsq, linscan_opq, linscan_pq, qerror, qerror_opq,
+                        qerror_pq, quantize_opq, quantize_pq, seed_b200, veccost)

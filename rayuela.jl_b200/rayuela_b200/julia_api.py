@@ -1,0 +1,243 @@
+"""Host-side mirror of Rayuela.jl's API for the two hot paths: same function names, positional arguments,
+shapes and index bases as the Julia package, so scripts written against the reference (e.g.
+demos/demos_train_query_base.jl) translate line by line and the parity tests read like its own would.
+
+Julia conventions kept at this level:
+    X   d-by-n Float32        C  list of m d-by-h Float32 matrices       R  d-by-d Float32
+    B   m-by-n Int16, ONE-based codes                 results k-by-nq, ids ONE-based
+A Julia column-major d-by-n array and a numpy C-order (n, d) array are the same bytes, so passing
+`np.asfortranarray(X)` (or a transposed C-order array) costs no copy.  (Julia is not installed in this image;
+julia/RayuelaB200.jl holds the equivalent ccall shim.)
+"""
+import numpy as np
+
+from . import core
+from .core import H, SCAN_CQ, SCAN_LSQ, SCAN_PQ, RayuelaError
+
+_state = {"seed": 0}
+
+
+def seed_b200(seed):
+    """Reproducible stream for the ILS perturbations / visiting orders (the reference draws from Julia's
+    global MersenneTwister; here every encode call consumes one seed from this counter)."""
+    _state["seed"] = int(seed)
+
+
+def _next_seed():
+    s = _state["seed"]
+    _state["seed"] = (s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    return s
+
+
+def _img(A):
+    """Julia d-by-n matrix -> its memory image as a C-order (n, d) float32 array (no copy when possible)."""
+    return np.ascontiguousarray(np.asarray(A, dtype=np.float32).T)
+
+
+def _hcat(C):
+    """hcat(C...) of m d-by-h codebooks -> memory image (m*h, d)."""
+    return np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32).T for c in C], axis=0))
+
+
+def _codes0(B):
+    """m-by-n one-based Int16 -> (n, m) uint8 zero-based (convert(Matrix{UInt8}, B .- 1), src/LSQ.jl:228)."""
+    B = np.asarray(B)
+    if B.min() < 1 or B.max() > H:
+        raise RayuelaError("codes must be in 1..256")
+    return np.ascontiguousarray((B.T - 1).astype(np.uint8))
+
+
+def _codes1(B0):
+    return np.asfortranarray(B0.T.astype(np.int16) + 1)
+
+
+# ---- path (1) -----------------------------------------------------------------------------------------
+def encoding_icm(X, oldB, C, ilsiter, icmiter, randord, npert, cpp=True, V=False):
+    """encoding_icm(X, oldB, C, ilsiter, icmiter, randord, npert, cpp=true, V=true) -> B   (src/LSQ.jl:272-294)
+    oldB is updated in place like the reference does (src/LSQ.jl:248)."""
+    d, n = np.shape(X)
+    m = len(C)
+    h = np.shape(C[0])[1]
+    if h != H:
+        raise RayuelaError("The B200 implementation of ICM encoding only supports codebooks with 256 entries")
+    r = core.encode_icm(_img(X), _hcat(C), _codes0(oldB), ilsiter, icmiter, npert, randord, seed=_next_seed(),
+                        want_stats=V, inplace=True)
+    if V:
+        for it, (neq, nbet) in enumerate(r["stats"]):
+            print(" ILS iteration %d/%d done. %5.2f%% new codes are equal. %5.2f%% new codes are better."
+                  % (it + 1, ilsiter, 100.0 * neq / n, 100.0 * nbet / n))
+    B = _codes1(r["B"])
+    if isinstance(oldB, np.ndarray) and oldB.shape == B.shape:
+        oldB[...] = B
+    return B
+
+
+def encode_icm_cuda(RX, B, C, ilsiters, icmiter, npert, randord, nsplits=2, V=False):
+    """encode_icm_cuda(RX, B, C, ilsiters, icmiter, npert, randord, nsplits=2, V=false) -> Bs, objs
+    (src/LSQ_GPU.jl:218-264).  `nsplits` is accepted and ignored: the library tiles the base set itself."""
+    d, n = np.shape(RX)
+    ilsiters = [int(i) for i in ilsiters]
+    r = core.encode_icm(_img(RX), _hcat(C), _codes0(B), max(ilsiters), icmiter, npert, randord, seed=_next_seed(),
+                        snap_iters=ilsiters, want_stats=V, inplace=True)
+    if V:
+        for it, (neq, nbet) in enumerate(r["stats"]):
+            print(" ILS iteration %d/%d done. %5.2f%% new codes are equal. %5.2f%% new codes are better."
+                  % (it + 1, max(ilsiters), 100.0 * neq / n, 100.0 * nbet / n))
+    return [_codes1(b) for b in r["B_snap"]], r["objs"].copy()
+
+
+def veccost(X, B, C):
+    """veccost(X, B, C) (src/qerrors.jl:36-66)."""
+    return core.veccost(_img(X), _codes0(B), _hcat(C))
+
+
+def qerror(X, B, C):
+    """qerror(X, B, C) = mean(veccost(X, B, C)) (src/qerrors.jl:69-74)."""
+    return np.float32(core.qerror(_img(X), _codes0(B), _hcat(C)))
+
+
+def _pq_as_full(C, d):
+    """PQ codebooks (m blocks of sub-by-h) embedded as d-by-h additive codebooks (zeros off-block)."""
+    m = len(C)
+    out, at = [], 0
+    for c in C:
+        c = np.asarray(c, dtype=np.float32)
+        f = np.zeros((d, c.shape[1]), dtype=np.float32)
+        f[at:at + c.shape[0]] = c
+        at += c.shape[0]
+        out.append(f)
+    return out
+
+
+def qerror_opq(X, B, C, R):
+    """qerror_opq(X, B, C, R) = mean ||R*CB - X||^2 (src/qerrors.jl:77-90) = qerror of R'X against the
+    block codebooks (R orthogonal)."""
+    X = np.asarray(X, dtype=np.float32)
+    RX = np.asarray(R, dtype=np.float32).T @ X
+    return qerror(RX, B, _pq_as_full(C, X.shape[0]))
+
+
+def qerror_pq(X, B, C):
+    """qerror_pq(X, B, C) (src/qerrors.jl:93-100)."""
+    return qerror(X, B, _pq_as_full(C, np.shape(X)[0]))
+
+
+# ---- PQ / OPQ encode ------------------------------------------------------------------------------------
+def _cat3(C):
+    """cat(C..., dims=3) of m sub-by-h matrices -> memory image (m*h, sub)."""
+    return np.ascontiguousarray(np.concatenate([np.asarray(c, dtype=np.float32).T for c in C], axis=0))
+
+
+def quantize_pq(X, C, V=False):
+    """quantize_pq(X, C, V=false) -> B (m-by-n Int16, one-based)   (src/PQ.jl:18-48)."""
+    d, n = np.shape(X)
+    m = len(C)
+    if any(np.shape(c) != (d // m, H) for c in C) or d % m:
+        raise RayuelaError("quantize_pq needs m codebooks of size (d/m)-by-256")
+    return _codes1(core.quantize_pq(_img(X), _cat3(C), m))
+
+
+def quantize_opq(X, R, C, V=False):
+    """quantize_opq(X, R, C, V=false) = quantize_pq(R'X, C)   (src/OPQ.jl:19-27)."""
+    RX = np.asarray(R, dtype=np.float32).T @ np.asarray(X, dtype=np.float32)
+    return quantize_pq(RX, C, V)
+
+
+# ---- path (2) -----------------------------------------------------------------------------------------
+def _scan_codes(B):
+    B = np.asarray(B)
+    if B.dtype == np.uint8:      # the UInt8 methods take zero-based codes (src/Linscan.jl:5,93,118,160)
+        return np.ascontiguousarray(B.T)
+    return _codes0(B)            # the Integer methods subtract one (src/Linscan.jl:35,113,155,191)
+
+
+def _out(dists, idx):
+    return np.asfortranarray(dists.T), np.asfortranarray(idx.T.astype(np.uint32))
+
+
+def linscan_pq(B, X, C, b, k=10000):
+    """linscan_pq(B, X, C, b, k) -> dists, res (k-by-nq; res one-based)   (src/Linscan.jl:5-37)."""
+    codes = _scan_codes(B)
+    m = codes.shape[1]
+    if b != 8 * m:
+        raise RayuelaError("b must be log2(h)*m = 8*m")
+    ix = core.Index(SCAN_PQ, codes)
+    dists, idx = ix.search(_img(X), _cat3(C), k)
+    ix.free()
+    return _out(dists, idx + 1)          # res .+= 1, src/Linscan.jl:25
+
+
+def linscan_opq(B, X, C, b, R, k=10000):
+    """linscan_opq(B, X, C, b, R, k) = linscan_pq(B, R'X, C, b, k)   (src/Linscan.jl:93-115)."""
+    RX = np.asarray(R, dtype=np.float32).T @ np.asarray(X, dtype=np.float32)
+    return linscan_pq(B, RX, C, b, k)
+
+
+def linscan_lsq(B, X, C, dbnorms, R, k=10000):
+    """linscan_lsq(B, X, C, dbnorms, R, k) -> dists, res (one-based)   (src/Linscan.jl:118-157)."""
+    RX = np.asarray(R, dtype=np.float32).T @ np.asarray(X, dtype=np.float32)
+    ix = core.Index(SCAN_LSQ, _scan_codes(B), np.asarray(dbnorms, dtype=np.float32).reshape(-1))
+    dists, idx = ix.search(_img(RX), _hcat(C), k)
+    ix.free()
+    return _out(dists, idx)
+
+
+def linscan_cq(B, X, C, k=10000):
+    """linscan_cq(B, X, C, k) -> dists, res (one-based)   (src/Linscan.jl:160-193)."""
+    ix = core.Index(SCAN_CQ, _scan_codes(B))
+    dists, idx = ix.search(_img(X), _hcat(C), k)
+    ix.free()
+    return _out(dists, idx)
+
+
+def eval_recall(ids_gnd, ids_predicted, k, V=True):
+    """eval_recall(ids_gnd, ids_predicted, k) -> recall_at_i (k-vector)   (src/Linscan.jl:196-234).
+    A query counts as found at rank r only if the true id appears exactly once in its list (:208-214)."""
+    gt = np.asarray(ids_gnd).reshape(-1)
+    P = np.asarray(ids_predicted)
+    nq = P.shape[1]
+    assert nq == gt.size
+    hit = P[:k, :] == gt[None, :]
+    cnt = hit.sum(0)
+    ranks = np.where(cnt == 1, hit.argmax(0) + 1, k + 1)
+    recall = np.array([(ranks <= i).sum() / nq for i in range(1, k + 1)])
+    if V:
+        for i in (1, 2, 5, 10, 20, 50, 100, 200, 500, 1000, 2000, 5000, 10000):
+            if i <= k:
+                print("r@%d = %s" % (i, recall[i - 1] * 100))
+    return recall
+
+
+# ---- LSQ++ stochastic relaxations (host side, between encodes; src/SR_perturbations.jl) -------------------
+def apply_schedule(stdev, it, niter, schedule=1, p=0.5):
+    """apply_schedule (src/SR_perturbations.jl:4-24)."""
+    stdev = np.asarray(stdev, dtype=np.float64)
+    if schedule == 1:
+        return stdev * (1 - it / niter) ** p
+    if schedule == 2:
+        return stdev / ((1 + it) ** p)
+    if schedule == 3:
+        return stdev * p ** (it / 2)
+    raise RayuelaError("Schedule unknown: %s" % schedule)
+
+
+def SR_D_perturb(C, it, niter, schedule=1, p=0.5, rng=None):
+    """SR_D_perturb (src/SR_perturbations.jl:27-49): C[i][j,:] += randn(h) * std_j / m, scheduled."""
+    rng = rng or np.random.default_rng(_next_seed() & 0xFFFFFFFF)
+    m = len(C)
+    allc = np.concatenate([np.asarray(c, dtype=np.float32) for c in C], axis=1)
+    stdc = apply_schedule(allc.std(axis=1, ddof=1) / m, it, niter, schedule, p)   # Statistics.std is corrected
+    out = []
+    for c in C:
+        c = np.asarray(c, dtype=np.float32)
+        noise = rng.standard_normal(c.shape) * stdc[:, None]
+        out.append((c + noise).astype(np.float32))
+    return out
+
+
+def SR_C_perturb(X, it, niter, schedule=1, p=0.5, rng=None):
+    """SR_C_perturb (src/SR_perturbations.jl:52-73): X[i,:] += randn(n) * std_i, scheduled."""
+    rng = rng or np.random.default_rng(_next_seed() & 0xFFFFFFFF)
+    X = np.asarray(X, dtype=np.float32)
+    stdx = apply_schedule(X.std(axis=1, ddof=1), it, niter, schedule, p)
+    return (X + rng.standard_normal(X.shape) * stdx[:, None]).astype(np.float32)

@@ -1,0 +1,304 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle, the reference's own compiled C++
+(oracle/_ref, when it travelled with the snapshot) and the committed golden vectors.
+Bar: codes / ids bit-exact; fp32 distances and costs bit-exact here (the north_star tolerance is 1e-4
+relative, stated where a mean is compared)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gold(name):
+    return dict(np.load(os.path.join(GOLD, name + ".npz")))
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import rayuela_b200
+    return rayuela_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _icm_data(n, d, m, seed, kind="gauss"):
+    r = np.random.default_rng(seed)
+    if kind == "uniform":
+        X = (r.random((n, d)) * 10).astype(np.float32)
+        C = r.random((m * 256, d)).astype(np.float32)
+    else:
+        X = r.standard_normal((n, d)).astype(np.float32)
+        C = (r.standard_normal((m * 256, d)) / np.sqrt(m)).astype(np.float32)
+    return X, C, r.integers(0, 256, (n, m), dtype=np.uint8)
+
+
+# ---- path (1) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["icm_m8_gauss", "icm_m7_uniform", "icm_m16_gauss"])
+def test_icm_golden(rb, name):
+    g = gold(name)
+    r = rb.core.encode_icm(g["X"], g["C"], g["B"], int(g["ilsiter"]), int(g["icmiter"]), int(g["npert"]),
+                           bool(g["randord"]), seed=int(g["seed"]), g0=int(g["g0"]), snap_iters=g["snap_iters"],
+                           want_cost=True, want_stats=True)
+    assert np.array_equal(r["B"], g["B_out"])
+    assert np.array_equal(bits(r["cost"]), bits(g["cost"]))
+    assert np.array_equal(r["stats"], g["stats"])
+    assert np.array_equal(r["B_snap"], g["B_snap"])
+    assert np.allclose(r["objs"], g["objs"], rtol=1e-4)      # qerror: 1e-4 relative (north_star)
+
+
+@pytest.mark.parametrize("n,d,m,ils,icm,npert,randord,kind", [
+    (5000, 128, 8, 4, 4, 4, True, "gauss"),        # BASELINE config-3 shape, reduced n
+    (3001, 128, 7, 2, 4, 4, True, "gauss"),        # demo shape: 7 codebooks + norm byte; ragged n
+    (1500, 96, 16, 2, 2, 4, False, "uniform"),     # config-4 codebook count, test/common.jl data
+    (777, 30, 3, 3, 3, 9, True, "gauss"),          # d % 4 != 0, npert > 4 (three Philox blocks)
+    (1, 8, 2, 1, 1, 1, False, "gauss"),            # single vector
+    (64, 16, 1, 2, 2, 2, True, "gauss"),           # m = 1: no pairwise terms at all
+])
+def test_icm_matches_oracle(rb, n, d, m, ils, icm, npert, randord, kind):
+    X, C, B = _icm_data(n, d, m, seed=n + m, kind=kind)
+    o = orc.encode_icm(X, C, B, ils, icm, npert, randord, seed=42, g0=123456789012)
+    r = rb.core.encode_icm(X, C, B, ils, icm, npert, randord, seed=42, g0=123456789012, want_cost=True,
+                           want_stats=True)
+    assert np.array_equal(r["B"], o["B"])
+    assert np.array_equal(bits(r["cost"]), bits(o["cost"]))
+    assert np.array_equal(r["stats"], o["stats"])
+
+
+def test_icm_zero_iterations_and_explicit_orders(rb):
+    X, C, B = _icm_data(500, 32, 8, seed=3)
+    r = rb.core.encode_icm(X, C, B, 0, 4, 4, True, want_cost=True)
+    assert np.array_equal(r["B"], B)
+    assert np.array_equal(bits(r["cost"]), bits(orc.veccost(X, B, C)))
+    orders = np.array([[7, 6, 5, 4, 3, 2, 1, 0], [0, 2, 4, 6, 1, 3, 5, 7]], dtype=np.int32)
+    o = orc.encode_icm(X, C, B, 2, 3, 4, True, seed=1, orders=orders)
+    r = rb.core.encode_icm(X, C, B, 2, 3, 4, True, seed=1, orders=orders)
+    assert np.array_equal(r["B"], o["B"])
+
+
+def test_icm_shard_invariance_and_chunking(rb, monkeypatch):
+    """Codes depend on the GLOBAL vector index only: encoding halves with g0 offsets == encoding the whole;
+    and a tiny unary budget (forces several chunks inside one call) changes nothing."""
+    X, C, B = _icm_data(4000, 64, 8, seed=9)
+    whole = rb.core.encode_icm(X, C, B, 3, 4, 4, True, seed=5)["B"]
+    a = rb.core.encode_icm(X[:1700], C, B[:1700], 3, 4, 4, True, seed=5, g0=0)["B"]
+    b = rb.core.encode_icm(X[1700:], C, B[1700:], 3, 4, 4, True, seed=5, g0=1700)["B"]
+    assert np.array_equal(np.concatenate([a, b]), whole)
+    monkeypatch.setenv("RAYUELA_B200_UNARY_BYTES", str(1100 * 8 * 1024))
+    assert np.array_equal(rb.core.encode_icm(X, C, B, 3, 4, 4, True, seed=5)["B"], whole)
+
+
+def test_icm_device_pointers(rb):
+    import torch
+    X, C, B = _icm_data(2000, 128, 8, seed=21)
+    o = orc.encode_icm(X, C, B, 2, 4, 4, True, seed=8)
+    Xd, Cd, Bd = (torch.from_numpy(a).cuda() for a in (X, C, B))
+    r = rb.core.encode_icm(Xd, Cd, Bd, 2, 4, 4, True, seed=8, want_cost=True)
+    assert np.array_equal(r["B"].cpu().numpy(), o["B"])
+    assert np.array_equal(bits(r["cost"].cpu().numpy()), bits(o["cost"]))
+    assert np.array_equal(Bd.cpu().numpy(), B)            # not in place unless asked
+
+
+def test_icm_improves_and_never_worsens(rb):
+    X, C, B = _icm_data(3000, 128, 8, seed=33)
+    c0 = rb.core.veccost(X, B, C)
+    r = rb.core.encode_icm(X, C, B, 4, 4, 4, True, seed=2, want_cost=True)
+    assert np.all(r["cost"] <= c0)
+    assert r["cost"].mean() < 0.7 * c0.mean()
+
+
+@pytest.mark.parametrize("m,d", [(8, 128), (7, 33), (16, 64)])
+def test_veccost_qerror(rb, m, d):
+    X, C, B = _icm_data(2500, d, m, seed=m)
+    cost, mean = rb.core.veccost(X, B, C, want_mean=True)
+    assert np.array_equal(bits(cost), bits(orc.veccost(X, B, C)))
+    assert abs(mean - orc.qerror(X, B, C)) <= 1e-6 * abs(mean)
+
+
+@pytest.mark.parametrize("m", [8, 5])
+def test_condition_compat_symbol(rb, m):
+    """The exact-signature `condition` against the oracle's step (itself pinned to the reference's)."""
+    n, d = 2000, 32
+    X, C, B = _icm_data(n, d, m, seed=50 + m)
+    U = orc.get_unaries(X, C, m)
+    bins, bins_t, cbi = orc.get_binaries(C, m)
+    p2i = np.zeros((m, m), dtype=np.int32)
+    for i, (a, b) in enumerate(cbi):
+        p2i[a, b] = p2i[b, a] = i
+    B1, B2 = B.copy(), B.copy()
+    for j in (2, 0, m - 1):
+        tc = np.array([k for k in range(m) if k != j], dtype=np.int32)
+        u1, u2 = U[j].copy(), U[j].copy()
+        orc.condition(B1, u1, bins, bins_t, p2i, tc, j, use_ref=orc.have_ref())
+        rb.core.c_condition(B2, u2, bins, bins_t, p2i, tc, j)
+        assert np.array_equal(B1, B2)
+        assert np.array_equal(bits(u1), bits(u2))
+
+
+# ---- path (2) ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["scan_lsq_m8", "scan_lsq_m7_ties", "scan_cq_m8", "scan_pq_m8", "scan_pq_m16_ties"])
+def test_scan_golden(rb, name):
+    g = gold(name)
+    kind = int(g["kind"])
+    ix = rb.core.Index(kind, g["B"], g.get("nrm"))
+    d, i = ix.search(g["Xq"], g["cb"], int(g["k"]))
+    assert np.array_equal(bits(d), bits(g["dists"]))
+    assert np.array_equal(i, g["idx"])
+
+
+def _scan_case(kind, n, nq, m, d, seed, ties=False):
+    r = np.random.default_rng(seed)
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    Xq = r.standard_normal((nq, d)).astype(np.float32)
+    cb = r.standard_normal((m * 256, d // m if kind == orc.PQ else d)).astype(np.float32)
+    if ties:
+        Xq, cb = np.round(Xq * 2), np.round(cb * 2)
+        B = r.integers(0, 4, (n, m), dtype=np.uint8)
+    nrm = None
+    if kind == orc.LSQ:
+        nrm = (np.round(r.standard_normal(n) * 3) if ties else r.standard_normal(n) * 3).astype(np.float32)
+    return B, Xq, cb, nrm
+
+
+@pytest.mark.parametrize("kind", [orc.LSQ, orc.CQ, orc.PQ])
+@pytest.mark.parametrize("n,nq,m,k,ties", [
+    (100000, 40, 8, 1, False),
+    (100000, 33, 8, 1000, False),      # demos' knn (demos_train_query_base.jl:16); several compactions
+    (50000, 7, 7, 100, True),          # 7 codebooks (+ norm byte in the demo); massive ties
+    (30000, 16, 16, 10, False),
+    (300000, 5, 8, 50, True),          # few queries -> several DB slices + merge
+    (1000, 3, 4, 1000, False),         # k == n
+    (1500, 1, 1, 7, False),            # m = 1, single query
+])
+def test_scan_matches_reference(rb, kind, n, nq, m, k, ties):
+    d = 16 * m if kind == orc.PQ else 64
+    B, Xq, cb, nrm = _scan_case(kind, n, nq, m, d, seed=n + k + kind, ties=ties)
+    if orc.have_ref():
+        d0, i0 = orc.ref_linscan(kind, B, Xq, cb, k, nrm)      # the reference's own compiled C++
+    else:
+        d0, i0 = orc.linscan(kind, B, Xq, cb, k, nrm)
+    ix = rb.core.Index(kind, B, nrm)
+    d1, i1 = ix.search(Xq, cb, k)
+    assert np.array_equal(i1, i0)
+    assert np.array_equal(bits(d1), bits(d0))
+
+
+def test_scan_compat_symbols(rb):
+    for kind, fn in ((orc.PQ, "pq"), (orc.LSQ, "lsq"), (orc.CQ, "cq")):
+        B, Xq, cb, nrm = _scan_case(kind, 20000, 9, 8, 128, seed=kind)
+        d0, i0 = (orc.ref_linscan if orc.have_ref() else orc.linscan)(kind, B, Xq, cb, 25, nrm)
+        if kind == orc.PQ:
+            d1, i1 = rb.core.c_linscan_aqd_query(B, Xq, cb, 25)
+        elif kind == orc.LSQ:
+            d1, i1 = rb.core.c_linscan_aqd_query_extra_byte(B, Xq, cb, nrm, 25)
+        else:
+            d1, i1 = rb.core.c_linscan_aqd_cq_query_extra_byte(B, Xq, cb, 25)
+        assert np.array_equal(i1.astype(np.int64), i0.astype(np.int64))
+        assert np.array_equal(bits(d1), bits(d0))
+
+
+def test_scan_device_pointers_and_id_offset(rb):
+    import torch
+    B, Xq, cb, nrm = _scan_case(orc.LSQ, 60000, 20, 8, 128, seed=77)
+    d0, i0 = orc.linscan(orc.LSQ, B, Xq, cb, 10, nrm, id_offset=5_000_000)
+    ix = rb.core.Index(orc.LSQ, torch.from_numpy(B).cuda(), torch.from_numpy(nrm).cuda(), id_offset=5_000_000)
+    d1, i1 = ix.search(torch.from_numpy(Xq).cuda(), torch.from_numpy(cb).cuda(), 10)
+    assert np.array_equal(i1.cpu().numpy(), i0)
+    assert np.array_equal(bits(d1.cpu().numpy()), bits(d0))
+
+
+def test_base_sharded_scan_equals_single(rb):
+    """Config-5 structure on one GPU: shard the base, search each shard with its id offset, merge."""
+    B, Xq, cb, nrm = _scan_case(orc.LSQ, 90000, 25, 8, 64, seed=5, ties=True)
+    k = 100
+    d0, i0 = orc.linscan(orc.LSQ, B, Xq, cb, k, nrm)
+    parts = [(0, 30000), (30000, 52000), (52000, 90000)]
+    ds, is_ = [], []
+    for a, b in parts:
+        ix = rb.core.Index(orc.LSQ, B[a:b], nrm[a:b], id_offset=a)
+        d, i = ix.search(Xq, cb, k)
+        ds.append(d)
+        is_.append(i)
+    d1, i1 = rb.core.topk_merge(np.stack(ds), np.stack(is_))
+    assert np.array_equal(i1, i0)
+    assert np.array_equal(bits(d1), bits(d0))
+
+
+def test_topk_merge_against_lexsort(rb):
+    r = np.random.default_rng(0)
+    S, nq, k = 5, 37, 64
+    d = np.round(r.standard_normal((S, nq, k)) * 3).astype(np.float32)    # ties + negatives
+    i = r.permutation(S * nq * k).reshape(S, nq, k).astype(np.int32)
+    for s in range(S):                                                    # each list sorted by (dist, id)
+        for q in range(nq):
+            o = np.lexsort((i[s, q], d[s, q]))
+            d[s, q], i[s, q] = d[s, q][o], i[s, q][o]
+    dm, im = rb.core.topk_merge(d, i)
+    for q in range(nq):
+        dd, ii = d[:, q].reshape(-1), i[:, q].reshape(-1)
+        o = np.lexsort((ii, dd))[:k]
+        assert np.array_equal(im[q], ii[o]) and np.array_equal(bits(dm[q]), bits(dd[o]))
+
+
+# ---- PQ / OPQ encode -----------------------------------------------------------------------------------------
+def test_pq_encode_golden(rb):
+    g = gold("pq_encode_m8")
+    assert np.array_equal(rb.core.quantize_pq(g["X"], g["Cpq"], int(g["m"])), g["B_out"])
+
+
+@pytest.mark.parametrize("n,m,sub", [(20000, 8, 16), (3333, 4, 8), (1000, 16, 2), (500, 2, 24)])
+def test_pq_encode_matches_oracle(rb, n, m, sub):
+    r = np.random.default_rng(n)
+    X = r.standard_normal((n, m * sub)).astype(np.float32)
+    Cpq = r.standard_normal((m * 256, sub)).astype(np.float32)
+    assert np.array_equal(rb.core.quantize_pq(X, Cpq, m), orc.quantize_pq(X, Cpq, m))
+
+
+# ---- the Julia-shaped API ---------------------------------------------------------------------------------
+def test_julia_api_round_trip(rb):
+    """Same call sequence as experiment_lsq / demos: encode -> qerror -> norms -> linscan -> recall."""
+    n, d, m, nq, k = 4000, 32, 7, 50, 20
+    r = np.random.default_rng(1)
+    X = np.asfortranarray(r.standard_normal((d, n)).astype(np.float32))
+    Xq = np.asfortranarray((X[:, :nq] + 0.01 * r.standard_normal((d, nq))).astype(np.float32))
+    C = [np.asfortranarray((r.standard_normal((d, 256)) / 3).astype(np.float32)) for _ in range(m)]
+    B0 = r.integers(1, 257, (m, n)).astype(np.int16)
+    rb.seed_b200(99)
+    oldB = B0.copy()
+    B = rb.encoding_icm(X, oldB, C, 3, 4, True, 4, True, False)
+    assert B.shape == (m, n) and B.dtype == np.int16 and B.min() >= 1 and B.max() <= 256
+    assert np.array_equal(oldB, B)                                  # oldB mutated (src/LSQ.jl:248)
+    Cimg = np.concatenate([c.T for c in C])
+    o = orc.encode_icm(X.T, Cimg, (B0.T - 1).astype(np.uint8), 3, 4, 4, True, seed=99)
+    assert np.array_equal(B.T - 1, o["B"])
+    q = rb.qerror(X, B, C)
+    assert abs(q - orc.qerror(X.T, o["B"], Cimg)) <= 1e-4 * q       # 1e-4 relative (north_star)
+    rec = sum(c[:, B[i] - 1] for i, c in enumerate(C))
+    dbnorms = (rec ** 2).sum(0).astype(np.float32)
+    dists, res = rb.linscan_lsq(B, Xq, C, dbnorms, np.eye(d, dtype=np.float32), k)
+    assert dists.shape == (k, nq) and res.shape == (k, nq) and res.min() >= 1
+    d0, i0 = orc.linscan(orc.LSQ, o["B"], Xq.T, Cimg, k, dbnorms)
+    assert np.array_equal(res.T.astype(np.int64), i0) and np.array_equal(bits(dists.T), bits(d0))
+    recall = rb.eval_recall(np.arange(1, nq + 1), res, k, V=False)
+    assert recall[-1] > 0.9 and np.allclose(recall, orc.eval_recall(np.arange(1, nq + 1), i0, k))
+    Bs, objs = rb.encode_icm_cuda(X, B0.copy(), C, [1, 3], 4, 4, True, 2, False)
+    assert len(Bs) == 2 and objs[1] < objs[0]
+
+
+def test_errors_are_reported_not_swallowed(rb):
+    X, C, B = _icm_data(10, 8, 2, seed=0)
+    with pytest.raises(rb.RayuelaError):
+        rb.core.encode_icm(X, C[:, :4].copy(), B, 1, 1, 1, False)       # wrong codebook shape
+    with pytest.raises(rb.RayuelaError):
+        rb.core.Index(orc.LSQ, B, None)                                 # LSQ scan needs norms
+    ix = rb.core.Index(orc.CQ, B)
+    with pytest.raises(rb.RayuelaError):
+        ix.search(X, C, 11)                                             # k > n
