@@ -1,0 +1,526 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two hot paths on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--path icm|linscan]
+
+Default (--path icm): BASELINE.json configs[2] -- LSQ++ (SR-D) m=8 h=256 icmiter=4 npert=4 randord, 1M x 128
+synthetic base encoded from random initial codes with ilsiter=32 (the reference's base-set setting,
+src/LSQ_GPU.jl:351-352).  One step = one rayuela_encode_icm call over the whole base shard.
+`value` = encoded vectors/s with inputs resident in HBM; `e2e` = the same through the C ABI with pinned HOST
+buffers (H2D of X/C/B and D2H of the codes inside the timed region).  The JSON line also carries a `linscan`
+object: queries/s and Recall@1 of linscan_lsq (10k queries over the just-encoded base) with its own roofline.
+--impl reference times the reference's CPU algorithm (oracle restatement of the Julia host logic driving the
+reference's own compiled `condition` / linscan symbols from oracle/_ref) on a bounded sample per step.
+Under torchrun (N > 1) every rank works on its own shard (weak scaling, no data-path collective for the
+encode; one all-gather + merge for the base-sharded scan).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "rayuela.jl_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+H = 256
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic workload (harness code: torch on the GPU, never timed)
+# ---------------------------------------------------------------------------------------------------------
+def make_data(n, nq, d, seed, device, rank=0):
+    """SIFT-like synthetic base: 1024 Gaussian clusters with a power-law spectrum (sigma_i ~ i^-0.75) plus
+    unit within-cluster noise on the same spectrum, then a fixed random rotation; queries come from the same
+    distribution.  Isotropic noise would make Recall@1 degenerate (~1%); this gives R@1 ~ 0.3 at 64-bit codes,
+    the regime of the reference's SIFT1M demo (probe: scratch/recall_probe.py)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(1234)
+    s = torch.arange(1, d + 1, device=device, dtype=torch.float32) ** -0.75
+    rot, _ = torch.linalg.qr(torch.randn(d, d, generator=g, device=device))
+    centres = torch.randn(1024, d, generator=g, device=device) * s
+
+    def draw(k, gen):
+        z = centres[torch.randint(0, 1024, (k,), generator=gen, device=device)] + \
+            torch.randn(k, d, generator=gen, device=device) * s
+        return (z @ rot).contiguous()
+    X = draw(n, torch.Generator(device=device).manual_seed(seed + 7919 * rank))
+    Q = draw(nq, torch.Generator(device=device).manual_seed(4321))
+    return X, Q
+
+
+def kmeans(x, k, iters, gen):
+    import torch
+    c = x[torch.randperm(x.shape[0], generator=gen, device=x.device)[:k]].clone()
+    for _ in range(iters):
+        d2 = (c * c).sum(1)[None, :] - 2 * x @ c.T
+        a = d2.argmin(1)
+        s = torch.zeros_like(c).index_add_(0, a, x)
+        cnt = torch.bincount(a, minlength=k).clamp(min=1)[:, None]
+        c = s / cnt
+    d2 = (c * c).sum(1)[None, :] - 2 * x @ c.T
+    return c, d2.argmin(1)
+
+
+def train_codebooks(Xt, m, device):
+    """Harness stand-in for the (out-of-scope) trainer: residual k-means init, then SR-D noise as
+    SR_D_perturb does at iter 1 of 25, schedule 1, p = 0.5 (src/SR_perturbations.jl:27-49)."""
+    import torch
+    gen = torch.Generator(device=device).manual_seed(99)
+    res = Xt.clone()
+    Cs = []
+    for _ in range(m):
+        c, a = kmeans(res, H, 8, gen)
+        Cs.append(c)
+        res -= c[a]
+    C = torch.stack(Cs)                                     # [m][256][d]
+    std = C.reshape(m * H, -1).std(0, unbiased=True) / m
+    std = std * (1 - 1 / 25) ** 0.5
+    C = C + torch.randn(C.shape, generator=gen, device=device) * std
+    return C.reshape(m * H, -1).contiguous()
+
+
+def exact_nn(X, Q):
+    import torch
+    best = torch.full((Q.shape[0],), float("inf"), device=X.device)
+    arg = torch.zeros(Q.shape[0], dtype=torch.long, device=X.device)
+    qn = (Q * Q).sum(1)
+    for s in range(0, X.shape[0], 1 << 18):
+        xb = X[s:s + (1 << 18)]
+        d2 = qn[:, None] + (xb * xb).sum(1)[None, :] - 2 * Q @ xb.T
+        v, i = d2.min(1)
+        upd = v < best
+        best = torch.where(upd, v, best)
+        arg = torch.where(upd, i + s, arg)
+    return arg
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+        "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_sized(fn, first, target_s=12.0, cap=None):
+    """Run fn(size) once at `first`; if that took well under the target, run again at a size scaled to
+    ~target_s (bounded by cap) and return the larger run."""
+    t, kind = fn(first)
+    size = first
+    if t < target_s / 3:
+        size = int(min(cap or 10 ** 9, max(first, first * target_s / max(t, 1e-3))))
+        if size > first:
+            t, kind = fn(size)
+    return size, t, kind
+
+
+def cpu_icm_sample(cfg, n_s, seed=0):
+    """oracle.encode_icm (encode_icm_fully! restated, src/LSQ.jl:152-252) driving the reference's own compiled
+    `condition` when oracle/_ref is present.  Returns seconds for n_s vectors at cfg's ilsiter."""
+    from oracle import oracle as orc
+    r = np.random.default_rng(seed)
+    X = r.standard_normal((n_s, cfg["d"])).astype(np.float32)
+    C = (r.standard_normal((cfg["m"] * H, cfg["d"])) / np.sqrt(cfg["m"])).astype(np.float32)
+    B = r.integers(0, H, (n_s, cfg["m"]), dtype=np.uint8)
+    t0 = time.perf_counter()
+    orc.encode_icm(X, C, B, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=1, use_ref_step=orc.have_ref())
+    return time.perf_counter() - t0, ("reference" if orc.have_ref() else "port")
+
+
+def cpu_scan_sample(cfg, nq_s, n, seed=0):
+    from oracle import oracle as orc
+    r = np.random.default_rng(seed)
+    m = cfg["m"]
+    B = r.integers(0, H, (n, m), dtype=np.uint8)
+    Xq = r.standard_normal((nq_s, cfg["d"])).astype(np.float32)
+    cb = r.standard_normal((m * H, cfg["d"])).astype(np.float32)
+    nrm = r.standard_normal(n).astype(np.float32)
+    fn = orc.ref_linscan if orc.have_ref() else orc.linscan
+    t0 = time.perf_counter()
+    fn(orc.LSQ, B, Xq, cb, cfg["k"], nrm)
+    return time.perf_counter() - t0, ("reference" if orc.have_ref() else "port")
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    cores = host_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    times = []
+    if args.path == "icm":
+        n_s = args.ref_sample or 32768
+        for i in range(args.warmup + args.steps):
+            t, kind = cpu_icm_sample(cfg, n_s, seed=i)
+            if i >= args.warmup:
+                times.append(t)
+        per = float(np.mean(times))
+        value, unit, metric = n_s / per, "vectors/s", "lsq_icm_encode_vectors_per_sec"
+        sample = "%d of %d vectors per step, same m/ilsiter/icmiter/npert; vectors/s is size-independent" % (
+            n_s, cfg["n"])
+    else:
+        nq_s = args.ref_sample or 256 * cores
+        for i in range(args.warmup + args.steps):
+            t, kind = cpu_scan_sample(cfg, nq_s, cfg["n"], seed=i)
+            if i >= args.warmup:
+                times.append(t)
+        per = float(np.mean(times))
+        value, unit, metric = nq_s / per, "queries/s", "linscan_lsq_queries_per_sec"
+        sample = "%d of %d queries per step over the full %d-code base" % (nq_s, cfg["nq"], cfg["n"])
+    line = {
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args),
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample,
+                         "note": "reference C++ (oracle/_ref) + restated Julia host logic; Julia is not installed"},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(cfg, args):
+    return {"workload": "BASELINE.json configs[2]: LSQ++ (SR-D) m=%d h=256 icmiter=%d npert=%d randord ilsiter=%d, "
+                        "%dx%d synthetic base per GPU, random initial codes; linscan_lsq %d queries k=%d over the "
+                        "encoded base" % (cfg["m"], cfg["icmiter"], cfg["npert"], cfg["ilsiter"], cfg["n"], cfg["d"],
+                                          cfg["nq"], cfg["k"]),
+            "path": args.path, "n_per_gpu": cfg["n"], "d": cfg["d"], "m": cfg["m"], "h": H,
+            "ilsiter": cfg["ilsiter"], "icmiter": cfg["icmiter"], "npert": cfg["npert"], "nq": cfg["nq"],
+            "k": cfg["k"], "l2": "inputs larger than L2 (X 512 MB + unaries 8 GB per step; codes+norms 12 MB are "
+                                 "re-read per query tile by design, LUTs 82 MB)"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def timed_steps(fn, steps, warmup, dist, device):
+    """warmup, then exactly `steps` calls between barrier+synchronize; device time by CUDA events on the
+    launching (current) stream; max over ranks."""
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def wall_steps(fn, steps, warmup, dist, device):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    torch.cuda.synchronize(device)
+    ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def pinned(a):
+    import torch
+    t = torch.empty(a.shape, dtype=a.dtype, pin_memory=True)
+    t.copy_(a)
+    return t.numpy()
+
+
+def run_ours(args, cfg):
+    import torch
+    import rayuela_b200 as rb
+    from rayuela_b200 import core
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+    pk, pk_src = peaks()
+    n, d, m, nq, k = cfg["n"], cfg["d"], cfg["m"], cfg["nq"], cfg["k"]
+
+    # ---- workload -----------------------------------------------------------------------------------------
+    X, Q = make_data(n, nq, d, seed=1000, device=device, rank=rank)
+    C = train_codebooks(X[:50000], m, device)
+    gB = torch.Generator(device=device).manual_seed(5 + rank)
+    B0 = torch.randint(0, H, (n, m), generator=gB, device=device, dtype=torch.uint8)   # src/LSQ_GPU.jl:351
+    g0 = rank * n
+    Bwork = B0.clone()
+
+    def icm_step():
+        Bwork.copy_(B0)
+        core.encode_icm(X, C, Bwork, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0,
+                        inplace=True)
+
+    out = {}
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = rb.launch_count()
+    # ---- path (1): ICM encode -------------------------------------------------------------------------------
+    icm_ms = timed_steps(icm_step, args.steps, args.warmup, dist, device)
+    icm_launches = rb.launch_count() - l0
+    icm_per = icm_ms / args.steps
+    icm_value = world * n / (icm_per * 1e-3)
+    # dominant kernel alone (K3), timed by events on the launching stream: encode minus unary/table kernels is
+    # not separable from outside, so time a second pass with ilsiter=0 (K0+K1+K2 + one cost pass) and subtract
+    Bscratch = B0.clone()
+
+    def icm_setup_only():
+        core.encode_icm(X, C, Bscratch, 0, cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0, inplace=True)
+    setup_ms = timed_steps(icm_setup_only, max(2, args.steps // 2), 1, dist, device) / max(2, args.steps // 2)
+    k3_ms = max(icm_per - setup_ms, 1e-6)
+    gather_bytes = float(n) * cfg["ilsiter"] * cfg["icmiter"] * m * (m - 1) * H * 4
+    qerr = core.qerror(X, Bwork, C)
+    qerr0 = core.qerror(X, B0, C)
+
+    # e2e through the C ABI with pinned host buffers
+    Xh, Ch, B0h = pinned(X.cpu()), pinned(C.cpu()), pinned(B0.cpu())
+    Bh = pinned(B0.cpu())
+
+    def icm_e2e():
+        np.copyto(Bh, B0h)
+        core.encode_icm(Xh, Ch, Bh, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0,
+                        inplace=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    icm_e2e_ms = wall_steps(icm_e2e, e2e_steps, 1, dist, device) / e2e_steps
+    same = bool(np.array_equal(Bh, Bwork.cpu().numpy()))
+    del Xh
+
+    # ---- path (2): linscan_lsq over the encoded base -----------------------------------------------------------
+    Cm = C.reshape(m, H, d)
+    rec = torch.zeros(n, d, device=device)
+    for j in range(m):
+        rec += Cm[j][Bwork[:, j].long()]
+    dbnorms = (rec * rec).sum(1).contiguous()
+    del rec
+    index = core.Index(core.SCAN_LSQ, Bwork, dbnorms, id_offset=g0)
+    res = {}
+
+    def scan_step():
+        dl, il = index.search(Q, C, k)
+        if dist is not None:
+            gd = torch.empty((world * nq, k), device=device, dtype=dl.dtype)
+            gi = torch.empty((world * nq, k), device=device, dtype=il.dtype)
+            dist.all_gather_into_tensor(gd, dl)
+            dist.all_gather_into_tensor(gi, il)
+            dl, il = core.topk_merge(gd.view(world, nq, k), gi.view(world, nq, k))
+        res["d"], res["i"] = dl, il
+
+    l1 = rb.launch_count()
+    scan_ms = timed_steps(scan_step, args.steps, args.warmup, dist, device)
+    scan_launches = rb.launch_count() - l1
+    scan_per = scan_ms / args.steps
+    scan_value = nq / (scan_per * 1e-3)
+    # Recall@1 against exact fp32 brute force over the GLOBAL base
+    gt = exact_nn(X, Q)
+    if dist is not None:
+        # per-rank best -> global best: compare distances
+        dbest = ((X[gt] - Q) ** 2).sum(1)
+        alld = torch.empty(world * nq, device=device)
+        alli = torch.empty(world * nq, device=device, dtype=torch.long)
+        dist.all_gather_into_tensor(alld, dbest)
+        dist.all_gather_into_tensor(alli, gt + g0)
+        alld, alli = alld.view(world, nq), alli.view(world, nq)
+        gt_global = alli.gather(0, alld.argmin(0, keepdim=True))[0]
+    else:
+        gt_global = gt
+    recall1 = float((res["i"][:, 0].long() - 1 == gt_global).float().mean().item())   # ids are 1-based
+
+    Qh, Ch2 = pinned(Q.cpu()), pinned(C.cpu())
+
+    def scan_e2e():
+        dl, il = index.search(Qh, Ch2, k)     # host queries/codebooks in, host results out
+        res["dh"], res["ih"] = dl, il
+    scan_e2e_ms = wall_steps(scan_e2e, e2e_steps, 1, None, device) / e2e_steps
+    clocks = sampler.stop() if sampler else {}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample ---------------------------------------------------
+    cpu = None
+    cpu_scan = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.build()
+        cores = host_threads()
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        n_s, t, kind = cpu_sized(lambda s_: cpu_icm_sample(cfg, s_), 16384, cap=n)
+        cpu = {"value": n_s / t, "unit": "vectors/s", "cores": cores, "kind": kind,
+               "sample": "%d of %d vectors, one encode at the same m/ilsiter/icmiter/npert (%.1f s)" % (n_s, n, t),
+               "note": "reference compiled `condition` + restated Julia host logic (Julia not installed)"}
+        nq_s, t2, kind2 = cpu_sized(lambda s_: cpu_scan_sample(cfg, s_, n), max(64, 4 * cores), cap=nq)
+        cpu_scan = {"value": nq_s / t2, "unit": "queries/s", "cores": cores, "kind": kind2,
+                    "sample": "%d of %d queries over the full %d-code base (%.1f s)" % (nq_s, nq, n, t2)}
+
+    sm_mhz = clocks.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
+    onchip_peak = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s of L1/shared load bandwidth at the sampled clock
+    icm_roof = {"bound": "hbm", "achieved": gather_bytes / (k3_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                "unit": "GB/s", "traffic": None, "peak_source": pk_src,
+                "kernel": "icm_warp_kernel<8>", "kernel_ms": k3_ms,
+                "onchip_peak": onchip_peak,
+                "note": "algorithmic bytes = pairwise-table gather bytes n*ilsiter*icmiter*m*(m-1)*256*4 "
+                        "(SURVEY 8d); they are served by L2/L1, not HBM, so `frac` against the HBM copy peak may "
+                        "exceed 1; onchip_frac is the same figure against 148 SM x 128 B/clk x sampled SM clock"}
+    icm_roof["frac"] = icm_roof["achieved"] / icm_roof["peak"]
+    icm_roof["onchip_frac"] = icm_roof["achieved"] / onchip_peak
+    scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base
+    scan_roof = {"bound": "hbm", "achieved": scan_bytes / (scan_per * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                 "unit": "GB/s", "traffic": None, "peak_source": pk_src, "kernel": "scan_kernel<8,16,true>",
+                 "note": "algorithmic bytes = nq*n*(m+4): what the reference streams per query "
+                         "(pairwise_byte.cpp:56-83); whole search step (LUT + scan + merge) in the denominator"}
+    scan_roof["frac"] = scan_roof["achieved"] / scan_roof["peak"]
+
+    primary_icm = args.path == "icm"
+    line = {
+        "metric": "lsq_icm_encode_vectors_per_sec" if primary_icm else "linscan_lsq_queries_per_sec",
+        "value": icm_value if primary_icm else scan_value,
+        "unit": "vectors/s" if primary_icm else "queries/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": icm_per if primary_icm else scan_per,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args),
+        "clocks": clocks,
+        "e2e": ({"value": world * n / (icm_e2e_ms * 1e-3), "unit": "vectors/s",
+                 "h2d_bytes_per_step": n * d * 4 + m * H * d * 4 + n * m, "d2h_bytes_per_step": n * m,
+                 "ms_per_step": icm_e2e_ms, "codes_equal_device_path": same}
+                if primary_icm else
+                {"value": nq / (scan_e2e_ms * 1e-3), "unit": "queries/s",
+                 "h2d_bytes_per_step": nq * d * 4 + m * H * d * 4, "d2h_bytes_per_step": nq * k * 8,
+                 "ms_per_step": scan_e2e_ms}),
+        "gpu_launches": icm_launches if primary_icm else scan_launches,
+        "roofline": icm_roof if primary_icm else scan_roof,
+        "cpu_baseline": cpu if primary_icm else cpu_scan,
+        "icm": {"vectors_per_sec": icm_value, "vector_ils_iters_per_sec": icm_value * cfg["ilsiter"],
+                "ms_per_step": icm_per, "setup_ms(K0+K1+K2+cost)": setup_ms, "qerror_before": qerr0,
+                "qerror_after": qerr, "e2e_vectors_per_sec": world * n / (icm_e2e_ms * 1e-3), "roofline": icm_roof,
+                "cpu_baseline": cpu, "gpu_launches": icm_launches},
+        "linscan": {"metric": "linscan_lsq_queries_per_sec", "queries_per_sec": scan_value, "recall_at_1": recall1,
+                    "k": k, "nq": nq, "n_base_total": world * n, "ms_per_step": scan_per,
+                    "e2e_queries_per_sec": nq / (scan_e2e_ms * 1e-3), "roofline": scan_roof,
+                    "cpu_baseline": cpu_scan, "gpu_launches": scan_launches,
+                    "sharding": "base-sharded, one all-gather of per-shard top-k + merge" if world > 1 else "none"},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--path", default="icm", choices=["icm", "linscan"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--m", type=int, default=8)
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--k", type=int, default=1)
+    ap.add_argument("--ilsiter", type=int, default=32)
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("BENCH_ALLOW_SHORT"), "warmup must be >= 3"
+    cfg = dict(n=args.n, nq=args.nq, m=args.m, d=args.d, k=args.k, ilsiter=args.ilsiter, icmiter=4, npert=4)
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

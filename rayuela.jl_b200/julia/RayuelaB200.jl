@@ -1,0 +1,136 @@
+# RayuelaB200.jl -- drop-in Julia shim over librayuela_b200.so for Rayuela.jl's two hot paths.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The Python mirror
+# (rayuela_b200/julia_api.py) passes the library exactly the buffers these ccalls pass and is what the parity
+# tests drive.  Usage inside Rayuela.jl: `include("RayuelaB200.jl"); using .RayuelaB200` after src/Rayuela.jl's
+# own includes -- the methods below replace encoding_icm / encode_icm_cuda / linscan_* / quantize_pq / veccost
+# with the same positional signatures and return values (citations: file:line in the Rayuela.jl tree).
+module RayuelaB200
+
+export encoding_icm, encode_icm_cuda, veccost, qerror, quantize_pq, quantize_opq,
+       linscan_pq, linscan_opq, linscan_lsq, linscan_cq, seed_b200!
+
+using Printf, Statistics, LinearAlgebra
+
+const librayuela_b200 = get(ENV, "RAYUELA_B200_LIB",
+                            joinpath(@__DIR__, "..", "lib", "librayuela_b200.so"))
+
+const SEED = Ref{UInt64}(0)
+"Reproducible stream for the ILS perturbations / visiting orders (each encode call consumes one seed)."
+seed_b200!(s::Integer) = (SEED[] = UInt64(s); nothing)
+function next_seed()
+  s = SEED[]; SEED[] = s + 0x9E3779B97F4A7C15; s
+end
+
+function check(rc::Cint)
+  rc == 0 && return
+  msg = unsafe_string(ccall((:rayuela_last_error, librayuela_b200), Cstring, ()))
+  error("librayuela_b200 error $rc: $msg")
+end
+
+codes0(B::Matrix{<:Integer}) = convert(Matrix{UInt8}, B .- one(eltype(B)))   # src/LSQ.jl:228
+codes1(B::Matrix{UInt8})     = convert(Matrix{Int16}, B) .+ one(Int16)        # src/LSQ.jl:232
+
+# --- path (1) ---------------------------------------------------------------------------------------------
+"encoding_icm(X, oldB, C, ilsiter, icmiter, randord, npert, cpp=true, V=true) -> B   (src/LSQ.jl:272-294)"
+function encoding_icm(X::Matrix{Float32}, oldB::Matrix{Int16}, C::Vector{Matrix{Float32}},
+                      ilsiter::Integer, icmiter::Integer, randord::Bool, npert::Integer,
+                      cpp::Bool=true, V::Bool=true)
+  d, n = size(X); m = length(C); _, h = size(C[1])
+  h == 256 || error("The B200 implementation of ICM encoding only supports codebooks with 256 entries")
+  B     = codes0(oldB)
+  stats = zeros(Cint, 2, max(ilsiter, 1))
+  check(ccall((:rayuela_encode_icm, librayuela_b200), Cint,
+    (Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cuchar}, Int64, Cint, Cint, Cint, Cint, Cint, Cint, Cint, UInt64, Int64,
+     Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cint}, Cuint, Ptr{Cvoid}),
+    X, hcat(C...), B, n, d, m, h, ilsiter, icmiter, npert, randord, next_seed(), 0,
+    C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, stats, 0, C_NULL))
+  if V
+    for i = 1:ilsiter                                                         # src/LSQ.jl:243-245
+      @printf(" ILS iteration %d/%d done. %5.2f%% new codes are equal. %5.2f%% new codes are better.\n",
+              i, ilsiter, 100*stats[1,i]/n, 100*stats[2,i]/n)
+    end
+  end
+  newB = codes1(B)
+  copyto!(oldB, newB)                                                         # src/LSQ.jl:248
+  return newB
+end
+
+"encode_icm_cuda(RX, B, C, ilsiters, icmiter, npert, randord, nsplits=2, V=false) -> Bs, objs   (src/LSQ_GPU.jl:218-264)"
+function encode_icm_cuda(RX::Matrix{Float32}, B::Matrix{Int16}, C::Vector{Matrix{Float32}},
+                         ilsiters::Vector{Int64}, icmiter::Integer, npert::Integer, randord::Bool,
+                         nsplits::Integer=2, V::Bool=false)
+  d, n = size(RX); m = length(C); _, h = size(C[1]); nr = length(ilsiters)
+  B0    = codes0(B)
+  snaps = zeros(UInt8, m, n, nr)
+  objs  = zeros(Cfloat, nr)
+  check(ccall((:rayuela_encode_icm, librayuela_b200), Cint,
+    (Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cuchar}, Int64, Cint, Cint, Cint, Cint, Cint, Cint, Cint, UInt64, Int64,
+     Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cint}, Cuint, Ptr{Cvoid}),
+    RX, hcat(C...), B0, n, d, m, h, maximum(ilsiters), icmiter, npert, randord, next_seed(), 0,
+    C_NULL, convert(Vector{Cint}, ilsiters), nr, snaps, objs, C_NULL, C_NULL, 0, C_NULL))
+  Bs = [codes1(snaps[:, :, i]) for i = 1:nr]
+  return Bs, objs
+end
+
+"veccost(X, B, C)   (src/qerrors.jl:36-66)"
+function veccost(X::Matrix{Float32}, B::Matrix{<:Integer}, C::Vector{Matrix{Float32}})
+  d, n = size(X); m = length(C)
+  cost = zeros(Cfloat, n)
+  check(ccall((:rayuela_veccost, librayuela_b200), Cint,
+    (Ptr{Cfloat}, Ptr{Cuchar}, Ptr{Cfloat}, Int64, Cint, Cint, Cint, Ptr{Cfloat}, Ptr{Cdouble}, Cuint, Ptr{Cvoid}),
+    X, codes0(B), hcat(C...), n, d, m, 256, cost, C_NULL, 0, C_NULL))
+  return cost
+end
+qerror(X, B, C) = mean(veccost(X, B, C))                                     # src/qerrors.jl:69-74
+
+# --- PQ / OPQ encode -----------------------------------------------------------------------------------------
+"quantize_pq(X, C, V=false) -> B   (src/PQ.jl:18-48)"
+function quantize_pq(X::Matrix{Float32}, C::Vector{Matrix{Float32}}, V::Bool=false)
+  d, n = size(X); m = length(C); h = size(C[1], 2)
+  B = zeros(UInt8, m, n)
+  check(ccall((:rayuela_quantize_pq, librayuela_b200), Cint,
+    (Ptr{Cfloat}, Ptr{Cfloat}, Int64, Cint, Cint, Cint, Ptr{Cuchar}, Cuint, Ptr{Cvoid}),
+    X, cat(C..., dims=3), n, d, m, h, B, 0, C_NULL))
+  return codes1(B)
+end
+quantize_opq(X, R, C, V::Bool=false) = quantize_pq(R' * X, C, V)             # src/OPQ.jl:19-27
+
+# --- path (2): the three reference symbols, exact signatures (only the library path changes) ---------------
+"linscan_pq(B, X, C, b, k)   (src/Linscan.jl:5-37)"
+function linscan_pq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, b::Int, k::Int=10000)
+  m, n = size(B); d, nq = size(X)
+  dists = zeros(Cfloat, k, nq); res = zeros(Cuint, k, nq)
+  ccall((:linscan_aqd_query, librayuela_b200), Nothing,
+    (Ptr{Cfloat}, Ptr{Cuint}, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Cint, Cuint, Cint, Cint, Cint, Cint, Cint),
+    dists, res, B, cat(C..., dims=3), X, Cint(n), Cuint(nq), Cint(b), Cint(k), Cint(m), Cint(d), Cint(d/m))
+  return dists, (res .+= 1)
+end
+linscan_pq(B::Matrix{<:Integer}, X, C, b::Int, k::Int=10000) = linscan_pq(codes0(B), X, C, b, k)
+linscan_opq(B, X, C, b::Int, R::Matrix{Cfloat}, k::Int=10000) = linscan_pq(B, R' * X, C, b, k)  # src/Linscan.jl:93-115
+
+"linscan_lsq(B, X, C, dbnorms, R, k)   (src/Linscan.jl:118-157)"
+function linscan_lsq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, dbnorms::Vector{Cfloat},
+                     R::Matrix{Cfloat}, k::Int=10000)
+  RX = R' * X
+  m, n = size(B); d, nq = size(RX); _, h = size(C[1])
+  dists = zeros(Cfloat, k, nq); res = zeros(Cuint, k, nq)
+  ccall((:linscan_aqd_query_extra_byte, librayuela_b200), Nothing,
+    (Ptr{Cfloat}, Ptr{Cint}, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cfloat}, Cuint, Cint, Cint, Cint, Cint, Cint),
+    dists, res, B, RX, hcat(C...), dbnorms, Cint(nq), Cint(n), Cint(m), Cint(h), Cint(d), Cint(k))
+  return dists, res
+end
+linscan_lsq(B::Matrix{<:Integer}, X, C, dbnorms, R, k::Int=10000) = linscan_lsq(codes0(B), X, C, dbnorms, R, k)
+
+"linscan_cq(B, X, C, k)   (src/Linscan.jl:160-193)"
+function linscan_cq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, k::Int=10000)
+  m, n = size(B); d, nq = size(X); _, h = size(C[1])
+  dists = zeros(Cfloat, k, nq); res = zeros(Cuint, k, nq)
+  ccall((:linscan_aqd_cq_query_extra_byte, librayuela_b200), Nothing,
+    (Ptr{Cfloat}, Ptr{Cint}, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Cuint, Cint, Cint, Cint, Cint, Cint),
+    dists, res, B, X, hcat(C...), Cint(nq), Cint(n), Cint(m), Cint(h), Cint(d), Cint(k))
+  return dists, res
+end
+linscan_cq(B::Matrix{<:Integer}, X, C, k::Int=10000) = linscan_cq(codes0(B), X, C, k)
+
+end # module
