@@ -52,6 +52,20 @@ inline int fail(int code, const std::string& msg) {
   } while (0)
 
 // ---- device buffer (stream-ordered) -----------------------------------------------------------------
+// The default memory pool hands freed blocks back to the driver at every synchronisation (release threshold 0),
+// which turns each call's scratch allocations into real cudaMalloc/cudaFree.  Keep them cached instead.
+inline void keep_pool_memory() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_dev = dev;
+}
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -65,6 +79,7 @@ struct DevBuf {
     s = stream;
     bytes = nbytes;
     if (nbytes == 0) return RAYUELA_OK;
+    keep_pool_memory();
     RYL_CUDA(cudaMallocAsync(&p, nbytes, stream));
     return RAYUELA_OK;
   }

@@ -217,7 +217,7 @@ struct IcmParams {
 // coalesced 512 B float4 loads per warp.  Unaries are re-read per step but a vector's 8 KB stay L2-resident
 // for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
 template <int M>
-__global__ void __launch_bounds__(256) icm_warp_kernel(IcmParams p) {
+__global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.d;
@@ -236,9 +236,15 @@ __global__ void __launch_bounds__(256) icm_warp_kernel(IcmParams p) {
       Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
       perturb<M>(nb, p.npert, p.seed, it, (uint64_t)(p.g0 + l));  // src/LSQ.jl:225
       const int* order = p.orders + it * M;
-      for (int sweep = 0; sweep < p.icmiter; sweep++) {
+      // Memoised conditioning: the step for codebook j is a pure function of (U_j, codes of the others).
+      // If none of the other codes changed since j was last evaluated in THIS iteration, its argmin is the
+      // code it already holds, so the step is skipped -- bit-identical to running it (all icmiter sweeps
+      // "always run" in the reference, encode_icm.cpp / src/LSQ.jl:64-78, they just cannot change anything).
+      uint32_t dirty = (1u << M) - 1u;
+      for (int sweep = 0; sweep < p.icmiter && dirty; sweep++) {
         for (int s = 0; s < M; s++) {
           const int j = __ldg(order + s);
+          if (!((dirty >> j) & 1u)) continue;
           float4 a0 = __ldg(Ul + j * 64 + lane);
           float4 a1 = __ldg(Ul + j * 64 + 32 + lane);
 #pragma unroll
@@ -269,7 +275,11 @@ __global__ void __launch_bounds__(256) icm_warp_kernel(IcmParams p) {
             int oc = __shfl_xor_sync(0xffffffffu, bc, off);
             if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
           }
-          nb.set(j, (uint32_t)bc);
+          dirty &= ~(1u << j);
+          if ((uint32_t)bc != nb.get(j)) {
+            nb.set(j, (uint32_t)bc);
+            dirty |= ((1u << M) - 1u) & ~(1u << j);             // everyone conditioned on j must be redone
+          }
         }
       }
       const float newcost = warp_cost<M>(x, p.C, nb, p.d, sq, lane);  // src/LSQ.jl:237
@@ -384,7 +394,7 @@ static int launch_icm(const IcmParams& p, cudaStream_t s) {
   RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
   RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t need = (p.nc + warps - 1) / warps;
-  int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);
+  int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);  // 4 blocks of 8 warps per SM
   RYL_LAUNCH(icm_warp_kernel<M>, grid, warps * 32, smem, s, p);
   return RAYUELA_OK;
 }

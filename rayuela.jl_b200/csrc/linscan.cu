@@ -27,7 +27,8 @@ static constexpr int kRound = kScanThreads * kCodesPerThread;  // codes per bloc
 // ------------------------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ queries, const float* __restrict__ cb,
-                                                  float* __restrict__ lut, int nq, int d, int len, int mh) {
+                                                  float* __restrict__ lut, int nq, int d, int len, int mh,
+                                                  int tiled) {
   constexpr int CH = 64;
   __shared__ float cs[32][CH + 1];
   __shared__ float qs[32][CH];
@@ -67,7 +68,16 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     int q = q0 + qg + 8 * i;
-    if (q < nq) lut[(size_t)q * mh + e0 + e] = acc[i];
+    if (q < nq) {
+      if (tiled) {
+        // layout of scan8_kernel's shared-memory tile (see there): [q/16][(q%16)/4][c][((q%4)/2)*8 + k][q%2]
+        const int ent = e0 + e, k = ent >> 8, c = ent & 255;
+        lut[(size_t)(q >> 4) * 32768 + ((q & 15) >> 2) * 8192 + c * 32 + ((((q & 3) >> 1) * 8 + k) << 1) + (q & 1)] =
+            acc[i];
+      } else {
+        lut[(size_t)q * mh + e0 + e] = acc[i];
+      }
+    }
   }
 }
 
@@ -237,6 +247,288 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// K5 (m <= 8): bank-conflict-free scan.
+//
+// A 4-byte LUT lookup per byte of code makes the scan shared-memory-gather bound (32 lookups/clk/SM), and
+// 32 lanes looking up random entries of the same 256-entry row collide ~3.6x (measured, profiles/r1_v1).
+// Here every lane of a half-warp is at a DIFFERENT codebook k at any instant, and the LUT tile is laid out
+// so that codebook k of query-pair g lives in bank-pair g*8 + k:
+//      tile[tt][c][bp = g*8 + k][e]   (float; 4 queries per 32 KB tile: q = tt*4 + g*2 + e)
+// lane = hw*16 + g*8 + j handles code stream p = hw*8 + j of its warp's chunk and the query pair g of every
+// tile; at step s it is at codebook k = (s - j - 1) mod 8, so the 16 lanes of a half-warp hit 16 distinct
+// bank-pairs with one LDS.64 each -> no conflicts, 2 queries per load.  The sum for one code must still be
+// ((0 + t_0) + t_1) + ... in ascending k (pairwise_byte.cpp:70-73), so a lane's code simply starts j+1 steps
+// "late": the index stores each lane's byte stream pre-skewed (skew_codes_kernel) and the lane reads one
+// aligned 8-byte word per 8 steps.  Accumulate / restart / capture are done with packed FFMA2
+// (fma.rn.f32x2, exact per element):  acc = acc*keep_s + v   (keep_s = 0 at the step where the lane's next
+// code starts), done += acc*cap_s (cap_s = 1 at the step where its code completes).
+// The 128 KB LUT tile is staged with bulk async copies (cp.async.bulk + mbarrier).
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kChunkL = 64;                    // codes per lane stream per chunk
+static constexpr int kChunkCodes = 16 * kChunkL;      // 1024 codes per warp chunk
+static constexpr int kChunkBlocks = kChunkL + 1;      // 8-step blocks per chunk (one extra for the skew tail)
+static constexpr int kScan8Warps = 16;
+static constexpr int kScan8RBMax = 16;                // longest round (blocks per warp between overflow checks)
+static constexpr int kScan8SortKeys = 8192;           // shared-memory sort buffer (64 KB)
+static constexpr int kLutTileBytes = 131072;          // 16 queries * 8 codebooks * 256 * 4 B
+
+// W[chunk][t][p] (uint64): bytes of stream p = codes chunk*1024 + 16u + p (u = 0..63), delayed by (p&7)+1 bytes.
+__global__ void skew_codes_kernel(const uint8_t* __restrict__ codes, uint64_t* __restrict__ W, int64_t n, int m,
+                                  int64_t nchunks) {
+  const int64_t total = nchunks * kChunkBlocks * 16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i & 15);
+    const int t = (int)((i >> 4) % kChunkBlocks);
+    const int64_t chunk = (i >> 4) / kChunkBlocks;
+    const int delay = (p & 7) + 1;
+    uint64_t w = 0;
+    for (int b = 0; b < 8; b++) {
+      const int sb = 8 * t + b - delay;              // byte index in the lane's undelayed stream
+      if (sb < 0 || sb >= 8 * kChunkL) continue;
+      const int u = sb >> 3, k = sb & 7;
+      const int64_t id = chunk * kChunkCodes + 16 * u + p;
+      if (id < n && k < m) w |= (uint64_t)codes[id * m + k] << (8 * b);
+    }
+    W[i] = w;
+  }
+}
+
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  return ((uint64_t)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int IMM>
+__device__ __forceinline__ uint64_t lds64(uint32_t addr) {
+  uint64_t v;
+  asm("ld.shared.b64 %0, [%1+%2];" : "=l"(v) : "r"(addr), "n"(IMM));
+  return v;
+}
+
+struct Scan8Params {
+  const uint64_t* W;     // skewed codes [nchunks][65][16]
+  const float* norms;    // [n] or nullptr
+  const float* lut;      // tiled [qtiles][32768]
+  uint64_t* cand;        // [slices][qtiles*16][cap]
+  uint64_t* part;        // [slices][nq][k]
+  int64_t n, nchunks, chunks_per_slice;
+  int nq, k, cap, soft, rbmax;   // soft: compact a query's buffer once it holds more than this many keys
+};
+
+template <bool NORMS>
+__global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params p) {
+  constexpr int NT = kScan8Warps * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int cnt_s[16];
+  __shared__ float tau_s[16];
+  __shared__ __align__(8) uint64_t mbar;
+
+  const uint32_t lut_addr = smem_u32(smem_raw);
+  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(smem_raw + kLutTileBytes);
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int j = lane & 7, g = (lane >> 3) & 1, pidx = (lane >> 4) * 8 + j;
+  const int q0 = blockIdx.x * 16;
+  const int slice = blockIdx.y;
+  uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * 16 + (size_t)blockIdx.x * 16) * p.cap;
+
+  // ---- stage the LUT tile: 4 bulk async copies of 32 KB, completion on one mbarrier -----------------------
+  const uint32_t mbar_addr = smem_u32(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 16) {
+    cnt_s[tid] = 0;
+    tau_s[tid] = __int_as_float(0x7f800000);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(kLutTileBytes)
+                 : "memory");
+    const char* src = reinterpret_cast<const char*>(p.lut) + (size_t)blockIdx.x * kLutTileBytes;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              lut_addr + i * 32768),
+          "l"(src + i * 32768), "r"(32768), "r"(mbar_addr)
+          : "memory");
+  }
+  {
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(mbar_addr)
+          : "memory");
+    }
+  }
+
+  // ---- per-lane constants -----------------------------------------------------------------------------------
+  uint32_t off[8];
+  uint64_t keep2[8], cap2[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    off[s] = lut_addr + ((g * 8 + ((s - j - 1) & 7)) << 3);
+    const float kp = (s == ((j + 1) & 7)) ? 0.f : 1.f;
+    const float cp = (s == j) ? 1.f : 0.f;
+    keep2[s] = pack2(kp, kp);
+    cap2[s] = pack2(cp, cp);
+  }
+  float tau[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) tau[i] = __int_as_float(0x7f800000);
+  uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
+
+  auto compact = [&](int q) {
+    const int c = cnt_s[q];
+    const int np2 = pow2ceil(c);
+    uint64_t* cq = cand + (size_t)q * p.cap;
+    for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
+    __syncthreads();
+    block_bitonic_sort(sortbuf, np2);
+    const int keep = min(c, p.k);
+    for (int t = tid; t < keep; t += NT) cq[t] = sortbuf[t];
+    if (tid == 0) {
+      cnt_s[q] = keep;
+      if (c >= p.k) tau_s[q] = ordered_to_f32((uint32_t)(sortbuf[p.k - 1] >> 32));
+    }
+    __syncthreads();
+  };
+
+  // ---- this block's chunk range; warp w takes chunks c0 + w, c0 + w + 16, ... ---------------------------------
+  const int64_t c0 = (int64_t)slice * p.chunks_per_slice;
+  const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
+  const int nci = (int)((c1 - c0 + kScan8Warps - 1) / kScan8Warps);
+
+  const uint32_t n32 = (uint32_t)p.n;
+  const int hard = p.cap - kScan8Warps * 16 * p.rbmax;   // a round adds at most 256 keys per block-step
+  int sched = 1;                                          // warm-up: rounds of 1,1,2,4,... blocks so tau
+  bool first = true;                                      // stops being +inf as early as possible
+
+  for (int ci = 0; ci < nci; ci++) {
+    const int64_t chunk = c0 + (int64_t)ci * kScan8Warps + w;
+    const bool active = chunk < c1;                                    // warp-uniform
+    const uint64_t* wp = p.W + (active ? chunk : c0) * (kChunkBlocks * 16) + pidx;
+    const float* np = p.norms + chunk * kChunkCodes + pidx;            // norm of the code completed in block t+1
+    uint32_t id = (uint32_t)(chunk * kChunkCodes) + pidx - 16;         // code completed in block t (t >= 1)
+    uint64_t W0 = 0, W1 = 0;
+    if (active) {
+      W0 = __ldg(wp);
+      W1 = __ldg(wp + 16);
+    }
+    wp += 32;
+    float nrm0 = 0.f;
+    int t = 0;
+    while (t < kChunkBlocks) {
+      const int len = min(sched, kChunkBlocks - t);
+      for (int b = 0; b < len; b++, t++) {
+        if (active) {
+          uint64_t W2 = 0;
+          if (t + 2 < kChunkBlocks) W2 = __ldg(wp);
+          float nrm1 = 0.f;
+          if (NORMS && t + 1 < kChunkBlocks && id + 16 < n32) nrm1 = __ldg(np);
+          const uint32_t lo = (uint32_t)W0, hi = (uint32_t)(W0 >> 32);
+#define RYL_STEP(S, WREG, SHL, SHR)                                                      \
+  {                                                                                      \
+    const uint32_t a = ((SHL ? (WREG << 7) : (WREG >> SHR)) & 0x7F80u) + off[S];         \
+    uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a); \
+    acc[0] = ffma2(acc[0], keep2[S], v0);                                                \
+    acc[1] = ffma2(acc[1], keep2[S], v1);                                                \
+    acc[2] = ffma2(acc[2], keep2[S], v2);                                                \
+    acc[3] = ffma2(acc[3], keep2[S], v3);                                                \
+    done[0] = ffma2(acc[0], cap2[S], done[0]);                                           \
+    done[1] = ffma2(acc[1], cap2[S], done[1]);                                           \
+    done[2] = ffma2(acc[2], cap2[S], done[2]);                                           \
+    done[3] = ffma2(acc[3], cap2[S], done[3]);                                           \
+  }
+          RYL_STEP(0, lo, 1, 0)
+          RYL_STEP(1, lo, 0, 1)
+          RYL_STEP(2, lo, 0, 9)
+          RYL_STEP(3, lo, 0, 17)
+          RYL_STEP(4, hi, 1, 0)
+          RYL_STEP(5, hi, 0, 1)
+          RYL_STEP(6, hi, 0, 9)
+          RYL_STEP(7, hi, 0, 17)
+#undef RYL_STEP
+          if (t >= 1 && id < n32) {
+            float dv[8];
+            const uint64_t n2 = pack2(nrm0, nrm0);
+            bool anyp = false;
+#pragma unroll
+            for (int tt = 0; tt < 4; tt++) {
+              uint64_t dd = done[tt];
+              if (NORMS) dd = fadd2(dd, n2);                   // + dbnorms[i] last, pairwise_byte.cpp:74
+              dv[2 * tt] = __uint_as_float((uint32_t)dd);
+              dv[2 * tt + 1] = __uint_as_float((uint32_t)(dd >> 32));
+              anyp |= (dv[2 * tt] <= tau[2 * tt]) | (dv[2 * tt + 1] <= tau[2 * tt + 1]);
+            }
+            if (anyp) {
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                if (dv[i] <= tau[i]) {
+                  const int q = (i >> 1) * 4 + g * 2 + (i & 1);
+                  int pos = atomicAdd(&cnt_s[q], 1);
+                  cand[(size_t)q * p.cap + pos] = make_key(dv[i], id);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int tt = 0; tt < 4; tt++) done[tt] = 0ull;
+          W0 = W1;
+          W1 = W2;
+          nrm0 = nrm1;
+          wp += 16;
+          np += 16;
+          id += 16;
+        }
+      }
+      sched = min(p.rbmax, first ? 1 : sched * 2);
+      first = false;
+      // a buffer is compacted when it exceeds the soft limit, could overflow in the next round, or holds its
+      // first k candidates (tau still +inf)
+      bool mine = false;
+      if (tid < 16) {
+        const int c = cnt_s[tid];
+        mine = c > p.soft || c > hard || (c >= p.k && tau_s[tid] == __int_as_float(0x7f800000));
+      }
+      if (__syncthreads_or(mine)) {
+        for (int q = 0; q < 16; q++) {
+          const int c = cnt_s[q];
+          if (c > p.soft || c > hard || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000))) compact(q);
+        }
+#pragma unroll
+        for (int tt = 0; tt < 4; tt++) {
+          tau[2 * tt] = tau_s[tt * 4 + g * 2];
+          tau[2 * tt + 1] = tau_s[tt * 4 + g * 2 + 1];
+        }
+      }
+    }
+  }
+
+  for (int q = 0; q < 16; q++) {
+    if (q0 + q >= p.nq) break;
+    compact(q);
+    const int c = cnt_s[q];
+    uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
+    for (int i = tid; i < p.k; i += NT) out[i] = i < c ? sortbuf[i] : ~0ull;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // K6: merge of S sorted lists per query into the global top-k, by the (dist, id) total order.
 //   keys != null : lists are 64-bit keys [S][nq][k] from scan_kernel (ids local; id_add makes them final)
 //   else         : lists are (dists, idx) [S][nq][k] (already-final ids; the multi-GPU exchange format)
@@ -278,7 +570,8 @@ using namespace ryl;
 struct rayuela_index {
   int kind = 0, m = 0, h = 0, mp = 0, device = 0;
   int64_t n = 0, id_offset = 0;
-  DevBuf codes, norms;
+  int64_t nchunks = 0;   // m <= 8: skewed layout for scan8_kernel
+  DevBuf codes, norms, skew;
 };
 
 template <int M, int QT>
@@ -320,7 +613,7 @@ extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t
   RYL_ARG(kind >= 0 && kind <= 2, "index_create: unknown kind");
   RYL_ARG(h == kH, "index_create: only h = 256 is supported (one byte per codebook)");
   RYL_ARG(m >= 1 && m <= 16, "index_create: m must be in 1..16");
-  RYL_ARG(n >= 1 && n < (1ll << 32), "index_create: n must be in 1..2^32-1");
+  RYL_ARG(n >= 1 && n < (1ll << 32) - 4096, "index_create: n must be in 1..2^32-4097 per index shard");
   RYL_ARG(codes != nullptr, "index_create: codes is null");
   RYL_ARG(kind != RAYUELA_SCAN_LSQ || dbnorms != nullptr, "index_create: LSQ scan needs dbnorms");
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
@@ -335,9 +628,17 @@ extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t
   auto body = [&]() -> int {
     InArg<uint8_t> raw;
     RYL_TRY(raw.bind(codes, (size_t)n * m, dev, s));
-    RYL_TRY(ix->codes.alloc((size_t)n * ix->mp, s));
-    int blocks = (int)std::min<int64_t>((n * ix->mp + 255) / 256, 148 * 16);
-    RYL_LAUNCH(pad_codes_kernel, blocks, 256, 0, s, raw.d, ix->codes.as<uint8_t>(), n, m, ix->mp);
+    if (m <= 8) {   // skewed streams for the conflict-free scan
+      ix->nchunks = (n + kChunkCodes - 1) / kChunkCodes;
+      const int64_t words = ix->nchunks * kChunkBlocks * 16;
+      RYL_TRY(ix->skew.alloc((size_t)words * sizeof(uint64_t), s));
+      int blocks = (int)std::min<int64_t>((words + 255) / 256, 148 * 16);
+      RYL_LAUNCH(skew_codes_kernel, blocks, 256, 0, s, raw.d, ix->skew.as<uint64_t>(), n, m, ix->nchunks);
+    } else {
+      RYL_TRY(ix->codes.alloc((size_t)n * ix->mp, s));
+      int blocks = (int)std::min<int64_t>((n * ix->mp + 255) / 256, 148 * 16);
+      RYL_LAUNCH(pad_codes_kernel, blocks, 256, 0, s, raw.d, ix->codes.as<uint8_t>(), n, m, ix->mp);
+    }
     if (kind == RAYUELA_SCAN_LSQ) {
       RYL_TRY(ix->norms.alloc((size_t)n * sizeof(float), s));
       RYL_CUDA(cudaMemcpyAsync(ix->norms.p, dbnorms, (size_t)n * sizeof(float),
@@ -359,6 +660,7 @@ extern "C" int rayuela_index_free(rayuela_index* ix) {
   if (ix) {
     ix->codes.release();
     ix->norms.release();
+    ix->skew.release();
     delete ix;
   }
   return RAYUELA_OK;
@@ -380,6 +682,7 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   RYL_ARG(nq >= 1 && d >= 1, "index_search: nq and d must be positive");
   RYL_ARG(k >= 1 && (int64_t)k <= ix->n, "index_search: k must be in 1..n");
   RYL_ARG(k <= 4096, "index_search: k > 4096 is not supported yet");
+  RYL_ARG(ix->m <= 8 || k <= 3584, "index_search: k > 3584 is not supported for m > 8 yet");
   const int m = ix->m, mh = m * kH;
   const bool pq = ix->kind == RAYUELA_SCAN_PQ;
   RYL_ARG(!pq || d % m == 0, "index_search: PQ scan needs d divisible by m");
@@ -394,50 +697,87 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   RYL_TRY(d_out.bind(dists, (size_t)nq * k, dev, s));
   RYL_TRY(i_out.bind(idx, (size_t)nq * k, dev, s));
 
-  const int QT = scan_qt(m);
-  const int cap = host_pow2ceil(std::max(2 * kRound, 2 * k + kRound));
-  const size_t smem = (size_t)QT * mh * sizeof(float) + (size_t)cap * sizeof(uint64_t);
-  RYL_ARG(smem <= 227 * 1024, "index_search: shared-memory budget exceeded");
+  const bool v2 = m <= 8;                                   // conflict-free scan8_kernel
+  const int QT = v2 ? 16 : scan_qt(m);
+  // v2: soft compaction limit 2k, hard limit = capacity minus what one round can add (256 codes per block-step)
+  int soft = std::max(512, 2 * k), rbmax = kScan8RBMax;
+  if (soft + 256 * kScan8RBMax > kScan8SortKeys) {
+    soft = k + (kScan8SortKeys - k) / 2;
+    rbmax = std::max(1, (kScan8SortKeys - soft) / 256);
+  }
+  const int cap = v2 ? soft + 256 * rbmax : host_pow2ceil(std::max(2 * kRound, 2 * k + kRound));
+  const size_t smem = v2 ? (size_t)kLutTileBytes + (size_t)kScan8SortKeys * sizeof(uint64_t)
+                         : (size_t)QT * mh * sizeof(float) + (size_t)cap * sizeof(uint64_t);
+  RYL_ARG(smem <= 227 * 1024, "index_search: shared-memory budget exceeded (k too large)");
   const int64_t id_add = (pq ? 0 : 1) + ix->id_offset;  // linscan_aqd.cpp:88 vs pairwise_byte.cpp:76
+  const float* norms = ix->kind == RAYUELA_SCAN_LSQ ? ix->norms.as<float>() : nullptr;
 
   const int chunk_q = 16384;
   for (int qb = 0; qb < nq; qb += chunk_q) {
     const int nqc = std::min(chunk_q, nq - qb);
     const int qtiles = (nqc + QT - 1) / QT;
-    // DB slices: enough blocks for >= 2 waves, slices no shorter than 8 rounds, S*k within one merge pass
-    int S = std::max(1, (2 * sm_count() + qtiles - 1) / qtiles);
-    S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (8 * kRound)));
+    // DB slices: enough blocks for several waves, slices no shorter than 8 rounds, S*k within one merge pass
+    const int64_t unit = v2 ? (int64_t)kChunkCodes * kScan8Warps : kRound;   // codes per block round
+    int S = std::max(1, ((v2 ? 6 : 2) * sm_count() + qtiles - 1) / qtiles);
+    S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (v2 ? unit : 8 * unit)));
     S = std::min(S, std::max(1, 16384 / k));
     int64_t slice_len = (ix->n + S - 1) / S;
-    slice_len = (slice_len + kRound - 1) / kRound * kRound;
+    slice_len = (slice_len + unit - 1) / unit * unit;
     S = (int)((ix->n + slice_len - 1) / slice_len);
 
     DevBuf lut, cand, part;
-    RYL_TRY(lut.alloc((size_t)nqc * mh * sizeof(float), s));
+    const size_t lut_floats = v2 ? (size_t)qtiles * (kLutTileBytes / 4) : (size_t)nqc * mh;
+    RYL_TRY(lut.alloc(lut_floats * sizeof(float), s));
+    if (v2 && (m < 8 || nqc % 16)) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m
     RYL_TRY(cand.alloc((size_t)S * qtiles * QT * cap * sizeof(uint64_t), s));
     RYL_TRY(part.alloc((size_t)S * nqc * k * sizeof(uint64_t), s));
 
     dim3 lg(mh / 32, (nqc + 31) / 32);
     const float* qptr = q_in.d + (size_t)qb * d;
+    const int tiled = v2 ? 1 : 0;
     if (ix->kind == RAYUELA_SCAN_LSQ)
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
     else if (ix->kind == RAYUELA_SCAN_CQ)
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
     else
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
 
-    ScanParams p;
-    p.codes = ix->codes.as<uint8_t>();
-    p.norms = ix->kind == RAYUELA_SCAN_LSQ ? ix->norms.as<float>() : nullptr;
-    p.lut = lut.as<float>();
-    p.cand = cand.as<uint64_t>();
-    p.part = part.as<uint64_t>();
-    p.n = ix->n;
-    p.slice_len = slice_len;
-    p.nq = nqc;
-    p.k = k;
-    p.cap = cap;
-    RYL_TRY(launch_scan(m, p, p.norms != nullptr, dim3(qtiles, S), smem, s));
+    if (v2) {
+      Scan8Params p;
+      p.W = ix->skew.as<uint64_t>();
+      p.norms = norms;
+      p.lut = lut.as<float>();
+      p.cand = cand.as<uint64_t>();
+      p.part = part.as<uint64_t>();
+      p.n = ix->n;
+      p.nchunks = ix->nchunks;
+      p.chunks_per_slice = slice_len / kChunkCodes;
+      p.nq = nqc;
+      p.k = k;
+      p.cap = cap;
+      p.soft = soft;
+      p.rbmax = rbmax;
+      if (norms) {
+        RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RYL_LAUNCH(scan8_kernel<true>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
+      } else {
+        RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RYL_LAUNCH(scan8_kernel<false>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
+      }
+    } else {
+      ScanParams p;
+      p.codes = ix->codes.as<uint8_t>();
+      p.norms = norms;
+      p.lut = lut.as<float>();
+      p.cand = cand.as<uint64_t>();
+      p.part = part.as<uint64_t>();
+      p.n = ix->n;
+      p.slice_len = slice_len;
+      p.nq = nqc;
+      p.k = k;
+      p.cap = cap;
+      RYL_TRY(launch_scan(m, p, norms != nullptr, dim3(qtiles, S), smem, s));
+    }
     RYL_TRY(merge_lists(part.as<uint64_t>(), nullptr, nullptr, S, nqc, k, d_out.d + (size_t)qb * k,
                         i_out.d + (size_t)qb * k, id_add, s));
   }
