@@ -499,6 +499,10 @@ def run_ours(args, cfg):
 
 
 def main():
+    # stdout carries exactly one JSON line: route everything else (NCCL banners, library chatter) to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

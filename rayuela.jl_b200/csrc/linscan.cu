@@ -314,6 +314,63 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
   return v;
 }
 
+// Block-wide radix select over c distinct 64-bit keys in shared memory: returns the k-th smallest key
+// (1 <= k <= c).  Eight 8-bit passes from the most significant byte; per pass a 256-bin histogram of the keys
+// that match the prefix decided so far (lanes with equal digits are aggregated with match.any so the all-equal
+// leading bytes of similar distances cost one shared atomic per warp), then warp 0 picks the bin holding rank k.
+__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int c, int k, int* hist, int* sel) {
+  const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
+  uint64_t prefix = 0;
+  int krem = k;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = 56 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < c; t0 += nt) {          // uniform trip count: match.any needs converged warps
+      const int t = t0 + tid;
+      bool act = t < c;
+      uint32_t digit = 0;
+      if (act) {
+        const uint64_t key = buf[t];
+        act = pass == 0 || (key >> (shift + 8)) == prefix;
+        digit = (uint32_t)(key >> shift) & 255u;
+      }
+      const uint32_t peers = __match_any_sync(0xffffffffu, act ? digit : 256u + lane);
+      if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        loc[i] = hist[lane * 8 + i];
+        sum += loc[i];
+      }
+      int inc = sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += v;
+      }
+      int run = inc - sum;
+      if (run < krem && krem <= inc) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          if (run < krem && krem <= run + loc[i]) {
+            sel[0] = lane * 8 + i;
+            sel[1] = krem - run;
+          }
+          run += loc[i];
+        }
+      }
+    }
+    __syncthreads();
+    prefix = (prefix << 8) | (uint32_t)sel[0];
+    krem = sel[1];
+  }
+  return prefix;
+}
+
 struct Scan8Params {
   const uint64_t* W;     // skewed codes [nchunks][65][16]
   const float* norms;    // [n] or nullptr
@@ -391,20 +448,64 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
   for (int i = 0; i < 8; i++) tau[i] = __int_as_float(0x7f800000);
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
 
+  __shared__ int hist_s[256];
+  __shared__ int sel_s[4];
+  // Intermediate compaction: keep the k smallest keys (unordered) and set tau to the k-th distance.
   auto compact = [&](int q) {
+    const int c = cnt_s[q];
+    uint64_t* cq = cand + (size_t)q * p.cap;
+    if (c <= p.k) {            // nothing to drop; tau only if the buffer holds exactly k keys
+      if (c == p.k) {          // tau = the largest of the k keys
+        uint64_t mx = 0;
+        for (int t = tid; t < c; t += NT) mx = max(mx, cq[t]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+        if (lane == 0) sortbuf[w] = mx;
+        __syncthreads();
+        if (tid == 0) {
+          for (int i = 1; i < kScan8Warps; i++) mx = max(mx, sortbuf[i]);
+          tau_s[q] = ordered_to_f32((uint32_t)(mx >> 32));
+        }
+        __syncthreads();
+      }
+      return;
+    }
+    if (c <= 512) {            // small buffers: a bitonic sort is cheaper than eight radix passes
+      const int np2 = pow2ceil(c);
+      for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
+      __syncthreads();
+      block_bitonic_sort(sortbuf, np2);
+      for (int t = tid; t < p.k; t += NT) cq[t] = sortbuf[t];
+      if (tid == 0) {
+        cnt_s[q] = p.k;
+        tau_s[q] = ordered_to_f32((uint32_t)(sortbuf[p.k - 1] >> 32));
+      }
+      __syncthreads();
+      return;
+    }
+    for (int t = tid; t < c; t += NT) sortbuf[t] = cq[t];
+    if (tid == 0) sel_s[2] = 0;
+    __syncthreads();
+    const uint64_t pivot = block_radix_select(sortbuf, c, p.k, hist_s, sel_s);
+    for (int t = tid; t < c; t += NT) {
+      const uint64_t key = sortbuf[t];
+      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly k keys (keys are distinct)
+    }
+    if (tid == 0) {
+      cnt_s[q] = p.k;
+      tau_s[q] = ordered_to_f32((uint32_t)(pivot >> 32));
+    }
+    __syncthreads();
+  };
+  // Final: the k smallest, sorted, left in sortbuf[0 .. min(c,k)).
+  auto finalize = [&](int q) {
+    compact(q);
     const int c = cnt_s[q];
     const int np2 = pow2ceil(c);
     uint64_t* cq = cand + (size_t)q * p.cap;
     for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
     __syncthreads();
     block_bitonic_sort(sortbuf, np2);
-    const int keep = min(c, p.k);
-    for (int t = tid; t < keep; t += NT) cq[t] = sortbuf[t];
-    if (tid == 0) {
-      cnt_s[q] = keep;
-      if (c >= p.k) tau_s[q] = ordered_to_f32((uint32_t)(sortbuf[p.k - 1] >> 32));
-    }
-    __syncthreads();
   };
 
   // ---- this block's chunk range; warp w takes chunks c0 + w, c0 + w + 16, ... ---------------------------------
@@ -520,7 +621,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
 
   for (int q = 0; q < 16; q++) {
     if (q0 + q >= p.nq) break;
-    compact(q);
+    finalize(q);
     const int c = cnt_s[q];
     uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
     for (int i = tid; i < p.k; i += NT) out[i] = i < c ? sortbuf[i] : ~0ull;
@@ -718,7 +819,7 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
     const int qtiles = (nqc + QT - 1) / QT;
     // DB slices: enough blocks for several waves, slices no shorter than 8 rounds, S*k within one merge pass
     const int64_t unit = v2 ? (int64_t)kChunkCodes * kScan8Warps : kRound;   // codes per block round
-    int S = std::max(1, ((v2 ? 6 : 2) * sm_count() + qtiles - 1) / qtiles);
+    int S = std::max(1, ((v2 && k <= 64 ? 6 : 2) * sm_count() + qtiles - 1) / qtiles);
     S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (v2 ? unit : 8 * unit)));
     S = std::min(S, std::max(1, 16384 / k));
     int64_t slice_len = (ix->n + S - 1) / S;
