@@ -61,6 +61,11 @@ int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, in
                        const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
                        float* cost_out, int* stats, unsigned flags, void* stream);
 
+/* Conditioning steps (n * ilsiter * icmiter * m in the reference, src/LSQ.jl:64-78) actually executed by the last
+ * rayuela_encode_icm call of this thread that requested `stats`, and that total: a step whose conditioning codes
+ * did not change since its last evaluation is skipped (its result is provably unchanged). Measurement aid. */
+int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total);
+
 /* Replaces veccost (src/qerrors.jl:36-66).  mean_out (host double, may be NULL) receives qerror
  * (src/qerrors.jl:69-74). cost may be NULL when only the mean is wanted. */
 int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,

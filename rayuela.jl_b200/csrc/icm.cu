@@ -207,6 +207,7 @@ struct IcmParams {
   const int* snap_iters;  // [n_snap] (1-based ILS iteration counts)
   uint8_t* B_snap;      // [n_snap][n_total][m], already offset to this chunk's first vector
   int* stats;           // [ilsiter][2] (#equal, #better)
+  unsigned long long* steps;  // [1] conditioning steps actually executed (memoisation skips the rest)
   int64_t nc, n_total, g0;
   uint64_t seed;
   int d, ilsiter, icmiter, npert, n_snap;
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   __syncthreads();
 
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
+  unsigned long long nsteps = 0;
   for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < p.nc; l += wstride) {
     const float* x = p.X + (size_t)l * p.d;
     Code cur = load_code<M>(p.B + (size_t)l * M);
@@ -245,6 +247,7 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
         for (int s = 0; s < M; s++) {
           const int j = __ldg(order + s);
           if (!((dirty >> j) & 1u)) continue;
+          nsteps++;
           float4 a0 = __ldg(Ul + j * 64 + lane);
           float4 a1 = __ldg(Ul + j * 64 + 32 + lane);
 #pragma unroll
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
     if (lane < M) p.B[(size_t)l * M + lane] = (uint8_t)cur.get(lane);
     if (p.cost && lane == 0) p.cost[l] = curcost;
   }
+  if (lane == 0 && nsteps) atomicAdd(p.steps, nsteps);
   __syncthreads();
   if (p.stats)
     for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x)
@@ -386,6 +390,14 @@ __global__ void __launch_bounds__(256) condition_kernel(uint8_t* __restrict__ B,
 // host side
 // ======================================================================================================
 using namespace ryl;
+
+static thread_local uint64_t g_icm_steps_done = 0, g_icm_steps_total = 0;
+
+extern "C" int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total) {
+  if (executed) *executed = g_icm_steps_done;
+  if (total) *total = g_icm_steps_total;
+  return RAYUELA_OK;
+}
 
 template <int M>
 static int launch_icm(const IcmParams& p, cudaStream_t s) {
@@ -493,8 +505,9 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   RYL_CUDA(cudaMemcpyAsync(ord_d.p, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   RYL_TRY(snapit_d.alloc((size_t)std::max(n_snap, 1) * sizeof(int), s));
   if (n_snap) RYL_CUDA(cudaMemcpyAsync(snapit_d.p, snap_iters, n_snap * sizeof(int), cudaMemcpyHostToDevice, s));
-  RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int), s));
+  RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int) + 8, s));   // + 8: executed-step counter
   RYL_CUDA(cudaMemsetAsync(stats_d.p, 0, stats_d.bytes, s));
+  unsigned long long* steps_d = reinterpret_cast<unsigned long long*>(stats_d.as<int>() + (size_t)std::max(ilsiter, 1) * 2);
 
   // K0 + K2: ||c||^2 and the pairwise tables (get_binaries + binaries_t, src/LSQ.jl:288,180-183)
   RYL_TRY(nrm_d.alloc((size_t)mh * sizeof(float), s));
@@ -528,6 +541,7 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
     p.snap_iters = snapit_d.as<int>();
     p.B_snap = snap_out.d ? snap_out.d + (size_t)l0 * m : nullptr;
     p.stats = stats_d.as<int>();
+    p.steps = steps_d;
     p.nc = nc;
     p.n_total = n;
     p.g0 = g0 + l0;
@@ -559,8 +573,12 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   RYL_TRY(snap_out.flush(s));
   RYL_TRY(cost_o.flush(s));
   if (stats) {
+    unsigned long long done_steps = 0;
     RYL_CUDA(cudaMemcpyAsync(stats, stats_d.p, (size_t)ilsiter * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaMemcpyAsync(&done_steps, steps_d, sizeof(done_steps), cudaMemcpyDeviceToHost, s));
     RYL_CUDA(cudaStreamSynchronize(s));
+    g_icm_steps_done = done_steps;
+    g_icm_steps_total = (uint64_t)n * ilsiter * icmiter * m;
   }
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
   return RAYUELA_OK;

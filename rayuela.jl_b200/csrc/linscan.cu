@@ -384,7 +384,7 @@ struct Scan8Params {
 template <bool NORMS>
 __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params p) {
   constexpr int NT = kScan8Warps * 32;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int cnt_s[16];
   __shared__ float tau_s[16];
   __shared__ __align__(8) uint64_t mbar;

@@ -135,6 +135,13 @@ def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=N
     return dict(B=B, cost=cost, stats=stats[:ilsiter] if want_stats else None, B_snap=Bs, objs=objs)
 
 
+def last_icm_steps():
+    """(executed, total) conditioning steps of the last encode_icm(..., want_stats=True) call."""
+    a, b = ct.c_uint64(0), ct.c_uint64(0)
+    check(_lib.lib().rayuela_encode_icm_steps(ct.addressof(a), ct.addressof(b)))
+    return int(a.value), int(b.value)
+
+
 def veccost(X, B, C, want_mean=False):
     """veccost / qerror (src/qerrors.jl:36-74)."""
     L = _lib.lib()
