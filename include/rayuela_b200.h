@@ -117,6 +117,14 @@ int rayuela_topk_merge(const float* dists_in, const int32_t* idx_in, int S, int 
 int rayuela_quantize_pq(const float* X, const float* Cpq, int64_t n, int d, int m, int h, uint8_t* B,
                         unsigned flags, void* stream);
 
+/* ---- codebook update, data-parallel half ("next" row 1) ------------------------------------------------- */
+/* Replaces fast_bin_matmul (src/codebook_update.jl:96-171), the O(n) part of update_codebooks_fast_bin
+ * (:175-204): A = B'B + rho*I ((m*h)-by-(m*h) double, symmetric) and b = B'X' ((m*h)-by-d double, column-major).
+ * A holds exact counts; b is accumulated in Float64 in ascending vector order like the reference, so both are
+ * bit-identical to it.  The dense solve (LAPACK getrf!/getrs!, :193-196) stays with the caller. */
+int rayuela_fast_bin_matmul(const float* X, const uint8_t* B, int64_t n, int d, int m, int h, double rho,
+                            double* A, double* b, unsigned flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

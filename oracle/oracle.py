@@ -225,3 +225,27 @@ def eval_recall(gt, idx, k):
     cnt = hit.sum(1)
     rank = np.where(cnt == 1, hit.argmax(1) + 1, k + 1)
     return np.array([(rank <= i).sum() / nq for i in range(1, k + 1)])
+
+
+def fast_bin_matmul(X, B, h=256, rho=1e-4):
+    """fast_bin_matmul restatement: returns A ((m*h, m*h) float64, symmetric) and b as its column-major image
+    viewed C-order, i.e. shape (d, m*h) with b[t, i*h + c]."""
+    X = _f32(X)
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    n, d = X.shape
+    m = B.shape[1]
+    A = np.zeros((m * h, m * h), dtype=np.float64)
+    b = np.zeros((d, m * h), dtype=np.float64)
+    f64p = ct.POINTER(ct.c_double)
+    lib().orc_fast_bin_matmul(_p(X, _f32p), _p(B, _u8p), ct.c_int64(n), d, m, h, ct.c_double(rho),
+                              A.ctypes.data_as(f64p), b.ctypes.data_as(f64p))
+    return A, b
+
+
+def update_codebooks_fast_bin(X, B, h=256, rho=1e-4):
+    """update_codebooks_fast_bin (src/codebook_update.jl:175-204): LAPACK getrf + getrs on (A, b), result
+    converted to Float32.  Returns the codebooks as the (m*h, d) image of hcat(C...)."""
+    from scipy.linalg import lu_factor, lu_solve
+    A, b = fast_bin_matmul(X, B, h, rho)
+    C = lu_solve(lu_factor(A), b.T)          # (m*h, d)
+    return C.astype(np.float32)

@@ -380,3 +380,29 @@ void orc_quantize_pq(const float* X, const float* Cpq, int64_t n, int d, int m, 
     }
   free(cn);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * fast_bin_matmul (src/codebook_update.jl:96-171): A = B'B + rho*I, b = B'X' exploiting that each
+ * column of the indicator matrix has exactly one 1 per codebook.
+ *   A  (m*h)-by-(m*h) double: A[(i,ci),(j,cj)] = #{l : B[i,l]=ci and B[j,l]=cj}  (+rho on the diagonal);
+ *      the reference counts in Float32 (exact below 2^24) and widens when adding rho*I (:166).
+ *   b  (m*h)-by-d double, column-major (b[t*mh + i*h + c]) = sum over l with B[i,l]=c of X[t,l], accumulated
+ *      in Float64 in ascending l (:151-161; the @simd runs over t, so the order over l is as written).
+ * PINNED by construction: every quantity is either an exact integer or a sequential double sum.
+ * ---------------------------------------------------------------------------------------- */
+void orc_fast_bin_matmul(const float* X, const uint8_t* B, int64_t n, int d, int m, int h, double rho,
+                         double* A, double* b) {
+  size_t mh = (size_t)m * h;
+  memset(A, 0, sizeof(double) * mh * mh);
+  memset(b, 0, sizeof(double) * mh * d);
+  for (int64_t l = 0; l < n; l++)
+    for (int i = 0; i < m; i++) {
+      size_t ri = (size_t)i * h + B[l * m + i];
+      for (int j = 0; j < m; j++) {
+        size_t rj = (size_t)j * h + B[l * m + j];
+        A[rj * mh + ri] += 1.0;
+      }
+      for (int t = 0; t < d; t++) b[(size_t)t * mh + ri] += (double)X[l * d + t];
+    }
+  for (size_t r = 0; r < mh; r++) A[r * mh + r] += rho;
+}

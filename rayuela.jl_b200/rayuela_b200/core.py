@@ -278,3 +278,38 @@ def c_condition(B, ub, binaries, binaries_t, pair2idx, to_condition, j):
     p2i, tc = _i32(pair2idx), _i32(to_condition)
     _lib.lib().condition(B.ctypes.data, ub.ctypes.data, bins.ctypes.data, bins_t.ctypes.data, p2i.ctypes.data,
                          tc.ctypes.data, j, n, m)
+
+
+def fast_bin_matmul(X, B, rho=1e-4):
+    """fast_bin_matmul (src/codebook_update.jl:96-171) on the GPU: A = B'B + rho*I ((m*h, m*h) float64) and
+    b = B'X' returned as the C-order image (d, m*h) of the reference's (m*h)-by-d column-major matrix."""
+    L = _lib.lib()
+    n, d = X.shape
+    m = B.shape[1]
+    a = _Args()
+    xp = a.inp(X, np.float32, (n, d))
+    bp = a.inp(B, np.uint8, (n, m))
+    dev = _is_dev(X)
+    if dev:
+        A = torch.empty((m * H, m * H), dtype=torch.float64, device=X.device)
+        bb = torch.empty((d, m * H), dtype=torch.float64, device=X.device)
+        a._side(True)
+        ap, bbp = A.data_ptr(), bb.data_ptr()
+    else:
+        A = np.empty((m * H, m * H), dtype=np.float64)
+        bb = np.empty((d, m * H), dtype=np.float64)
+        ap, bbp = A.ctypes.data, bb.ctypes.data
+    check(L.rayuela_fast_bin_matmul(xp, bp, n, d, m, H, ct.c_double(rho), ap, bbp, a.flags, a.stream))
+    return A, bb
+
+
+def update_codebooks_fast_bin(X, B, rho=1e-4):
+    """update_codebooks_fast_bin (src/codebook_update.jl:175-204): GPU fast_bin_matmul, then the reference's own
+    dense solve -- LAPACK getrf + getrs in Float64 (scipy on host arrays, torch.linalg on device tensors) --
+    and conversion to Float32.  Returns the (m*h, d) image of hcat(C...)."""
+    A, bb = fast_bin_matmul(X, B, rho)
+    if _is_dev(X):
+        lu, piv = torch.linalg.lu_factor(A)
+        return torch.linalg.lu_solve(lu, piv, bb.T.contiguous()).to(torch.float32).contiguous()
+    from scipy.linalg import lu_factor, lu_solve
+    return np.ascontiguousarray(lu_solve(lu_factor(A), bb.T).astype(np.float32))

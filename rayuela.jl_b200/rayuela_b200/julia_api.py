@@ -241,3 +241,86 @@ def SR_C_perturb(X, it, niter, schedule=1, p=0.5, rng=None):
     X = np.asarray(X, dtype=np.float32)
     stdx = apply_schedule(X.std(axis=1, ddof=1), it, niter, schedule, p)
     return (X + rng.standard_normal(X.shape) * stdx[:, None]).astype(np.float32)
+
+
+# ---- codebook update and the trainers that alternate it with the encoder ("next" row 1) ---------
+def _unhcat(Cimg, m):
+    return [np.asfortranarray(Cimg[i * H:(i + 1) * H].T) for i in range(m)]
+
+
+def update_codebooks_fast_bin(X, B, h, V=False, rho=1e-4):
+    """update_codebooks_fast_bin(X, B, h, V=false, rho=1e-4) -> C   (src/codebook_update.jl:175-204)."""
+    if h != H:
+        raise RayuelaError("only h = 256 is supported")
+    m = np.shape(B)[0]
+    return _unhcat(core.update_codebooks_fast_bin(_img(X), _codes0(B), rho), m)
+
+
+def update_codebooks(X, B, h, V=False, method="fastbin"):
+    """update_codebooks(X, B, h, V=false, method="fastbin")   (src/codebook_update.jl:235-278); only the method
+    every LSQ / LSQ++ trainer uses ("fastbin") is provided."""
+    if method != "fastbin":
+        raise RayuelaError("Codebook update method not available on B200: " + method)
+    return update_codebooks_fast_bin(X, B, h, V)
+
+
+def train_lsq(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, cpp=True, V=True):
+    """train_lsq(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, cpp=true, V=true) -> C, B, obj
+    (src/LSQ.jl:323-372; train_lsq_cuda src/LSQ_GPU.jl:267-319 is the same alternation)."""
+    X = np.asarray(X, dtype=np.float32)
+    R = np.asarray(R, dtype=np.float32)
+    RX = R.T @ X
+    C = update_codebooks(RX, B, h, V, "fastbin")                     # src/LSQ.jl:343-344
+    C = [R @ c for c in C]                                           # :347
+    if V:
+        print("%3d %e" % (-2, qerror(X, B, C)))
+    B = encoding_icm(X, np.array(B, dtype=np.int16), C, ilsiter, icmiter, randord, npert, cpp, V)   # :351
+    if V:
+        print("%3d %e" % (-1, qerror(X, B, C)))
+    obj = np.zeros(niter, dtype=np.float32)
+    for it in range(niter):
+        obj[it] = qerror(X, B, C)                                    # :357
+        if V:
+            print("%3d %e" % (it + 1, obj[it]))
+        C = update_codebooks(X, B, h, V, "fastbin")                  # :361
+        B = encoding_icm(X, B, C, ilsiter, icmiter, randord, npert, cpp, V)   # :364
+    return C, B, obj
+
+
+def train_lsq_cuda(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, nsplits=1, V=False):
+    """train_lsq_cuda (src/LSQ_GPU.jl:267-319): same alternation; nsplits is accepted and ignored."""
+    return train_lsq(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, True, V)
+
+
+def train_sr_cuda(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, method, schedule, p=0.5, nsplits=1,
+                  V=False):
+    """train_sr_cuda(...) -> C, B, objarray   (src/SR.jl:88-175): LSQ++ = LSQ with SR-C (noise on X before the
+    codebook update) or SR-D (noise on C before the encode)."""
+    if method not in ("SR_C", "SR_D"):
+        raise RayuelaError("SR method unknown")
+    X = np.asarray(X, dtype=np.float32)
+    R = np.asarray(R, dtype=np.float32)
+    RX = np.ascontiguousarray(R.T @ X)
+    if method == "SR_C":
+        C = update_codebooks(SR_C_perturb(RX, 0, niter, schedule, p), B, h, V, "fastbin")        # :118-121
+    else:
+        C = update_codebooks(RX, B, h, V, "fastbin")                                               # :124
+        C = SR_D_perturb(C, 1, niter, schedule, p)                                                 # :127
+    Bs, _ = encode_icm_cuda(RX, B, C, [ilsiter], icmiter, npert, randord, nsplits, V)              # :134
+    B = Bs[-1]
+    objarray = np.zeros(niter + 1, dtype=np.float32)
+    for it in range(1, niter + 1):
+        objarray[it - 1] = qerror(RX, B, C)                                                        # :146-147
+        if V:
+            print("%3d %e" % (it, objarray[it - 1]))
+        if method == "SR_C":
+            C = update_codebooks(SR_C_perturb(RX, it, niter, schedule, p), B, h, V, "fastbin")   # :152-154
+        else:
+            C = update_codebooks(RX, B, h, V, "fastbin")                                           # :157
+            C = SR_D_perturb(C, it, niter, schedule, p)                                            # :158
+        Bs, _ = encode_icm_cuda(RX, B, C, [ilsiter], icmiter, npert, randord, nsplits, V)          # :162
+        B = Bs[-1]
+        C = update_codebooks(RX, B, h, V, "fastbin")                                               # :166
+    objarray[niter] = qerror(RX, B, C)                                                             # :169
+    C = [R @ c for c in C]                                                                         # :172
+    return C, B, objarray

@@ -302,3 +302,54 @@ def test_errors_are_reported_not_swallowed(rb):
     ix = rb.core.Index(orc.CQ, B)
     with pytest.raises(rb.RayuelaError):
         ix.search(X, C, 11)                                             # k > n
+
+
+# ---- "next" row 1: codebook update --------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,m", [(10000, 32, 4), (30011, 128, 8), (700, 20, 16), (5, 3, 1)])
+def test_fast_bin_matmul_bit_exact(rb, n, d, m):
+    """A (exact counts + rho) and b (Float64, ascending-l accumulation) are bit-identical to the oracle."""
+    r = np.random.default_rng(n)
+    X = (r.random((n, d)) * 10).astype(np.float32)               # test/common.jl:2-8
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    A0, b0 = orc.fast_bin_matmul(X, B)
+    A1, b1 = rb.core.fast_bin_matmul(X, B)
+    assert np.array_equal(A1, A0)
+    assert np.array_equal(b1.view(np.uint64), b0.view(np.uint64))
+    import torch
+    A2, b2 = rb.core.fast_bin_matmul(torch.from_numpy(X).cuda(), torch.from_numpy(B).cuda())
+    assert np.array_equal(A2.cpu().numpy(), A0) and np.array_equal(b2.cpu().numpy().view(np.uint64), b0.view(np.uint64))
+
+
+def test_update_codebooks_and_reference_own_test(rb):
+    """test/chainq.jl:2-11: update_codebooks_fast_bin ~ update_codebooks_fast_bin2 (d=32, n=10k, m=4, h=256)."""
+    d, n, m, h = 32, 10000, 4, 256
+    r = np.random.default_rng(1)
+    X = np.asfortranarray((r.random((d, n)) * 10).astype(np.float32))
+    B = r.integers(1, h + 1, (m, n)).astype(np.int16)
+    C1 = rb.update_codebooks_fast_bin(X, B, h, False, 1e-4)
+    A, b = rb.core.fast_bin_matmul(np.ascontiguousarray(X.T), (B.T - 1).astype(np.uint8), 1e-4)
+    C2 = (np.linalg.inv(A) @ b.T).astype(np.float32)               # update_codebooks_fast_bin2, :209-229
+    C1img = np.concatenate([c.T for c in C1])
+    assert np.allclose(C1img, C2, rtol=1e-4, atol=1e-5)            # Julia's isapprox default is rtol = sqrt(eps)
+    C0 = orc.update_codebooks_fast_bin(X.T, (B.T - 1).astype(np.uint8))
+    assert np.allclose(C1img, C0, rtol=1e-6, atol=1e-7)            # same A, b, same LAPACK routine
+    assert len(C1) == m and C1[0].shape == (d, h)
+
+
+def test_train_lsq_and_sr_run_end_to_end(rb):
+    """The alternation of src/LSQ.jl:323-372 / src/SR.jl:88-175 through the GPU encoder and codebook update."""
+    d, n, m, h = 16, 6000, 4, 256
+    r = np.random.default_rng(2)
+    basis = r.standard_normal((d, d)) * (np.arange(1, d + 1) ** -0.7)[:, None]
+    X = np.asfortranarray((basis.T @ r.standard_normal((d, n))).astype(np.float32))
+    B0 = r.integers(1, h + 1, (m, n)).astype(np.int16)
+    C0 = [np.zeros((d, h), dtype=np.float32) for _ in range(m)]
+    R = np.eye(d, dtype=np.float32)
+    rb.seed_b200(7)
+    C, B, obj = rb.train_lsq(X, m, h, R, B0, C0, 4, 2, 2, True, 2, True, False)
+    assert B.shape == (m, n) and len(C) == m and obj.shape == (4,)
+    assert obj[-1] < obj[0] and obj[0] < 0.6 * float((X ** 2).sum(0).mean())
+    C2, B2, obj2 = rb.train_sr_cuda(X, m, h, R, B0, C0, 4, 2, 2, True, 2, "SR_D", 1, 0.5, 1, False)
+    assert obj2.shape == (5,) and obj2[-1] < obj2[0]
+    C3, B3, obj3 = rb.train_sr_cuda(X, m, h, R, B0, C0, 3, 2, 2, True, 2, "SR_C", 1, 0.5, 1, False)
+    assert obj3[-1] < obj3[0]

@@ -159,3 +159,23 @@ def test_eval_recall_counts_exactly_once():
     idx = np.array([[5, 1, 2], [7, 7, 3], [1, 2, 9]])
     rec = orc.eval_recall(gt, idx, 3)
     assert rec.tolist() == [1 / 3, 1 / 3, 2 / 3]  # query 1 lists the NN twice -> miss (src/Linscan.jl:208-214)
+
+
+def test_fast_bin_matmul_against_numpy():
+    """fast_bin_matmul restatement vs an explicit one-hot matrix (test/common.jl data, test/chainq.jl:2-11 shape)."""
+    n, d, m = 4000, 32, 4
+    r = np.random.default_rng(6)
+    X = (r.random((n, d)) * 10).astype(np.float32)
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    A, b = orc.fast_bin_matmul(X, B)
+    oh = np.zeros((n, m * 256))
+    for i in range(m):
+        oh[np.arange(n), i * 256 + B[:, i].astype(np.int64)] = 1
+    assert np.array_equal(A, oh.T @ oh + 1e-4 * np.eye(m * 256))
+    assert np.allclose(b.T, oh.T @ X.astype(np.float64), rtol=1e-12)
+    # the reference's own test: update_codebooks_fast_bin ~ update_codebooks_fast_bin2 (inv(A)*b), chainq.jl:2-11
+    C1 = orc.update_codebooks_fast_bin(X, B)
+    C2 = (np.linalg.inv(A) @ b.T).astype(np.float32)
+    assert np.allclose(C1, C2, rtol=1e-4, atol=1e-5)
+    # and it is the least-squares minimiser: no worse than the mean-of-assigned-vectors initialisation
+    assert np.linalg.norm(oh @ C1 - X) <= np.linalg.norm(oh @ C2 - X) * (1 + 1e-6)
