@@ -117,6 +117,13 @@ int rayuela_topk_merge(const float* dists_in, const int32_t* idx_in, int S, int 
 int rayuela_quantize_pq(const float* X, const float* Cpq, int64_t n, int d, int m, int h, uint8_t* B,
                         unsigned flags, void* stream);
 
+/* ---- norm quantization ("next" row 2) ------------------------------------------------------------------- */
+/* Replaces quantize_norms (src/utils.jl:29-59): norms_out[i] = ||sum_k C_k[:, b_k]||^2 (reconstruct + sequential
+ * sum of squares) and norm_codes[i] = first-minimum argmin_c (norm - cbnorms[c])^2 over the 256 norm centroids
+ * (0-based).  cbnorms / norm_codes may be NULL to get the norms only (what get_norms_codebook, :4-26, clusters). */
+int rayuela_quantize_norms(const uint8_t* B, const float* C, const float* cbnorms, int64_t n, int d, int m, int h,
+                           uint8_t* norm_codes, float* norms_out, unsigned flags, void* stream);
+
 /* ---- codebook update, data-parallel half ("next" row 1) ------------------------------------------------- */
 /* Replaces fast_bin_matmul (src/codebook_update.jl:96-171), the O(n) part of update_codebooks_fast_bin
  * (:175-204): A = B'B + rho*I ((m*h)-by-(m*h) double, symmetric) and b = B'X' ((m*h)-by-d double, column-major).

@@ -249,3 +249,17 @@ def update_codebooks_fast_bin(X, B, h=256, rho=1e-4):
     A, b = fast_bin_matmul(X, B, h, rho)
     C = lu_solve(lu_factor(A), b.T)          # (m*h, d)
     return C.astype(np.float32)
+
+
+def quantize_norms(B, C, cbnorms=None, h=256):
+    """quantize_norms restatement: returns (norm_codes uint8 0-based or None, norms float32)."""
+    B = np.ascontiguousarray(B, dtype=np.uint8)
+    C = _f32(C)
+    n, m = B.shape
+    d = C.shape[1]
+    norms = np.empty(n, dtype=np.float32)
+    codes = np.empty(n, dtype=np.uint8) if cbnorms is not None else None
+    cb = _f32(cbnorms) if cbnorms is not None else None
+    lib().orc_quantize_norms(_p(B, _u8p), _p(C, _f32p), _p(cb, _f32p) if cb is not None else None, ct.c_int64(n), d,
+                             m, h, _p(codes, _u8p) if codes is not None else None, _p(norms, _f32p))
+    return codes, norms

@@ -406,3 +406,30 @@ void orc_fast_bin_matmul(const float* X, const uint8_t* B, int64_t n, int d, int
     }
   for (size_t r = 0; r < mh; r++) A[r * mh + r] += rho;
 }
+
+/* quantize_norms (src/utils.jl:29-59): reconstruct (src/qerrors.jl:6-33) accumulates the codebook entries from
+ * +0 in codebook order; the norm is the sum of squares (the reference's @simd leaves the order open; fixed to
+ * sequential, unfused); code = first minimum of (norm - cbnorms[c])^2 (findmin). cbnorms/codes may be NULL. */
+void orc_quantize_norms(const uint8_t* B, const float* C, const float* cbnorms, int64_t n, int d, int m, int h,
+                        uint8_t* codes, float* norms) {
+#pragma omp parallel for schedule(static)
+  for (int64_t l = 0; l < n; l++) {
+    float nrm = 0.0f;
+    for (int t = 0; t < d; t++) {
+      float cb = 0.0f;
+      for (int k = 0; k < m; k++) cb += C[((size_t)k * h + B[l * m + k]) * d + t];
+      float sq = cb * cb;
+      nrm += sq;
+    }
+    if (norms) norms[l] = nrm;
+    if (cbnorms && codes) {
+      float best = 0; int bi = 0;
+      for (int c = 0; c < h; c++) {
+        float df = nrm - cbnorms[c];
+        float v = df * df;
+        if (c == 0 || v < best) { best = v; bi = c; }
+      }
+      codes[l] = (uint8_t)bi;
+    }
+  }
+}

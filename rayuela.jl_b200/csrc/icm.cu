@@ -322,6 +322,51 @@ __global__ void __launch_bounds__(256) veccost_kernel(const float* __restrict__ 
   }
 }
 
+
+// "next" row 2: quantize_norms (src/utils.jl:29-59).  One warp per vector:
+// CB = sum_k C_k[:, b_k] from +0 in codebook order (reconstruct, src/qerrors.jl:6-33), norm = sequential sum
+// of CB[t]^2 (unfused), code = first minimum of (norm - cbnorms[c])^2 over the 256 norm centroids.
+template <int M>
+__global__ void __launch_bounds__(256) norms_kernel(const uint8_t* __restrict__ B, const float* __restrict__ C,
+                                                    const float* __restrict__ cbnorms, int64_t n, int d,
+                                                    uint8_t* __restrict__ codes, float* __restrict__ norms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * d;
+  for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < n; l += (int64_t)gridDim.x * nwarps) {
+    Code code = load_code<M>(B + (size_t)l * M);
+    for (int t = lane; t < d; t += 32) {
+      float cb = 0.f;
+#pragma unroll
+      for (int k = 0; k < M; k++) cb = __fadd_rn(cb, __ldg(C + ((size_t)k * kH + code.get(k)) * d + t));
+      sq[t] = __fmul_rn(cb, cb);
+    }
+    __syncwarp();
+    float nrm = 0.f;
+    for (int t = 0; t < d; t++) nrm = __fadd_rn(nrm, sq[t]);
+    __syncwarp();
+    if (norms && lane == 0) norms[l] = nrm;
+    if (cbnorms && codes) {
+      float bv = 0.f;
+      int bc = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int c = lane * 8 + r;
+        const float df = __fsub_rn(nrm, __ldg(cbnorms + c));
+        const float v = __fmul_rn(df, df);
+        if (r == 0 || v < bv) { bv = v; bc = c; }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+        int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+        if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+      }
+      if (lane == 0) codes[l] = (uint8_t)bc;
+    }
+  }
+}
+
 // deterministic two-stage sum in double (qerror = mean(veccost), src/qerrors.jl:69-74)
 __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ v, int64_t n, double* __restrict__ partial) {
   __shared__ double sh[256];
@@ -607,6 +652,46 @@ extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C,
   RYL_TRY(device_veccost(x_in.d, b_in.d, c_in.d, n, d, m, cd, s));
   if (mean_out) RYL_TRY(device_mean(cd, n, mean_out, s));
   RYL_TRY(cost_o.flush(s));
+  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  return RAYUELA_OK;
+}
+
+
+template <int M>
+static int launch_norms(const uint8_t* B, const float* C, const float* cbnorms, int64_t n, int d, uint8_t* codes,
+                        float* norms, cudaStream_t s) {
+  const int warps = 8;
+  size_t smem = (size_t)warps * d * sizeof(float);
+  RYL_ARG(smem <= 200 * 1024, "quantize_norms: d too large for shared memory");
+  RYL_CUDA(cudaFuncSetAttribute(norms_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)std::min<int64_t>((n + warps - 1) / warps, (int64_t)sm_count() * 8);
+  RYL_LAUNCH(norms_kernel<M>, grid, warps * 32, smem, s, B, C, cbnorms, n, d, codes, norms);
+  return RAYUELA_OK;
+}
+
+extern "C" int rayuela_quantize_norms(const uint8_t* B, const float* C, const float* cbnorms, int64_t n, int d, int m,
+                                      int h, uint8_t* norm_codes, float* norms_out, unsigned flags, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  RYL_ARG(h == kH && m >= 1 && m <= 16 && n >= 1 && d >= 1, "quantize_norms: bad shape (h must be 256, m in 1..16)");
+  RYL_ARG(B && C && (norm_codes || norms_out), "quantize_norms: null array");
+  RYL_ARG(!norm_codes || cbnorms, "quantize_norms: norm codes need the norms codebook");
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  InArg<uint8_t> b_in;
+  InArg<float> c_in, cb_in;
+  RYL_TRY(b_in.bind(B, (size_t)n * m, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)m * kH * d, dev, s));
+  RYL_TRY(cb_in.bind(cbnorms, (size_t)kH, dev, s));
+  OutArg<uint8_t> codes_o;
+  OutArg<float> norms_o;
+  RYL_TRY(codes_o.bind(norm_codes, (size_t)n, dev, s));
+  RYL_TRY(norms_o.bind(norms_out, (size_t)n, dev, s));
+  int rc = RAYUELA_OK;
+#define CALL(M) rc = launch_norms<M>(b_in.d, c_in.d, cb_in.d, n, d, codes_o.d, norms_o.d, s)
+  RYL_M_SWITCH(m, CALL)
+#undef CALL
+  RYL_TRY(rc);
+  RYL_TRY(codes_o.flush(s));
+  RYL_TRY(norms_o.flush(s));
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
   return RAYUELA_OK;
 }

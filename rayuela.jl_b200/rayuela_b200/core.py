@@ -313,3 +313,21 @@ def update_codebooks_fast_bin(X, B, rho=1e-4):
         return torch.linalg.lu_solve(lu, piv, bb.T.contiguous()).to(torch.float32).contiguous()
     from scipy.linalg import lu_factor, lu_solve
     return np.ascontiguousarray(lu_solve(lu_factor(A), bb.T).astype(np.float32))
+
+
+def quantize_norms(B, C, cbnorms=None):
+    """quantize_norms (src/utils.jl:29-59) on the GPU: (norm_codes u8 0-based or None, norms f32)."""
+    L = _lib.lib()
+    n, m = B.shape
+    d = C.shape[1]
+    a = _Args()
+    bp = a.inp(B, np.uint8, (n, m))
+    cp = a.inp(C, np.float32, (m * H, d))
+    cbp = a.inp(cbnorms, np.float32, (H,)) if cbnorms is not None else None
+    dev = _is_dev(B)
+    norms, npp = a.new(dev, np.float32, (n,), device=B.device if dev else None)
+    codes = cdp = None
+    if cbnorms is not None:
+        codes, cdp = a.new(dev, np.uint8, (n,), device=B.device if dev else None)
+    check(L.rayuela_quantize_norms(bp, cp, cbp, n, d, m, H, cdp, npp, a.flags, a.stream))
+    return codes, norms

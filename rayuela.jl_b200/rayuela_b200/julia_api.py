@@ -324,3 +324,48 @@ def train_sr_cuda(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, met
     objarray[niter] = qerror(RX, B, C)                                                             # :169
     C = [R @ c for c in C]                                                                         # :172
     return C, B, objarray
+
+
+# ---- norm quantization ("next" row 2): produces the dbnorms linscan_lsq consumes ------------------------------
+def kmeans_1d(x, k, rng, maxiter=100):
+    """1-D k-means (k-means++ seeding, Lloyd) -- the role Clustering.kmeans(dbnorms, h) plays at
+    src/utils.jl:20.  The reference's result depends on Julia's global RNG and is not reproducible; this one is
+    seeded.  Returns (assignments 0-based, centers)."""
+    x = np.asarray(x, dtype=np.float64).reshape(-1)
+    n = x.size
+    centers = np.empty(k)
+    centers[0] = x[rng.integers(n)]
+    d2 = (x - centers[0]) ** 2
+    for i in range(1, k):
+        tot = d2.sum()
+        centers[i] = x[rng.integers(n)] if tot <= 0 else x[np.searchsorted(np.cumsum(d2), rng.random() * tot)]
+        d2 = np.minimum(d2, (x - centers[i]) ** 2)
+    for _ in range(maxiter):
+        centers.sort()
+        edges = (centers[1:] + centers[:-1]) / 2
+        a = np.searchsorted(edges, x)
+        sums = np.bincount(a, weights=x, minlength=k)
+        cnts = np.bincount(a, minlength=k)
+        new = np.where(cnts > 0, sums / np.maximum(cnts, 1), centers)
+        if np.allclose(new, centers, rtol=0, atol=1e-12):
+            centers = new
+            break
+        centers = new
+    centers.sort()
+    a = np.searchsorted((centers[1:] + centers[:-1]) / 2, x)
+    return a, centers.astype(np.float32)
+
+
+def get_norms_codebook(B, C):
+    """get_norms_codebook(B, C) -> norms_codes (1-based), norms_codebook   (src/utils.jl:4-26)."""
+    m = len(C)
+    assert np.shape(B)[0] == m
+    _, dbnorms = core.quantize_norms(_codes0(B), _hcat(C))            # reconstruct + sum of squares on the GPU
+    a, centers = kmeans_1d(dbnorms, np.shape(C[0])[1], np.random.default_rng(_next_seed() & 0xFFFFFFFF))
+    return (a + 1).astype(np.int16), centers
+
+
+def quantize_norms(B, C, cbnorms):
+    """quantize_norms(B, C, cbnorms) -> dbnormsB (1-based), dbnormsX   (src/utils.jl:29-59)."""
+    codes, norms = core.quantize_norms(_codes0(B), _hcat(C), np.asarray(cbnorms, dtype=np.float32))
+    return codes.astype(np.int16) + 1, norms

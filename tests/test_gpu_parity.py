@@ -353,3 +353,45 @@ def test_train_lsq_and_sr_run_end_to_end(rb):
     assert obj2.shape == (5,) and obj2[-1] < obj2[0]
     C3, B3, obj3 = rb.train_sr_cuda(X, m, h, R, B0, C0, 3, 2, 2, True, 2, "SR_C", 1, 0.5, 1, False)
     assert obj3[-1] < obj3[0]
+
+
+# ---- "next" row 2: norm quantization, and the demo pipeline around it ---------------------------------------
+@pytest.mark.parametrize("n,d,m", [(20000, 128, 7), (3001, 30, 16), (1, 8, 1)])
+def test_quantize_norms_bit_exact(rb, n, d, m):
+    r = np.random.default_rng(n + m)
+    C = r.standard_normal((m * 256, d)).astype(np.float32)
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    cb = np.sort(r.random(256) * 4 * d).astype(np.float32)
+    cb[10] = cb[11]                                         # duplicate centroid: first-min must pick the lower one
+    c0, n0 = orc.quantize_norms(B, C, cb)
+    c1, n1 = rb.core.quantize_norms(B, C, cb)
+    assert np.array_equal(bits(n1), bits(n0)) and np.array_equal(c1, c0)
+    _, n2 = rb.core.quantize_norms(B, C)
+    assert np.array_equal(bits(n2), bits(n0))
+
+
+def test_lsq_demo_pipeline(rb):
+    """experiment_lsq_cuda's tail (src/LSQ_GPU.jl:348-366): norms codebook -> encode base -> quantize_norms ->
+    linscan_lsq with the QUANTISED norms -> eval_recall."""
+    d, n, m, h, nq, k = 32, 8000, 7, 256, 64, 50
+    r = np.random.default_rng(4)
+    basis = r.standard_normal((d, d)) * (np.arange(1, d + 1) ** -0.8)[:, None]
+    X = np.asfortranarray((basis.T @ r.standard_normal((d, n))).astype(np.float32))
+    Xq = np.asfortranarray((X[:, :nq] + 0.02 * r.standard_normal((d, nq))).astype(np.float32))
+    rb.seed_b200(11)
+    C0 = [np.zeros((d, h), dtype=np.float32) for _ in range(m)]
+    C, B, _ = rb.train_lsq(X, m, h, np.eye(d, dtype=np.float32), r.integers(1, h + 1, (m, n)).astype(np.int16), C0,
+                           3, 2, 3, True, 2, True, False)
+    norms_B, norms_C = rb.get_norms_codebook(B, C)
+    assert norms_C.shape == (h,) and norms_B.min() >= 1 and norms_B.max() <= h
+    B_base = rb.encode_icm_cuda(X, r.integers(1, h + 1, (m, n)).astype(np.int16), C, [8], 3, 2, True, 1, False)[0][-1]
+    base_norms_B, db_norms_X = rb.quantize_norms(B_base, C, norms_C)
+    Cimg = np.concatenate([c.T for c in C])
+    c0, n0 = orc.quantize_norms((B_base.T - 1).astype(np.uint8), Cimg, norms_C)
+    assert np.array_equal(base_norms_B - 1, c0) and np.array_equal(bits(db_norms_X), bits(n0))
+    db_norms = norms_C[base_norms_B - 1]
+    dists, idx = rb.linscan_lsq(B_base, Xq, C, db_norms, np.eye(d, dtype=np.float32), k)
+    d0, i0 = orc.linscan(orc.LSQ, (B_base.T - 1).astype(np.uint8), Xq.T, Cimg, k, db_norms)
+    assert np.array_equal(idx.T.astype(np.int64), i0) and np.array_equal(bits(dists.T), bits(d0))
+    recall = rb.eval_recall(np.arange(1, nq + 1, dtype=np.uint32), idx, k, V=False)
+    assert recall[-1] > 0.8
