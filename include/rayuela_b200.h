@@ -117,6 +117,16 @@ int rayuela_topk_merge(const float* dists_in, const int32_t* idx_in, int S, int 
 int rayuela_quantize_pq(const float* X, const float* Cpq, int64_t n, int d, int m, int h, uint8_t* B,
                         unsigned flags, void* stream);
 
+/* ---- ChainQ Viterbi encode ("next" row 3) ----------------------------------------------------------------- */
+/* Replaces quantize_chainq (src/ChainQ.jl:287-348): unaries, chain tables 2*C[i]'*C[i+1], exact min-sum Viterbi
+ * over the m-chain (first-minimum ties as src/ChainQ.jl:97-110 / deps/src/encode_icm.cpp:108-118), back-trace.
+ * B out: m-by-n uint8, 0-based. */
+int rayuela_quantize_chainq(const float* X, const float* C, int64_t n, int d, int m, int h, uint8_t* B,
+                            unsigned flags, void* stream);
+/* Exact-signature replacement of the reference symbol (deps/src/encode_icm.cpp:170-178; src/ChainQ.jl:26-28):
+ * unaries = vcat(unaries...) ((m*256)-by-n), binaries = hcat(binaries...) (256-by-256*(m-1)); host pointers. */
+void viterbi_encoding(unsigned char* B, float* unaries, float* binaries, int n, int m);
+
 /* ---- norm quantization ("next" row 2) ------------------------------------------------------------------- */
 /* Replaces quantize_norms (src/utils.jl:29-59): norms_out[i] = ||sum_k C_k[:, b_k]||^2 (reconstruct + sequential
  * sum of squares) and norm_codes[i] = first-minimum argmin_c (norm - cbnorms[c])^2 over the 256 norm centroids

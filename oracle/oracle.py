@@ -263,3 +263,29 @@ def quantize_norms(B, C, cbnorms=None, h=256):
     lib().orc_quantize_norms(_p(B, _u8p), _p(C, _f32p), _p(cb, _f32p) if cb is not None else None, ct.c_int64(n), d,
                              m, h, _p(codes, _u8p) if codes is not None else None, _p(norms, _f32p))
     return codes, norms
+
+
+VITERBI_FN = ct.CFUNCTYPE(None, _u8p, _f32p, _f32p, ct.c_int, ct.c_int)
+
+
+def viterbi_encoding(unaries, binaries, m, use_ref=False):
+    """viterbi_encoding with the reference's argument layout: unaries (n, m*256), binaries (m-1, 256, 256) with
+    binaries[i][j, k] = cost of going from state k of codebook i to state j of codebook i+1."""
+    U = _f32(unaries)
+    bb = _f32(binaries)
+    n = U.shape[0]
+    B = np.zeros((n, m), dtype=np.uint8)
+    fn = ref("encode_icm").viterbi_encoding if use_ref else lib().orc_viterbi_encoding
+    fn(_p(B, _u8p), _p(U, _f32p), _p(bb, _f32p), ct.c_int(n), ct.c_int(m))
+    return B
+
+
+def quantize_chainq(X, C, m, h=256, use_ref=False):
+    X, C = _f32(X), _f32(C)
+    n, d = X.shape
+    B = np.zeros((n, m), dtype=np.uint8)
+    fn = lib().orc_quantize_chainq
+    fn.argtypes = [_f32p, _f32p, ct.c_int64, ct.c_int, ct.c_int, ct.c_int, _u8p, VITERBI_FN]
+    vit = ct.cast(ref("encode_icm").viterbi_encoding, VITERBI_FN) if use_ref else ct.cast(None, VITERBI_FN)
+    fn(_p(X, _f32p), _p(C, _f32p), n, d, m, h, _p(B, _u8p), vit)
+    return B

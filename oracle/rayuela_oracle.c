@@ -433,3 +433,64 @@ void orc_quantize_norms(const uint8_t* B, const float* C, const float* cbnorms, 
     }
   }
 }
+
+/* viterbi_encoding (deps/src/encode_icm.cpp:63-152; Julia twin src/ChainQ.jl:36-128): exact min-sum Viterbi on
+ * the chain.  unaries n-by-(m*H) (vector-major), binaries (m-1) tables bb[j*H + k] = cost of k -> j.
+ * Same signature as the reference symbol.  PINNED against oracle/_ref/encode_icm.so (tests/test_oracle.py). */
+void orc_viterbi_encoding(unsigned char* B, float* unaries, float* binaries, int n, int m) {
+  const int H = H256;
+#pragma omp parallel
+  {
+    float* U = (float*)malloc(sizeof(float) * m * H);
+    float* mincost = (float*)calloc(H, sizeof(float));
+    int* minidx = (int*)calloc((size_t)m * H, sizeof(int));
+#pragma omp for schedule(static)
+    for (int idx = 0; idx < n; idx++) {
+      for (int i = 0; i < m * H; i++) U[i] = unaries[(size_t)idx * H * m + i];
+      for (int i = 0; i < m - 1; i++) {
+        if (i > 0) for (int j = 0; j < H; j++) U[i * H + j] += mincost[j];
+        const float* bb = binaries + (size_t)H * H * i;
+        float newcost[H256];
+        for (int j = 0; j < H; j++) {
+          float minv = U[i * H] + bb[j * H];
+          int mini = 0;
+          for (int k = 1; k < H; k++) {
+            float c = U[i * H + k] + bb[j * H + k];
+            if (c < minv) { minv = c; mini = k; }
+          }
+          newcost[j] = minv;
+          minidx[i * H + j] = mini;
+        }
+        memcpy(mincost, newcost, sizeof(newcost));
+      }
+      if (m > 1) for (int j = 0; j < H; j++) U[(m - 1) * H + j] += mincost[j];
+      float minv = U[(m - 1) * H];
+      int state = 0;
+      for (int j = 1; j < H; j++) if (U[(m - 1) * H + j] < minv) { minv = U[(m - 1) * H + j]; state = j; }
+      B[(size_t)idx * m + (m - 1)] = (unsigned char)state;
+      for (int i = m - 2; i >= 0; i--) { state = minidx[i * H + state]; B[(size_t)idx * m + i] = (unsigned char)state; }
+    }
+    free(U); free(mincost); free(minidx);
+  }
+}
+
+/* quantize_chainq (src/ChainQ.jl:287-348): unaries (get_unaries), binaries[i] = 2*C[i]'*C[i+1] (:303-306), Viterbi.
+ * vit: orc_viterbi_encoding or the reference's own symbol. */
+typedef void (*viterbi_fn)(unsigned char*, float*, float*, int, int);
+void orc_quantize_chainq(const float* X, const float* C, int64_t n, int d, int m, int h, uint8_t* B, viterbi_fn vit) {
+  size_t hh = (size_t)h * h;
+  float* U = (float*)malloc(sizeof(float) * (size_t)m * n * h);       /* [j][l][c] as the reference holds them */
+  float* U2 = (float*)malloc(sizeof(float) * (size_t)m * n * h);      /* vcat(unaries...): [l][j][c] */
+  float* bin = (float*)malloc(sizeof(float) * hh * (m > 1 ? m - 1 : 1));
+  orc_get_unaries(X, C, n, d, m, h, U);
+  for (int64_t l = 0; l < n; l++)
+    for (int j = 0; j < m; j++)
+      memcpy(U2 + ((size_t)l * m + j) * h, U + ((size_t)j * n + l) * h, sizeof(float) * h);
+  for (int i = 0; i + 1 < m; i++)
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < h; b++)
+      for (int a = 0; a < h; a++)
+        bin[(size_t)i * hh + (size_t)b * h + a] = 2.0f * dot_seq(C + ((size_t)i * h + a) * d, C + ((size_t)(i + 1) * h + b) * d, d);
+  (vit ? vit : orc_viterbi_encoding)(B, U2, bin, (int)n, m);
+  free(U); free(U2); free(bin);
+}

@@ -367,6 +367,103 @@ __global__ void __launch_bounds__(256) norms_kernel(const uint8_t* __restrict__ 
   }
 }
 
+// "next" row 3: ChainQ Viterbi encode (quantize_chainq, src/ChainQ.jl:36-128; C++ twin
+// deps/src/encode_icm.cpp:63-152).  Block = 256 threads (one per destination state j) x VB vectors.
+// Forward pass i = 0..m-2: cost[k] = U_i[k] + bb_i[k -> j], first-minimum over ascending k (strict <);
+// mincost[j] is added to U_{i+1}[j] (:97-100,123-125); final first-minimum over U_{m-1}; back-trace.
+// TT[i] is the transposed chain table, TT[i][k*256 + j] = 2<C_i[:,k], C_{i+1}[:,j]>, so the block's reads are
+// coalesced over j and every table element is read once per VB vectors.
+template <int VB>
+__global__ void __launch_bounds__(256) viterbi_kernel(const float* __restrict__ U, const float* __restrict__ TT,
+                                                      int64_t tt_stride, int64_t n, int m,
+                                                      uint8_t* __restrict__ B) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* ucur = reinterpret_cast<float*>(smem_raw);                      // [VB][256]
+  uint8_t* minidx = reinterpret_cast<uint8_t*>(ucur + VB * kH);          // [VB][m-1][256]
+  __shared__ float red_v[8][VB];
+  __shared__ int red_i[8][VB];
+  const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+  for (int64_t v0 = (int64_t)blockIdx.x * VB; v0 < n; v0 += (int64_t)gridDim.x * VB) {
+    float carry[VB];                                                     // mincost[j] of the previous stage
+#pragma unroll
+    for (int v = 0; v < VB; v++) carry[v] = 0.f;
+    for (int i = 0; i < m; i++) {
+      // U_i[j] (+ mincost[j] for i > 0: "add the precomputed costs")
+      float ui[VB];
+#pragma unroll
+      for (int v = 0; v < VB; v++) {
+        const int64_t l = min(v0 + v, n - 1);
+        const float u = U[((size_t)l * m + i) * kH + j];
+        ui[v] = i > 0 ? __fadd_rn(u, carry[v]) : u;
+      }
+      if (i == m - 1) {
+        // final first-minimum over j, then the backward trace (one thread per vector)
+#pragma unroll
+        for (int v = 0; v < VB; v++) {
+          float bv = ui[v];
+          int bj = j;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            int oj = __shfl_xor_sync(0xffffffffu, bj, off);
+            if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+          }
+          if (lane == 0) { red_v[warp][v] = bv; red_i[warp][v] = bj; }
+        }
+        __syncthreads();
+        if (j < VB && v0 + j < n) {
+          float bv = red_v[0][j];
+          int bj = red_i[0][j];
+          for (int w = 1; w < 8; w++)
+            if (red_v[w][j] < bv || (red_v[w][j] == bv && red_i[w][j] < bj)) { bv = red_v[w][j]; bj = red_i[w][j]; }
+          uint8_t* out = B + (size_t)(v0 + j) * m;
+          int state = bj;
+          out[m - 1] = (uint8_t)state;
+          for (int ii = m - 2; ii >= 0; ii--) {
+            state = minidx[((size_t)j * (m - 1) + ii) * kH + state];
+            out[ii] = (uint8_t)state;
+          }
+        }
+        __syncthreads();
+        break;
+      }
+#pragma unroll
+      for (int v = 0; v < VB; v++) ucur[v * kH + j] = ui[v];
+      __syncthreads();
+      const float* tt = TT + (size_t)i * tt_stride;
+      float best[VB];
+      int bi[VB];
+#pragma unroll 4
+      for (int k = 0; k < kH; k++) {
+        const float t = __ldg(tt + (size_t)k * kH + j);
+#pragma unroll
+        for (int v = 0; v < VB; v++) {
+          const float c = __fadd_rn(ucur[v * kH + k], t);
+          if (k == 0 || c < best[v]) { best[v] = c; bi[v] = k; }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VB; v++) {
+        carry[v] = best[v];
+        minidx[((size_t)v * (m - 1) + i) * kH + j] = (uint8_t)bi[v];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// bb[i][j*256 + k] (the reference's binaries[i], column-major h-by-h) -> TT[i][k*256 + j]
+__global__ void transpose_tables_kernel(const float* __restrict__ in, float* __restrict__ out, int count) {
+  __shared__ float tile[32][33];
+  const float* src = in + (size_t)blockIdx.z * kH * kH;
+  float* dst = out + (size_t)blockIdx.z * kH * kH;
+  const int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) tile[r][threadIdx.x] = src[(size_t)(y0 + r) * kH + x];
+  __syncthreads();
+  const int xo = blockIdx.y * 32 + threadIdx.x, yo0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) dst[(size_t)(yo0 + r) * kH + xo] = tile[threadIdx.x][r];
+}
+
 // deterministic two-stage sum in double (qerror = mean(veccost), src/qerrors.jl:69-74)
 __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ v, int64_t n, double* __restrict__ partial) {
   __shared__ double sh[256];
@@ -694,6 +791,83 @@ extern "C" int rayuela_quantize_norms(const uint8_t* B, const float* C, const fl
   RYL_TRY(norms_o.flush(s));
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
   return RAYUELA_OK;
+}
+
+static int launch_viterbi(const float* U, const float* TT, int64_t tt_stride, int64_t n, int m, uint8_t* B,
+                          cudaStream_t s) {
+  constexpr int VB = 8;
+  size_t smem = (size_t)VB * kH * sizeof(float) + (size_t)VB * std::max(m - 1, 1) * kH;
+  RYL_CUDA(cudaFuncSetAttribute(viterbi_kernel<VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (int)std::min<int64_t>((n + VB - 1) / VB, (int64_t)sm_count() * 6);
+  RYL_LAUNCH(viterbi_kernel<VB>, grid, 256, smem, s, U, TT, tt_stride, n, m, B);
+  return RAYUELA_OK;
+}
+
+extern "C" int rayuela_quantize_chainq(const float* X, const float* C, int64_t n, int d, int m, int h, uint8_t* B,
+                                       unsigned flags, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  RYL_ARG(h == kH, "quantize_chainq: only codebooks with 256 entries are supported (src/ChainQ.jl:18-21)");
+  RYL_ARG(m >= 1 && m <= 16 && n >= 1 && d >= 1, "quantize_chainq: bad shape (m in 1..16)");
+  RYL_ARG(X && C && B, "quantize_chainq: null array");
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  const int mh = m * kH;
+  InArg<float> x_in, c_in;
+  RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)mh * d, dev, s));
+  OutArg<uint8_t> b_out;
+  RYL_TRY(b_out.bind(B, (size_t)n * m, dev, s));
+  DevBuf nrm_d, T_d, U_d;
+  RYL_TRY(nrm_d.alloc((size_t)mh * sizeof(float), s));
+  RYL_LAUNCH(sqnorm_kernel, (mh + 255) / 256, 256, 0, s, c_in.d, d, mh, nrm_d.as<float>());
+  RYL_TRY(T_d.alloc((size_t)m * m * kH * kH * sizeof(float), s));
+  if (m > 1) RYL_LAUNCH(tables_kernel, dim3(kH / 32, kH / 32, m * m), 256, 0, s, c_in.d, T_d.as<float>(), d, m);
+  const int64_t per_vec = (int64_t)mh * sizeof(float);
+  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
+  RYL_TRY(U_d.alloc((size_t)std::min(chunk, n) * per_vec, s));
+  // chain table i -> i+1 with k (state of i) major: T[(i+1)*m + i][b = k][c = j] = 2<C_{i+1}[:,j], C_i[:,k]>
+  const float* TT = T_d.as<float>() + (size_t)(1 * m + 0) * kH * kH;
+  const int64_t tt_stride = (int64_t)(m + 1) * kH * kH;
+  for (int64_t l0 = 0; l0 < n; l0 += chunk) {
+    const int64_t nc = std::min(chunk, n - l0);
+    dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
+    if (d % 4 == 0)
+      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
+                 U_d.as<float>(), nc, d, mh);
+    else
+      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
+                 U_d.as<float>(), nc, d, mh);
+    RYL_TRY(launch_viterbi(U_d.as<float>(), TT, tt_stride, nc, m, b_out.d + (size_t)l0 * m, s));
+  }
+  RYL_TRY(b_out.flush(s));
+  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  return RAYUELA_OK;
+}
+
+// exact-signature compat for the reference symbol (deps/src/encode_icm.cpp:170-178, called at src/ChainQ.jl:26-28)
+extern "C" void viterbi_encoding(unsigned char* B, float* unaries, float* binaries, int n, int m) {
+  auto body = [&]() -> int {
+    cudaStream_t s = nullptr;
+    RYL_ARG(m >= 1 && m <= 16 && n >= 1, "viterbi_encoding: bad shape");
+    InArg<float> u_in, b_in;
+    RYL_TRY(u_in.bind(unaries, (size_t)n * m * kH, false, s));
+    RYL_TRY(b_in.bind(binaries, (size_t)std::max(m - 1, 1) * kH * kH, false, s));
+    OutArg<uint8_t> b_out;
+    RYL_TRY(b_out.bind(B, (size_t)n * m, false, s));
+    DevBuf tt;
+    RYL_TRY(tt.alloc((size_t)std::max(m - 1, 1) * kH * kH * sizeof(float), s));
+    if (m > 1)
+      RYL_LAUNCH(transpose_tables_kernel, dim3(kH / 32, kH / 32, m - 1), dim3(32, 8), 0, s, b_in.d, tt.as<float>(),
+                 m - 1);
+    RYL_TRY(launch_viterbi(u_in.d, tt.as<float>(), (int64_t)kH * kH, n, m, b_out.d, s));
+    RYL_TRY(b_out.flush(s));
+    RYL_CUDA(cudaStreamSynchronize(s));
+    return RAYUELA_OK;
+  };
+  int rc = body();
+  if (rc != RAYUELA_OK) {
+    fprintf(stderr, "librayuela_b200: viterbi_encoding failed (%d): %s\n", rc, rayuela_last_error());
+    abort();
+  }
 }
 
 extern "C" void condition(unsigned char* B, float* ub, float* binaries, float* binaries_t, int* cbpair2binaryidx,

@@ -9,7 +9,7 @@ No CPU fallback exists: importing is cheap, but every call needs the built libra
 from . import core, julia_api, xvecs  # noqa: F401
 from .xvecs import bvecs_read, fvecs_read, fvecs_write, ivecs_read, ivecs_write  # noqa: F401
 from ._lib import LIB_PATH, RayuelaError, launch_count  # noqa: F401
-from .julia_api import (get_norms_codebook, quantize_norms,  # noqa: F401
+from .julia_api import (get_norms_codebook, quantize_chainq, quantize_norms,  # noqa: F401
                         SR_C_perturb, SR_D_perturb, apply_schedule, encode_icm_cuda, encoding_icm,  # noqa: F401
                         eval_recall, linscan_cq, linscan_lsq, linscan_opq, linscan_pq, qerror, qerror_opq,
                         qerror_pq, quantize_opq, quantize_pq, seed_b200, train_lsq, train_lsq_cuda, train_sr_cuda,

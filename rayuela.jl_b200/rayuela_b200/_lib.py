@@ -34,6 +34,8 @@ SIGNATURES = {
     "rayuela_index_free": (_int, [_vp]),
     "rayuela_topk_merge": (_int, [_vp, _vp, _int, _int, _int, _vp, _vp, ct.c_uint, _vp]),
     "rayuela_quantize_pq": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, ct.c_uint, _vp]),
+    "rayuela_quantize_chainq": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, ct.c_uint, _vp]),
+    "viterbi_encoding": (None, [_vp, _vp, _vp, _int, _int]),
     "rayuela_quantize_norms": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, ct.c_uint, _vp]),
     "rayuela_fast_bin_matmul": (_int, [_vp, _vp, _i64, _int, _int, _int, ct.c_double, _vp, _vp, ct.c_uint, _vp]),
 }

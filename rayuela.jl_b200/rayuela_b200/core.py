@@ -331,3 +331,24 @@ def quantize_norms(B, C, cbnorms=None):
         codes, cdp = a.new(dev, np.uint8, (n,), device=B.device if dev else None)
     check(L.rayuela_quantize_norms(bp, cp, cbp, n, d, m, H, cdp, npp, a.flags, a.stream))
     return codes, norms
+
+
+def quantize_chainq(X, C, m):
+    """quantize_chainq (src/ChainQ.jl:287-348) on the GPU: exact Viterbi over the chain.  Returns B (n, m) u8."""
+    L = _lib.lib()
+    n, d = X.shape
+    a = _Args()
+    xp = a.inp(X, np.float32, (n, d))
+    cp = a.inp(C, np.float32, (m * H, d))
+    B, bp = a.new(_is_dev(X), np.uint8, (n, m), device=X.device if _is_dev(X) else None)
+    check(L.rayuela_quantize_chainq(xp, cp, n, d, m, H, bp, a.flags, a.stream))
+    return B
+
+
+def c_viterbi_encoding(unaries, binaries, m):
+    """`viterbi_encoding` as src/ChainQ.jl:26-28 calls it (host arrays): unaries (n, m*256), binaries (m-1,256,256)."""
+    U, bb = _np(unaries, np.float32), _np(binaries, np.float32)
+    n = U.shape[0]
+    B = np.zeros((n, m), dtype=np.uint8)
+    _lib.lib().viterbi_encoding(B.ctypes.data, U.ctypes.data, bb.ctypes.data, n, m)
+    return B

@@ -369,3 +369,13 @@ def quantize_norms(B, C, cbnorms):
     """quantize_norms(B, C, cbnorms) -> dbnormsB (1-based), dbnormsX   (src/utils.jl:29-59)."""
     codes, norms = core.quantize_norms(_codes0(B), _hcat(C), np.asarray(cbnorms, dtype=np.float32))
     return codes.astype(np.int16) + 1, norms
+
+
+# ---- ChainQ Viterbi encode ("next" row 3) --------------------------------------------------------------------
+def quantize_chainq(X, C, use_cuda=False, use_cpp=False):
+    """quantize_chainq(X, C, use_cuda=false, use_cpp=false) -> B, ellapsed   (src/ChainQ.jl:287-348).
+    The three reference implementations give identical codes (test/chainq.jl:27-39); here there is one."""
+    import time
+    t0 = time.perf_counter()
+    B0 = core.quantize_chainq(_img(X), _hcat(C), len(C))
+    return _codes1(B0), time.perf_counter() - t0

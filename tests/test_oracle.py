@@ -179,3 +179,29 @@ def test_fast_bin_matmul_against_numpy():
     assert np.allclose(C1, C2, rtol=1e-4, atol=1e-5)
     # and it is the least-squares minimiser: no worse than the mean-of-assigned-vectors initialisation
     assert np.linalg.norm(oh @ C1 - X) <= np.linalg.norm(oh @ C2 - X) * (1 + 1e-6)
+
+
+@needs_ref
+@pytest.mark.parametrize("m", [4, 8, 2])
+def test_viterbi_matches_reference_bitwise(m):
+    """test/chainq.jl:27-39 shape (d=32, n=1000, uniform data): restated Viterbi == the reference's own C++."""
+    orc.build()
+    n, d = 1000, 32
+    X, C, _ = _data(n, d, m, seed=40 + m, kind="uniform")
+    a = orc.quantize_chainq(X, C, m)
+    b = orc.quantize_chainq(X, C, m, use_ref=True)
+    assert np.array_equal(a, b)
+    # Viterbi is exact: no single-code change can lower the chain objective
+    U = orc.get_unaries(X[:50], C, m)                      # [m][n][h]
+    Cm = C.reshape(m, 256, d).astype(np.float64)
+
+    def energy(codes, l):
+        e = sum(U[i, l, codes[i]] for i in range(m))
+        return e + sum(2 * Cm[i, codes[i]] @ Cm[i + 1, codes[i + 1]] for i in range(m - 1))
+    for l in range(0, 50, 7):
+        base = energy(a[l], l)
+        for i in range(m):
+            for c in range(0, 256, 17):
+                alt = a[l].copy()
+                alt[i] = c
+                assert energy(alt, l) >= base - 1e-2
