@@ -128,6 +128,7 @@ struct ScanParams {
   const float* lut;      // [nq][m*256]
   uint64_t* cand;        // [slices][nqtiles*QT][cap]
   uint64_t* part;        // [slices][nq][k] sorted keys (low word = local id)
+  const uint64_t* lb;    // [nq] or nullptr: only keys strictly greater than lb[q] qualify (k > one pass)
   int64_t n, slice_len;
   int nq, k, cap;
 };
@@ -148,9 +149,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanParams p) {
   uint64_t* sortbuf = reinterpret_cast<uint64_t*>(lut_s + QT * M * kH);    // [cap]
   __shared__ int cnt_s[QT];
   __shared__ float tau_s[QT];
+  __shared__ uint64_t lb_s[QT];
 
   const int q0 = blockIdx.x * QT;
   const int slice = blockIdx.y;
+  if (threadIdx.x < QT) lb_s[threadIdx.x] = p.lb ? p.lb[min(q0 + (int)threadIdx.x, p.nq - 1)] : 0ull;
   const int64_t begin = (int64_t)slice * p.slice_len;
   const int64_t end = min(p.n, begin + p.slice_len);
   uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * QT + (size_t)blockIdx.x * QT) * p.cap;
@@ -216,8 +219,11 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanParams p) {
           }
           if (NORMS) s = __fadd_rn(s, nrm);
           if (s <= tau[q]) {
-            int pos = atomicAdd(&cnt_s[q], 1);
-            cand[(size_t)q * p.cap + pos] = make_key(s, (uint32_t)i);
+            const uint64_t key = make_key(s, (uint32_t)i);
+            if (!p.lb || key > lb_s[q]) {
+              int pos = atomicAdd(&cnt_s[q], 1);
+              cand[(size_t)q * p.cap + pos] = key;
+            }
           }
         }
       }
@@ -377,6 +383,7 @@ struct Scan8Params {
   const float* lut;      // tiled [qtiles][32768]
   uint64_t* cand;        // [slices][qtiles*16][cap]
   uint64_t* part;        // [slices][nq][k]
+  const uint64_t* lb;    // [nq] or nullptr: only keys strictly greater than lb[q] qualify (k > one pass)
   int64_t n, nchunks, chunks_per_slice;
   int nq, k, cap, soft, rbmax;   // soft: compact a query's buffer once it holds more than this many keys
 };
@@ -404,9 +411,11 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __shared__ uint64_t lb_s[16];
   if (tid < 16) {
     cnt_s[tid] = 0;
     tau_s[tid] = __int_as_float(0x7f800000);
+    lb_s[tid] = p.lb ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
   }
   __syncthreads();
   if (tid == 0) {
@@ -580,8 +589,11 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
               for (int i = 0; i < 8; i++) {
                 if (dv[i] <= tau[i]) {
                   const int q = (i >> 1) * 4 + g * 2 + (i & 1);
-                  int pos = atomicAdd(&cnt_s[q], 1);
-                  cand[(size_t)q * p.cap + pos] = make_key(dv[i], id);
+                  const uint64_t key = make_key(dv[i], id);
+                  if (!p.lb || key > lb_s[q]) {
+                    int pos = atomicAdd(&cnt_s[q], 1);
+                    cand[(size_t)q * p.cap + pos] = key;
+                  }
                 }
               }
             }
@@ -638,7 +650,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
 __global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ din,
                                                     const int32_t* __restrict__ iin, int S, int nq, int k,
                                                     float* __restrict__ dout, int32_t* __restrict__ iout,
-                                                    int64_t id_add) {
+                                                    int64_t id_add, int ldo) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
   const int q = blockIdx.x;
@@ -656,9 +668,16 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__
   if (S > 1) block_bitonic_sort(s, np2);
   for (int t = threadIdx.x; t < k; t += blockDim.x) {
     uint64_t key = s[t];
-    dout[(size_t)q * k + t] = ordered_to_f32((uint32_t)(key >> 32));
-    iout[(size_t)q * k + t] = (int32_t)((int64_t)(uint32_t)key + id_add);
+    dout[(size_t)q * ldo + t] = ordered_to_f32((uint32_t)(key >> 32));
+    iout[(size_t)q * ldo + t] = (int32_t)((int64_t)(uint32_t)key + id_add);
   }
+}
+
+// lower bound for the next pass of a k > one-pass search: the last key the previous pass returned
+__global__ void lower_bound_kernel(const float* __restrict__ d, const int32_t* __restrict__ i, int nq, int ldo,
+                                   int col, int64_t id_add, uint64_t* __restrict__ lb) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nq) lb[q] = make_key(d[(size_t)q * ldo + col], (uint32_t)((int64_t)i[(size_t)q * ldo + col] - id_add));
 }
 
 }  // namespace ryl
@@ -768,11 +787,12 @@ extern "C" int rayuela_index_free(rayuela_index* ix) {
 }
 
 static int merge_lists(const uint64_t* keys, const float* din, const int32_t* iin, int S, int nq, int k, float* dout,
-                       int32_t* iout, int64_t id_add, cudaStream_t s) {
+                       int32_t* iout, int64_t id_add, cudaStream_t s, int ldo = 0) {
+  if (ldo == 0) ldo = k;
   size_t smem = (size_t)host_pow2ceil(S * k) * sizeof(uint64_t);
   RYL_ARG(smem <= 200 * 1024, "topk merge: S*k too large for a single pass (max 16384 keys... 25600)");
   RYL_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RYL_LAUNCH(merge_kernel, nq, 256, smem, s, keys, din, iin, S, nq, k, dout, iout, id_add);
+  RYL_LAUNCH(merge_kernel, nq, 256, smem, s, keys, din, iin, S, nq, k, dout, iout, id_add, ldo);
   return RAYUELA_OK;
 }
 
@@ -782,8 +802,6 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   RYL_ARG(ix != nullptr, "index_search: null index");
   RYL_ARG(nq >= 1 && d >= 1, "index_search: nq and d must be positive");
   RYL_ARG(k >= 1 && (int64_t)k <= ix->n, "index_search: k must be in 1..n");
-  RYL_ARG(k <= 4096, "index_search: k > 4096 is not supported yet");
-  RYL_ARG(ix->m <= 8 || k <= 3584, "index_search: k > 3584 is not supported for m > 8 yet");
   const int m = ix->m, mh = m * kH;
   const bool pq = ix->kind == RAYUELA_SCAN_PQ;
   RYL_ARG(!pq || d % m == 0, "index_search: PQ scan needs d divisible by m");
@@ -800,16 +818,10 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
 
   const bool v2 = m <= 8;                                   // conflict-free scan8_kernel
   const int QT = v2 ? 16 : scan_qt(m);
-  // v2: soft compaction limit 2k, hard limit = capacity minus what one round can add (256 codes per block-step)
-  int soft = std::max(512, 2 * k), rbmax = kScan8RBMax;
-  if (soft + 256 * kScan8RBMax > kScan8SortKeys) {
-    soft = k + (kScan8SortKeys - k) / 2;
-    rbmax = std::max(1, (kScan8SortKeys - soft) / 256);
-  }
-  const int cap = v2 ? soft + 256 * rbmax : host_pow2ceil(std::max(2 * kRound, 2 * k + kRound));
-  const size_t smem = v2 ? (size_t)kLutTileBytes + (size_t)kScan8SortKeys * sizeof(uint64_t)
-                         : (size_t)QT * mh * sizeof(float) + (size_t)cap * sizeof(uint64_t);
-  RYL_ARG(smem <= 227 * 1024, "index_search: shared-memory budget exceeded (k too large)");
+  // One pass returns at most kmax results per query (shared-memory selection buffer).  Larger k -- the reference's
+  // default is k = 10000 (src/Linscan.jl:10) -- takes ceil(k / kmax) passes: pass p keeps only keys strictly
+  // greater than the last key of pass p-1, which is exact because (dist, id) keys are a total order.
+  const int kmax = v2 ? 4096 : 3584;
   const int64_t id_add = (pq ? 0 : 1) + ix->id_offset;  // linscan_aqd.cpp:88 vs pairwise_byte.cpp:76
   const float* norms = ix->kind == RAYUELA_SCAN_LSQ ? ix->norms.as<float>() : nullptr;
 
@@ -817,22 +829,10 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   for (int qb = 0; qb < nq; qb += chunk_q) {
     const int nqc = std::min(chunk_q, nq - qb);
     const int qtiles = (nqc + QT - 1) / QT;
-    // DB slices: enough blocks for several waves, slices no shorter than 8 rounds, S*k within one merge pass
-    const int64_t unit = v2 ? (int64_t)kChunkCodes * kScan8Warps : kRound;   // codes per block round
-    int S = std::max(1, ((v2 && k <= 64 ? 6 : 2) * sm_count() + qtiles - 1) / qtiles);
-    S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (v2 ? unit : 8 * unit)));
-    S = std::min(S, std::max(1, 16384 / k));
-    int64_t slice_len = (ix->n + S - 1) / S;
-    slice_len = (slice_len + unit - 1) / unit * unit;
-    S = (int)((ix->n + slice_len - 1) / slice_len);
-
-    DevBuf lut, cand, part;
+    DevBuf lut, lb;
     const size_t lut_floats = v2 ? (size_t)qtiles * (kLutTileBytes / 4) : (size_t)nqc * mh;
     RYL_TRY(lut.alloc(lut_floats * sizeof(float), s));
     if (v2 && (m < 8 || nqc % 16)) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m
-    RYL_TRY(cand.alloc((size_t)S * qtiles * QT * cap * sizeof(uint64_t), s));
-    RYL_TRY(part.alloc((size_t)S * nqc * k * sizeof(uint64_t), s));
-
     dim3 lg(mh / 32, (nqc + 31) / 32);
     const float* qptr = q_in.d + (size_t)qb * d;
     const int tiled = v2 ? 1 : 0;
@@ -842,45 +842,77 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
     else
       RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
+    if (k > kmax) RYL_TRY(lb.alloc((size_t)nqc * sizeof(uint64_t), s));
 
-    if (v2) {
-      Scan8Params p;
-      p.W = ix->skew.as<uint64_t>();
-      p.norms = norms;
-      p.lut = lut.as<float>();
-      p.cand = cand.as<uint64_t>();
-      p.part = part.as<uint64_t>();
-      p.n = ix->n;
-      p.nchunks = ix->nchunks;
-      p.chunks_per_slice = slice_len / kChunkCodes;
-      p.nq = nqc;
-      p.k = k;
-      p.cap = cap;
-      p.soft = soft;
-      p.rbmax = rbmax;
-      if (norms) {
-        RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RYL_LAUNCH(scan8_kernel<true>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
-      } else {
-        RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RYL_LAUNCH(scan8_kernel<false>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
+    for (int koff = 0; koff < k; koff += kmax) {
+      const int kp = std::min(kmax, k - koff);
+      const uint64_t* lbp = koff > 0 ? lb.as<uint64_t>() : nullptr;
+      // v2: soft compaction limit 2k, hard limit = capacity minus what one round can add (256 codes per block-step)
+      int soft = std::max(512, 2 * kp), rbmax = kScan8RBMax;
+      if (soft + 256 * kScan8RBMax > kScan8SortKeys) {
+        soft = kp + (kScan8SortKeys - kp) / 2;
+        rbmax = std::max(1, (kScan8SortKeys - soft) / 256);
       }
-    } else {
-      ScanParams p;
-      p.codes = ix->codes.as<uint8_t>();
-      p.norms = norms;
-      p.lut = lut.as<float>();
-      p.cand = cand.as<uint64_t>();
-      p.part = part.as<uint64_t>();
-      p.n = ix->n;
-      p.slice_len = slice_len;
-      p.nq = nqc;
-      p.k = k;
-      p.cap = cap;
-      RYL_TRY(launch_scan(m, p, norms != nullptr, dim3(qtiles, S), smem, s));
+      const int cap = v2 ? soft + 256 * rbmax : host_pow2ceil(std::max(2 * kRound, 2 * kp + kRound));
+      const size_t smem = v2 ? (size_t)kLutTileBytes + (size_t)kScan8SortKeys * sizeof(uint64_t)
+                             : (size_t)QT * mh * sizeof(float) + (size_t)cap * sizeof(uint64_t);
+      RYL_ARG(smem <= 227 * 1024, "index_search: shared-memory budget exceeded");
+      // DB slices: enough blocks for several waves, slices no shorter than 8 rounds, S*k within one merge pass
+      const int64_t unit = v2 ? (int64_t)kChunkCodes * kScan8Warps : kRound;   // codes per block round
+      int S = std::max(1, ((v2 && kp <= 64 ? 6 : 2) * sm_count() + qtiles - 1) / qtiles);
+      S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (v2 ? unit : 8 * unit)));
+      S = std::min(S, std::max(1, 16384 / kp));
+      int64_t slice_len = (ix->n + S - 1) / S;
+      slice_len = (slice_len + unit - 1) / unit * unit;
+      S = (int)((ix->n + slice_len - 1) / slice_len);
+
+      DevBuf cand, part;
+      RYL_TRY(cand.alloc((size_t)S * qtiles * QT * cap * sizeof(uint64_t), s));
+      RYL_TRY(part.alloc((size_t)S * nqc * kp * sizeof(uint64_t), s));
+      if (v2) {
+        Scan8Params p;
+        p.W = ix->skew.as<uint64_t>();
+        p.norms = norms;
+        p.lut = lut.as<float>();
+        p.cand = cand.as<uint64_t>();
+        p.part = part.as<uint64_t>();
+        p.lb = lbp;
+        p.n = ix->n;
+        p.nchunks = ix->nchunks;
+        p.chunks_per_slice = slice_len / kChunkCodes;
+        p.nq = nqc;
+        p.k = kp;
+        p.cap = cap;
+        p.soft = soft;
+        p.rbmax = rbmax;
+        if (norms) {
+          RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          RYL_LAUNCH(scan8_kernel<true>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
+        } else {
+          RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          RYL_LAUNCH(scan8_kernel<false>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
+        }
+      } else {
+        ScanParams p;
+        p.codes = ix->codes.as<uint8_t>();
+        p.norms = norms;
+        p.lut = lut.as<float>();
+        p.cand = cand.as<uint64_t>();
+        p.part = part.as<uint64_t>();
+        p.lb = lbp;
+        p.n = ix->n;
+        p.slice_len = slice_len;
+        p.nq = nqc;
+        p.k = kp;
+        p.cap = cap;
+        RYL_TRY(launch_scan(m, p, norms != nullptr, dim3(qtiles, S), smem, s));
+      }
+      float* dq = d_out.d + (size_t)qb * k + koff;
+      int32_t* iq = i_out.d + (size_t)qb * k + koff;
+      RYL_TRY(merge_lists(part.as<uint64_t>(), nullptr, nullptr, S, nqc, kp, dq, iq, id_add, s, k));
+      if (koff + kp < k)
+        RYL_LAUNCH(lower_bound_kernel, (nqc + 255) / 256, 256, 0, s, dq, iq, nqc, k, kp - 1, id_add, lb.as<uint64_t>());
     }
-    RYL_TRY(merge_lists(part.as<uint64_t>(), nullptr, nullptr, S, nqc, k, d_out.d + (size_t)qb * k,
-                        i_out.d + (size_t)qb * k, id_add, s));
   }
   RYL_TRY(d_out.flush(s));
   RYL_TRY(i_out.flush(s));

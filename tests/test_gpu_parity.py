@@ -191,6 +191,19 @@ def test_scan_matches_reference(rb, kind, n, nq, m, k, ties):
     assert np.array_equal(bits(d1), bits(d0))
 
 
+@pytest.mark.parametrize("kind,m,k", [(orc.LSQ, 8, 10000), (orc.PQ, 16, 5000), (orc.CQ, 7, 4097)])
+def test_scan_large_k_multi_pass(rb, kind, m, k):
+    """k beyond one pass (the reference's default is k = 10000, src/Linscan.jl:10): several passes, each bounded
+    below by the last key of the previous one; tie-heavy data so pass boundaries fall inside runs of equal
+    distances."""
+    n, nq = 30000, 6
+    d = 16 * m if kind == orc.PQ else 32
+    B, Xq, cb, nrm = _scan_case(kind, n, nq, m, d, seed=k, ties=True)
+    d0, i0 = (orc.ref_linscan if orc.have_ref() else orc.linscan)(kind, B, Xq, cb, k, nrm)
+    d1, i1 = rb.core.Index(kind, B, nrm).search(Xq, cb, k)
+    assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0))
+
+
 def test_scan_compat_symbols(rb):
     for kind, fn in ((orc.PQ, "pq"), (orc.LSQ, "lsq"), (orc.CQ, "cq")):
         B, Xq, cb, nrm = _scan_case(kind, 20000, 9, 8, 128, seed=kind)
