@@ -71,39 +71,78 @@ __global__ void assemble_kernel(const unsigned int* __restrict__ counts, int m, 
   }
 }
 
+// Bt[i][l] = B[l][i], rows padded to a multiple of 16 with 0xFF... handled by the n bound in bxt_kernel.
+__global__ void transpose_codes_kernel(const uint8_t* __restrict__ B, uint8_t* __restrict__ Bt, int64_t n, int m,
+                                       int64_t ld) {
+  for (int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; l < n; l += (int64_t)gridDim.x * blockDim.x)
+    for (int i = 0; i < m; i++) Bt[(size_t)i * ld + l] = B[l * m + i];
+}
+
 // grid: (256 codes, m codebooks); block: 256 threads.  b is column-major (mh x d): b[t*mh + i*256 + c].
-__global__ void __launch_bounds__(256) bxt_kernel(const float* __restrict__ X, const uint8_t* __restrict__ B,
-                                                  int64_t n, int d, int m, double* __restrict__ b) {
-  __shared__ int list[256];
-  __shared__ int wcount[8];
-  __shared__ int total_s;
+// The block walks codebook i's code row 4096 codes at a time (one 16-byte load per thread, SIMD byte compare),
+// compacts the matching vector indices IN ASCENDING ORDER into shared memory, then every thread adds its
+// dimensions of those vectors sequentially in Float64 -- the reference's accumulation order (:151-161).
+__global__ void __launch_bounds__(256) bxt_kernel(const float* __restrict__ X, const uint8_t* __restrict__ Bt,
+                                                  int64_t ld, int64_t n, int d, int m, double* __restrict__ b) {
+  __shared__ int list[4096];
+  __shared__ int wsum[8];
   const int c = blockIdx.x, i = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const size_t mh = (size_t)m * kH;
-  // every thread owns dimensions tid, tid+256, ... (up to 8 => d <= 2048)
+  const uint8_t* row = Bt + (size_t)i * ld;
+  const unsigned pat = 0x01010101u * (unsigned)c;
   double acc[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) acc[r] = 0.0;
-  int fill = 0;
-  for (int64_t base = 0; base < n; base += 256) {
-    const int64_t l = base + tid;
-    const bool hit = l < n && B[l * m + i] == c;
-    const unsigned bal = __ballot_sync(0xffffffffu, hit);
-    if (lane == 0) wcount[w] = __popc(bal);
+  for (int64_t base = 0; base < n; base += 4096) {
+    const int64_t l0 = base + (int64_t)tid * 16;
+    unsigned hits = 0;                                    // bit e set: code l0 + e matches
+    if (l0 < n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(row + l0);   // ld is a multiple of 16 and padded
+      const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const unsigned eq = __vcmpeq4(wd[q], pat);        // 0xFF per equal byte
+        hits |= ((eq & 1u) | ((eq >> 7) & 2u) | ((eq >> 14) & 4u) | ((eq >> 21) & 8u)) << (4 * q);
+      }
+      if (l0 + 16 > n) hits &= (1u << (int)(n - l0)) - 1u;
+    }
+    const int cnt = __popc(hits);
+    int inc = cnt;                                        // inclusive scan over the block, in thread order
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
     __syncthreads();
-    int off = fill;
-    for (int ww = 0; ww < w; ww++) off += wcount[ww];
-    if (hit) list[off + __popc(bal & ((1u << lane) - 1u))] = (int)(l - base);
-    if (tid == 0) {
-      int t = fill;
-      for (int ww = 0; ww < 8; ww++) t += wcount[ww];
-      total_s = t;
+    int offs = inc - cnt, total = 0;
+    for (int ww = 0; ww < 8; ww++) {
+      if (ww < w) offs += wsum[ww];
+      total += wsum[ww];
+    }
+    while (hits) {
+      const int e = __ffs(hits) - 1;
+      hits &= hits - 1;
+      list[offs++] = tid * 16 + e;
     }
     __syncthreads();
-    fill = total_s;
-    // consume this window's matches (ascending l) before moving on: on average one match per 256 codes
-    if (fill > 0) {
-      for (int e = 0; e < fill; e++) {
+    if (d <= 256) {
+      // popular codes make this list long and the adds are one dependent Float64 chain per dimension: issue the
+      // row loads eight at a time so the chain is not also serialised on memory latency
+      if (tid < d) {
+        int e = 0;
+        for (; e + 8 <= total; e += 8) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = __ldg(X + (size_t)(base + list[e + u]) * d + tid);
+#pragma unroll
+          for (int u = 0; u < 8; u++) acc[0] += (double)v[u];
+        }
+        for (; e < total; e++) acc[0] += (double)__ldg(X + (size_t)(base + list[e]) * d + tid);
+      }
+    } else {
+      for (int e = 0; e < total; e++) {
         const float* x = X + (size_t)(base + list[e]) * d;
 #pragma unroll
         for (int r = 0; r < 8; r++) {
@@ -111,7 +150,6 @@ __global__ void __launch_bounds__(256) bxt_kernel(const float* __restrict__ X, c
           if (t < d) acc[r] += (double)x[t];
         }
       }
-      fill = 0;
     }
     __syncthreads();
   }
@@ -153,7 +191,12 @@ extern "C" int rayuela_fast_bin_matmul(const float* X, const uint8_t* B, int64_t
   RYL_CUDA(cudaFuncSetAttribute(cooc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   RYL_LAUNCH(cooc_kernel, dim3(npairs, slices), 512, smem, s, b_in.d, n, m, counts.as<unsigned int>(), per_slice);
   RYL_LAUNCH(assemble_kernel, npairs, 256, 0, s, counts.as<unsigned int>(), m, rho, a_out.d);
-  RYL_LAUNCH(bxt_kernel, dim3(kH, m), 256, 0, s, x_in.d, b_in.d, n, d, m, bb_out.d);
+  DevBuf bt;
+  const int64_t ld = (n + 15) / 16 * 16;
+  RYL_TRY(bt.alloc((size_t)m * ld, s));
+  RYL_LAUNCH(transpose_codes_kernel, (int)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, s, b_in.d,
+             bt.as<uint8_t>(), n, m, ld);
+  RYL_LAUNCH(bxt_kernel, dim3(kH, m), 256, 0, s, x_in.d, bt.as<uint8_t>(), ld, n, d, m, bb_out.d);
   RYL_TRY(a_out.flush(s));
   RYL_TRY(bb_out.flush(s));
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
