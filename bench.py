@@ -32,6 +32,14 @@ for _p in (ROOT, os.path.join(ROOT, "rayuela.jl_b200")):
 H = 256
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the SAME workload
+# (profiles/r1_v2_icm_warp_kernel_full_workload.txt, profiles/r1_v2_scan8_kernel.txt); bench.py cannot run ncu.
+NCU_TRAFFIC = {
+    ("icm", 1_000_000, 128, 8, 32): 13.426433e9 + 24.938240e6,
+    ("scan", 1_000_000, 10_000, 8, 1): 175.220736e6 + 53.773568e6,
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -452,8 +460,8 @@ def run_ours(args, cfg):
     sm_mhz = clocks.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
     onchip_peak = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s of L1/shared load bandwidth at the sampled clock
     icm_roof = {"bound": "hbm", "achieved": gather_bytes / (k3_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "traffic": None, "peak_source": pk_src,
-                "kernel": "icm_warp_kernel<8>", "kernel_ms": k3_ms,
+                "unit": "GB/s", "traffic": NCU_TRAFFIC.get(("icm", n, d, m, cfg["ilsiter"])), "peak_source": pk_src,
+                "kernel": "icm_warp_kernel<%d>" % m, "kernel_ms": k3_ms,
                 "onchip_peak": onchip_peak,
                 "steps_executed": steps_done, "steps_reference": steps_total,
                 "reference_equiv_achieved": gather_bytes_ref / (k3_ms * 1e-3) / 1e9,
@@ -466,7 +474,8 @@ def run_ours(args, cfg):
     icm_roof["onchip_frac"] = icm_roof["achieved"] / onchip_peak
     scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base
     scan_roof = {"bound": "hbm", "achieved": scan_bytes / (scan_per * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                 "unit": "GB/s", "traffic": None, "peak_source": pk_src, "kernel": "scan8_kernel<true>",
+                 "unit": "GB/s", "traffic": NCU_TRAFFIC.get(("scan", n, nq, m, k)), "peak_source": pk_src,
+                 "kernel": "scan8_kernel<true>" if m <= 8 else "scan_kernel<%d,8,true>" % m,
                  "note": "algorithmic bytes = nq*n*(m+4): what the reference streams per query "
                          "(pairwise_byte.cpp:56-83); whole search step (LUT + scan + merge) in the denominator"}
     scan_roof["frac"] = scan_roof["achieved"] / scan_roof["peak"]
