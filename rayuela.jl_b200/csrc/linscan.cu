@@ -326,23 +326,45 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
 // leading bytes of similar distances cost one shared atomic per warp), then warp 0 picks the bin holding rank k.
 __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int c, int k, int* hist, int* sel) {
   const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
-  uint64_t prefix = 0;
+  // Leading bytes shared by all keys (same exponent / high mantissa for similar distances) need no pass:
+  // OR of (key ^ buf[0]) over the block tells the first byte where any two keys differ.
+  uint64_t diff = 0;
+  const uint64_t k0 = buf[0];
+  for (int t = tid; t < c; t += nt) diff |= buf[t] ^ k0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, off);
+  if (tid == 0) {
+    sel[2] = 0;
+    sel[3] = 0;
+  }
+  __syncthreads();
+  if (lane == 0 && diff) {
+    atomicOr(&sel[2], (int)(uint32_t)diff);
+    atomicOr(&sel[3], (int)(uint32_t)(diff >> 32));
+  }
+  __syncthreads();
+  diff = ((uint64_t)(uint32_t)sel[3] << 32) | (uint32_t)sel[2];
+  const int first = diff ? (__clzll((long long)diff) >> 3) : 8;       // first pass that can discriminate
+  uint64_t prefix = first ? (k0 >> (64 - 8 * first)) : 0;
   int krem = k;
-  for (int pass = 0; pass < 8; pass++) {
+  for (int pass = first; pass < 8; pass++) {
     const int shift = 56 - 8 * pass;
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
-    for (int t0 = 0; t0 < c; t0 += nt) {          // uniform trip count: match.any needs converged warps
-      const int t = t0 + tid;
-      bool act = t < c;
-      uint32_t digit = 0;
-      if (act) {
-        const uint64_t key = buf[t];
-        act = pass == 0 || (key >> (shift + 8)) == prefix;
-        digit = (uint32_t)(key >> shift) & 255u;
+    if (pass == first) {
+      // the first discriminating byte usually takes few distinct values: aggregate equal digits per warp
+      for (int t0 = 0; t0 < c; t0 += nt) {        // uniform trip count: match.any needs converged warps
+        const int t = t0 + tid;
+        const bool act = t < c;
+        const uint32_t digit = act ? (uint32_t)(buf[t] >> shift) & 255u : 256u + lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+        if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
       }
-      const uint32_t peers = __match_any_sync(0xffffffffu, act ? digit : 256u + lane);
-      if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+    } else {
+      for (int t = tid; t < c; t += nt) {
+        const uint64_t key = buf[t];
+        if ((key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1);
+      }
     }
     __syncthreads();
     if (tid < 32) {
@@ -493,9 +515,10 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
       return;
     }
     for (int t = tid; t < c; t += NT) sortbuf[t] = cq[t];
-    if (tid == 0) sel_s[2] = 0;
     __syncthreads();
     const uint64_t pivot = block_radix_select(sortbuf, c, p.k, hist_s, sel_s);
+    if (tid == 0) sel_s[2] = 0;
+    __syncthreads();
     for (int t = tid; t < c; t += NT) {
       const uint64_t key = sortbuf[t];
       if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly k keys (keys are distinct)
@@ -848,7 +871,8 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       const int kp = std::min(kmax, k - koff);
       const uint64_t* lbp = koff > 0 ? lb.as<uint64_t>() : nullptr;
       // v2: soft compaction limit 2k, hard limit = capacity minus what one round can add (256 codes per block-step)
-      int soft = std::max(512, 2 * kp), rbmax = kScan8RBMax;
+      // soft compaction limit: up to 4k (fewer, relatively cheaper selections) while a full round still fits
+      int soft = std::max(512, std::min(4 * kp, std::max(2 * kp, kScan8SortKeys - 256 * kScan8RBMax))), rbmax = kScan8RBMax;
       if (soft + 256 * kScan8RBMax > kScan8SortKeys) {
         soft = kp + (kScan8SortKeys - kp) / 2;
         rbmax = std::max(1, (kScan8SortKeys - soft) / 256);
