@@ -848,9 +848,15 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   const int64_t id_add = (pq ? 0 : 1) + ix->id_offset;  // linscan_aqd.cpp:88 vs pairwise_byte.cpp:76
   const float* norms = ix->kind == RAYUELA_SCAN_LSQ ? ix->norms.as<float>() : nullptr;
 
-  const int chunk_q = 16384;
-  for (int qb = 0; qb < nq; qb += chunk_q) {
-    const int nqc = std::min(chunk_q, nq - qb);
+  // Query chunks: whole waves of query tiles first (one block per SM per wave, base unsliced), then the
+  // remainder, which is sliced along the base so the last partial wave still fills the machine.
+  const int sms = sm_count();
+  int nqc = 0;
+  for (int qb = 0; qb < nq; qb += nqc) {
+    const int tiles_left = (nq - qb + QT - 1) / QT;
+    const int max_tiles = std::max(sms, (16384 / QT) / sms * sms);
+    nqc = nq - qb;
+    if (tiles_left > sms) nqc = std::min(nqc, std::min(tiles_left / sms * sms, max_tiles) * QT);
     const int qtiles = (nqc + QT - 1) / QT;
     DevBuf lut, lb;
     const size_t lut_floats = v2 ? (size_t)qtiles * (kLutTileBytes / 4) : (size_t)nqc * mh;
@@ -883,7 +889,11 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       RYL_ARG(smem <= 227 * 1024, "index_search: shared-memory budget exceeded");
       // DB slices: enough blocks for several waves, slices no shorter than 8 rounds, S*k within one merge pass
       const int64_t unit = v2 ? (int64_t)kChunkCodes * kScan8Warps : kRound;   // codes per block round
-      int S = std::max(1, ((v2 && kp <= 64 ? 6 : 2) * sm_count() + qtiles - 1) / qtiles);
+      // whole waves of query tiles run unsliced; fewer tiles than SMs -> slice the base to fill one wave (two for
+      // small k, where the per-slice warm-up is cheap)
+      int S = 1;
+      if (qtiles % sms != 0) S = std::max(1, (v2 && kp <= 64 && qtiles * 2 <= sms ? 2 : 1) * sms / qtiles);
+      if (const char* e = getenv("RAYUELA_B200_SCAN_SLICES")) S = std::max(1, atoi(e));   // tuning knob
       S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (v2 ? unit : 8 * unit)));
       S = std::min(S, std::max(1, 16384 / kp));
       int64_t slice_len = (ix->n + S - 1) / S;
