@@ -187,7 +187,9 @@ class Index:
         check(L.rayuela_index_create(ct.byref(h), kind, cp, np_, n, m, H, id_offset, a.flags, a.stream))
         self._h, self.kind, self.n, self.m, self.id_offset = h, kind, n, m, id_offset
 
-    def search(self, queries, codebooks, k):
+    def search(self, queries, codebooks, k, out=None):
+        """Top-k of every query.  out=(dists, idx): preallocated (nq, k) float32 / int32 result arrays on the same
+        side as the queries (e.g. pinned host memory), like the caller-allocated outputs of src/Linscan.jl:132-133."""
         L = _lib.lib()
         if self._h is None:
             raise RayuelaError("index already freed")
@@ -197,8 +199,12 @@ class Index:
         cols = d // self.m if self.kind == SCAN_PQ else d
         cp = a.inp(codebooks, np.float32, (self.m * H, cols))
         dev = _is_dev(queries)
-        dists, dp = a.new(dev, np.float32, (nq, k), device=queries.device if dev else None)
-        idx, ip = a.new(dev, np.int32, (nq, k), device=queries.device if dev else None)
+        if out is not None:
+            dists, idx = out
+            dp, ip = a.out(dists, np.float32, (nq, k)), a.out(idx, np.int32, (nq, k))
+        else:
+            dists, dp = a.new(dev, np.float32, (nq, k), device=queries.device if dev else None)
+            idx, ip = a.new(dev, np.int32, (nq, k), device=queries.device if dev else None)
         check(L.rayuela_index_search(self._h, qp, cp, nq, d, k, dp, ip, a.flags, a.stream))
         return dists, idx
 
