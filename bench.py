@@ -477,7 +477,7 @@ def run_ours(args, cfg):
     scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base
     scan_roof = {"bound": "hbm", "achieved": scan_bytes / (scan_per * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                  "unit": "GB/s", "traffic": NCU_TRAFFIC.get(("scan", n, nq, m, k)), "peak_source": pk_src,
-                 "kernel": "scan8_kernel<true>" if m <= 8 else "scan_kernel<%d,8,true>" % m,
+                 "kernel": "scanx_kernel<%d,true>" % (8 if m <= 8 else 16),
                  "note": "algorithmic bytes = nq*n*(m+4): what the reference streams per query "
                          "(pairwise_byte.cpp:56-83); whole search step (LUT + scan + merge) in the denominator"}
     scan_roof["frac"] = scan_roof["achieved"] / scan_roof["peak"]

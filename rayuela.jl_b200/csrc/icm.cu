@@ -217,12 +217,17 @@ struct IcmParams {
 // Lane owns candidates c = r*128 + lane*4 + e (r<2, e<4): every 1 KB row (unary or pairwise) is two
 // coalesced 512 B float4 loads per warp.  Unaries are re-read per step but a vector's 8 KB stay L2-resident
 // for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
-template <int M>
-__global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
+// USM (m <= 8): the vector's m KB of unaries are staged once into the warp's shared-memory slot and every step reads
+// its unary row from there, which takes 1/m of the gather traffic off L2 (the binding resource, profiles/r1_v2_icm*);
+// 8 warps x (8 KB + d floats) per block -> 3 blocks = 24 warps per SM instead of 32.
+template <int M, bool USM>
+__global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.d;
-  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * p.d);
+  float4* us = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * (M * 64);      // [M][64] float4, USM only
+  float* smem_f = reinterpret_cast<float*>(smem_raw) + (USM ? (size_t)nwarps * M * kH : 0);
+  float* sq = smem_f + (size_t)warp * p.d;
+  int* stats_s = reinterpret_cast<int*>(smem_f + (size_t)nwarps * p.d);
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
   __syncthreads();
 
@@ -233,6 +238,12 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
     Code cur = load_code<M>(p.B + (size_t)l * M);
     float curcost = warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
     const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
+    if (USM) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < M * 2; i++) us[i * 32 + lane] = __ldg(Ul + i * 32 + lane);
+      __syncwarp();
+    }
 
     for (int it = 0; it < p.ilsiter; it++) {
       Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
@@ -248,8 +259,14 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
           const int j = __ldg(order + s);
           if (!((dirty >> j) & 1u)) continue;
           nsteps++;
-          float4 a0 = __ldg(Ul + j * 64 + lane);
-          float4 a1 = __ldg(Ul + j * 64 + 32 + lane);
+          float4 a0, a1;
+          if (USM) {
+            a0 = us[j * 64 + lane];
+            a1 = us[j * 64 + 32 + lane];
+          } else {
+            a0 = __ldg(Ul + j * 64 + lane);
+            a1 = __ldg(Ul + j * 64 + 32 + lane);
+          }
 #pragma unroll
           for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j, encode_icm.cpp:28-45
             const int k = kk + (kk >= j);
@@ -541,15 +558,30 @@ extern "C" int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total) {
   return RAYUELA_OK;
 }
 
+static bool icm_unaries_in_smem(int m, size_t smem_plain) {
+  const char* e = getenv("RAYUELA_B200_ICM_USM");       // tuning knob: 0 = unaries from L2 (default: staged in smem)
+  if (m > 8 || (e && *e && atoi(e) == 0)) return false;
+  return smem_plain + (size_t)8 * m * kH * sizeof(float) <= 72 * 1024;   // 3 blocks per SM must still fit
+}
+
 template <int M>
 static int launch_icm(const IcmParams& p, cudaStream_t s) {
   const int warps = 8;
   size_t smem = (size_t)warps * p.d * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
-  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t need = (p.nc + warps - 1) / warps;
+  if constexpr (M <= 8) {
+    if (icm_unaries_in_smem(M, smem)) {
+      smem += (size_t)warps * M * kH * sizeof(float);
+      RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 3);  // 3 blocks of 8 warps per SM
+      RYL_LAUNCH((icm_warp_kernel<M, true>), grid, warps * 32, smem, s, p);
+      return RAYUELA_OK;
+    }
+  }
+  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);  // 4 blocks of 8 warps per SM
-  RYL_LAUNCH(icm_warp_kernel<M>, grid, warps * 32, smem, s, p);
+  RYL_LAUNCH((icm_warp_kernel<M, false>), grid, warps * 32, smem, s, p);
   return RAYUELA_OK;
 }
 

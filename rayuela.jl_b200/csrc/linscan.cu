@@ -1,7 +1,7 @@
 // linscan.cu -- path (2): asymmetric-distance linear scan on B200.
 //   K4 lut_kernel     per-query m*256 lookup table, exact reference arithmetic order
-//   K5 scan_kernel    byte-code scan from a shared-memory LUT tile + streaming top-k (threshold filter,
-//                     candidate buffer, block bitonic compaction)
+//   K5 scanx_kernel   bank-conflict-free byte-code scan from a shared-memory LUT tile + streaming top-k
+//                     (threshold filter, candidate buffers, event-driven block radix-select compaction)
 //   K6 merge_kernel   k-way merge of sorted (dist,id) lists (DB slices of one GPU, or per-GPU shards)
 // Replaces deps/src/linscan_aqd.cpp:37-102 and deps/src/linscan_aqd_pairwise_byte.cpp:14-176.
 #include <algorithm>
@@ -12,9 +12,6 @@
 namespace ryl {
 
 static constexpr int kH = 256;
-static constexpr int kScanThreads = 256;
-static constexpr int kCodesPerThread = 4;
-static constexpr int kRound = kScanThreads * kCodesPerThread;  // codes per block round
 
 // ------------------------------------------------------------------------------------------------------
 // K4: LUT build.  One thread owns one (query, entry) pair and walks the dimension sequentially with
@@ -69,29 +66,19 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
   for (int i = 0; i < 4; i++) {
     int q = q0 + qg + 8 * i;
     if (q < nq) {
-      if (tiled) {
+      if (tiled == 1) {
         // layout of scan8_kernel's shared-memory tile (see there): [q/16][(q%16)/4][c][((q%4)/2)*8 + k][q%2]
         const int ent = e0 + e, k = ent >> 8, c = ent & 255;
         lut[(size_t)(q >> 4) * 32768 + ((q & 15) >> 2) * 8192 + c * 32 + ((((q & 3) >> 1) * 8 + k) << 1) + (q & 1)] =
             acc[i];
+      } else if (tiled == 2) {
+        // scanx_kernel<16>: [q/8][(q%8)/2][c][k][q%2]
+        const int ent = e0 + e, k = ent >> 8, c = ent & 255;
+        lut[(size_t)(q >> 3) * 32768 + ((q & 7) >> 1) * 8192 + c * 32 + (k << 1) + (q & 1)] = acc[i];
       } else {
         lut[(size_t)q * mh + e0 + e] = acc[i];
       }
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Index re-layout: codes m-by-n (vector-major, m bytes each) -> padded to MP = 8 or 16 bytes per vector so
-// the scan reads each code with one aligned 8/16-byte load.
-// ------------------------------------------------------------------------------------------------------
-__global__ void pad_codes_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int64_t n, int m, int mp) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int64_t total = n * mp;
-  for (; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t v = i / mp;
-    int k = (int)(i % mp);
-    out[i] = k < m ? in[v * m + k] : (uint8_t)0;
   }
 }
 
@@ -122,182 +109,10 @@ __device__ __forceinline__ int pow2ceil(int x) {
   return p;
 }
 
-struct ScanParams {
-  const uint8_t* codes;  // [n][MP]
-  const float* norms;    // [n] or nullptr
-  const float* lut;      // [nq][m*256]
-  uint64_t* cand;        // [slices][nqtiles*QT][cap]
-  uint64_t* part;        // [slices][nq][k] sorted keys (low word = local id)
-  const uint64_t* lb;    // [nq] or nullptr: only keys strictly greater than lb[q] qualify (k > one pass)
-  int64_t n, slice_len;
-  int nq, k, cap;
-};
-
-// ------------------------------------------------------------------------------------------------------
-// K5: scan.  grid = (query tiles, DB slices).  The block keeps the LUTs of QT queries in shared memory,
-// streams its slice of codes, and for every (code, query) sums the M lookups in ascending-k order starting
-// from +0 (pairwise_byte.cpp:70-73), adds the norm last (:74), and keeps (dist, id) if dist <= tau_q, the
-// k-th best distance known so far for that query.  Candidates go to a per-query buffer (global, L2-resident);
-// when a buffer could overflow in the next round the block sorts it (bitonic, shared memory), keeps the k
-// best and tightens tau_q.  The final buffers are sorted and written as keys.
-// ------------------------------------------------------------------------------------------------------
-template <int M, int QT, bool NORMS>
-__global__ void __launch_bounds__(kScanThreads) scan_kernel(ScanParams p) {
-  constexpr int MP = (M <= 8) ? 8 : 16;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* lut_s = reinterpret_cast<float*>(smem_raw);                       // [QT][M][256]
-  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(lut_s + QT * M * kH);    // [cap]
-  __shared__ int cnt_s[QT];
-  __shared__ float tau_s[QT];
-  __shared__ uint64_t lb_s[QT];
-
-  const int q0 = blockIdx.x * QT;
-  const int slice = blockIdx.y;
-  if (threadIdx.x < QT) lb_s[threadIdx.x] = p.lb ? p.lb[min(q0 + (int)threadIdx.x, p.nq - 1)] : 0ull;
-  const int64_t begin = (int64_t)slice * p.slice_len;
-  const int64_t end = min(p.n, begin + p.slice_len);
-  uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * QT + (size_t)blockIdx.x * QT) * p.cap;
-
-  for (int i = threadIdx.x; i < QT * M * kH / 4; i += kScanThreads) {
-    int q = (i * 4) / (M * kH);
-    int r = (i * 4) % (M * kH);
-    int qq = min(q0 + q, p.nq - 1);
-    reinterpret_cast<float4*>(lut_s)[i] = *reinterpret_cast<const float4*>(p.lut + (size_t)qq * M * kH + r);
-  }
-  if (threadIdx.x < QT) {
-    cnt_s[threadIdx.x] = 0;
-    tau_s[threadIdx.x] = __int_as_float(0x7f800000);
-  }
-  __syncthreads();
-
-  float tau[QT];
-#pragma unroll
-  for (int q = 0; q < QT; q++) tau[q] = __int_as_float(0x7f800000);
-
-  auto compact = [&](int q) {
-    const int c = cnt_s[q];
-    const int np2 = pow2ceil(c);
-    uint64_t* cq = cand + (size_t)q * p.cap;
-    for (int t = threadIdx.x; t < np2; t += kScanThreads) sortbuf[t] = t < c ? cq[t] : ~0ull;
-    __syncthreads();
-    block_bitonic_sort(sortbuf, np2);
-    const int keep = min(c, p.k);
-    for (int t = threadIdx.x; t < keep; t += kScanThreads) cq[t] = sortbuf[t];
-    if (threadIdx.x == 0) {
-      cnt_s[q] = keep;
-      if (c >= p.k) tau_s[q] = ordered_to_f32((uint32_t)(sortbuf[p.k - 1] >> 32));
-    }
-    __syncthreads();
-  };
-
-  for (int64_t base = begin; base < end; base += kRound) {
-#pragma unroll
-    for (int cc = 0; cc < kCodesPerThread; cc++) {
-      const int64_t i = base + cc * kScanThreads + threadIdx.x;
-      if (i < end) {
-        uint32_t w[MP / 4];
-        if (MP == 8) {
-          uint2 v = *reinterpret_cast<const uint2*>(p.codes + i * MP);
-          w[0] = v.x;
-          w[1] = v.y;
-        } else {
-          uint4 v = *reinterpret_cast<const uint4*>(p.codes + i * MP);
-          w[0] = v.x;
-          w[1] = v.y;
-          w[MP / 4 - 2] = v.z;
-          w[MP / 4 - 1] = v.w;
-        }
-        float nrm = 0.f;
-        if (NORMS) nrm = p.norms[i];
-#pragma unroll
-        for (int q = 0; q < QT; q++) {
-          float s = 0.0f;
-#pragma unroll
-          for (int k = 0; k < M; k++) {
-            uint32_t b = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
-            s = __fadd_rn(s, lut_s[(q * M + k) * kH + b]);
-          }
-          if (NORMS) s = __fadd_rn(s, nrm);
-          if (s <= tau[q]) {
-            const uint64_t key = make_key(s, (uint32_t)i);
-            if (!p.lb || key > lb_s[q]) {
-              int pos = atomicAdd(&cnt_s[q], 1);
-              cand[(size_t)q * p.cap + pos] = key;
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-    bool any = false;
-    for (int q = 0; q < QT; q++) {
-      if (cnt_s[q] > p.cap - kRound) {  // block-uniform
-        compact(q);
-        any = true;
-      }
-    }
-    if (any) {
-#pragma unroll
-      for (int q = 0; q < QT; q++) tau[q] = tau_s[q];
-    }
-  }
-
-  for (int q = 0; q < QT; q++) {
-    if (q0 + q >= p.nq) break;
-    compact(q);
-    const int c = cnt_s[q];
-    uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
-    for (int t = threadIdx.x; t < p.k; t += kScanThreads) out[t] = t < c ? sortbuf[t] : ~0ull;
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// K5 (m <= 8): bank-conflict-free scan.
-//
-// A 4-byte LUT lookup per byte of code makes the scan shared-memory-gather bound (32 lookups/clk/SM), and
-// 32 lanes looking up random entries of the same 256-entry row collide ~3.6x (measured, profiles/r1_v1).
-// Here every lane of a half-warp is at a DIFFERENT codebook k at any instant, and the LUT tile is laid out
-// so that codebook k of query-pair g lives in bank-pair g*8 + k:
-//      tile[tt][c][bp = g*8 + k][e]   (float; 4 queries per 32 KB tile: q = tt*4 + g*2 + e)
-// lane = hw*16 + g*8 + j handles code stream p = hw*8 + j of its warp's chunk and the query pair g of every
-// tile; at step s it is at codebook k = (s - j - 1) mod 8, so the 16 lanes of a half-warp hit 16 distinct
-// bank-pairs with one LDS.64 each -> no conflicts, 2 queries per load.  The sum for one code must still be
-// ((0 + t_0) + t_1) + ... in ascending k (pairwise_byte.cpp:70-73), so a lane's code simply starts j+1 steps
-// "late": the index stores each lane's byte stream pre-skewed (skew_codes_kernel) and the lane reads one
-// aligned 8-byte word per 8 steps.  Accumulate / restart / capture are done with packed FFMA2
-// (fma.rn.f32x2, exact per element):  acc = acc*keep_s + v   (keep_s = 0 at the step where the lane's next
-// code starts), done += acc*cap_s (cap_s = 1 at the step where its code completes).
-// The 128 KB LUT tile is staged with bulk async copies (cp.async.bulk + mbarrier).
-// ------------------------------------------------------------------------------------------------------
-static constexpr int kChunkL = 64;                    // codes per lane stream per chunk
-static constexpr int kChunkCodes = 16 * kChunkL;      // 1024 codes per warp chunk
-static constexpr int kChunkBlocks = kChunkL + 1;      // 8-step blocks per chunk (one extra for the skew tail)
+static constexpr int kChunkCodes = 1024;              // codes per warp chunk
 static constexpr int kScan8Warps = 16;
-static constexpr int kScan8RBMax = 16;                // longest round (blocks per warp between overflow checks)
-static constexpr int kScan8SortKeys = 8192;           // shared-memory sort buffer (64 KB)
-static constexpr int kLutTileBytes = 131072;          // 16 queries * 8 codebooks * 256 * 4 B
-
-// W[chunk][t][p] (uint64): bytes of stream p = codes chunk*1024 + 16u + p (u = 0..63), delayed by (p&7)+1 bytes.
-__global__ void skew_codes_kernel(const uint8_t* __restrict__ codes, uint64_t* __restrict__ W, int64_t n, int m,
-                                  int64_t nchunks) {
-  const int64_t total = nchunks * kChunkBlocks * 16;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int p = (int)(i & 15);
-    const int t = (int)((i >> 4) % kChunkBlocks);
-    const int64_t chunk = (i >> 4) / kChunkBlocks;
-    const int delay = (p & 7) + 1;
-    uint64_t w = 0;
-    for (int b = 0; b < 8; b++) {
-      const int sb = 8 * t + b - delay;              // byte index in the lane's undelayed stream
-      if (sb < 0 || sb >= 8 * kChunkL) continue;
-      const int u = sb >> 3, k = sb & 7;
-      const int64_t id = chunk * kChunkCodes + 16 * u + p;
-      if (id < n && k < m) w |= (uint64_t)codes[id * m + k] << (8 * b);
-    }
-    W[i] = w;
-  }
-}
+static constexpr int kScan8SortKeys = 8192;           // shared-memory selection buffer (64 KB)
+static constexpr int kLutTileBytes = 131072;          // 16 (m <= 8) or 8 (m <= 16) queries' tables
 
 __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
@@ -399,45 +214,122 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
   return prefix;
 }
 
-struct Scan8Params {
-  const uint64_t* W;     // skewed codes [nchunks][65][16]
-  const float* norms;    // [n] or nullptr
-  const float* lut;      // tiled [qtiles][32768]
-  uint64_t* cand;        // [slices][qtiles*16][cap]
-  uint64_t* part;        // [slices][nq][k]
-  const uint64_t* lb;    // [nq] or nullptr: only keys strictly greater than lb[q] qualify (k > one pass)
-  int64_t n, nchunks, chunks_per_slice;
-  int nq, k, cap, soft, rbmax;   // soft: compact a query's buffer once it holds more than this many keys
+// ------------------------------------------------------------------------------------------------------
+// K5: bank-conflict-free scan, period P = 8 (m <= 8) or 16 (m = 9..16) codebooks.
+//
+// A 4-byte LUT lookup per byte of code makes the scan shared-memory-gather bound (one LDS.64 warp-instruction per
+// 2 clk per SM, measured: scratch/ubench/lds_ffma2.cu), and 32 lanes looking up random entries of the same
+// 256-entry row collide ~3.6x (measured on the round-1 v1 kernel, profiles/r1_v1).  Here every lane of a half-warp
+// is at a DIFFERENT bank-pair at any instant:
+//   P = 8 : tile[tt][c][bp = g*8 + k][e]  (float; 4 queries per 32 KB tile: q = tt*4 + g*2 + e); lane = hw*16 + g*8 + j
+//           handles code stream hw*8 + j of its warp's chunk and the query pair g of each of the 4 tiles (16 queries
+//           per block, 16 streams per warp);
+//   P = 16: tile[tt][c][bp = k][e]  (2 queries per 32 KB tile, 8 queries per block); lane = stream (32 per warp).
+// At step s a lane is at codebook k = (s - j - 1) mod P (j = lane mod P), so the 16 lanes of a half-warp hit 16
+// distinct bank-pairs with one LDS.64 each -> no conflicts, 2 queries per load.  The sum for one code must still be
+// ((0 + t_0) + t_1) + ... in ascending k (pairwise_byte.cpp:70-73), so a lane's code simply starts j+1 steps
+// "late": the index stores each lane's stream pre-skewed (skew_fields_kernel).  Accumulate / restart / capture are
+// packed FFMA2 (fma.rn.f32x2, exact per element):  acc = acc*keep_s + v  (keep_s = 0 at the step where the lane's
+// next code starts), done += acc*cap_s (cap_s = 1 at the step where its code completes).
+// The index holds, per step, the 16-bit field (c << 7) | (k << 3): the byte offset of the LUT entry inside a tile
+// for THIS stream at THIS step (k is known when the index is built), and the tile is 32 KB-aligned in shared
+// memory, so a step's address is ONE instruction.  One period = P steps = one completed code per lane; a lane
+// reads 2P bytes of index per period.  The 128 KB LUT tile is staged with bulk async copies (cp.async.bulk +
+// mbarrier).
+// ------------------------------------------------------------------------------------------------------
+template <int P>
+struct ScanX {
+  static constexpr int G = 16 / P;                 // query-pair groups per half-warp (2 or 1)
+  static constexpr int NS = 32 / G;                // code streams per warp (16 or 32)
+  static constexpr int L = kChunkCodes / NS;       // codes per stream per chunk (64 or 32)
+  static constexpr int PERIODS = L + 1;            // + one period for the skew tail
+  static constexpr int HALVES = P / 8;             // uint4 words per lane per period
+  static constexpr int QB = 8 * G;                 // queries per block (16 or 8)
+  static constexpr int ADDS = kScan8Warps * NS;    // most keys one query can gain per block-period
 };
 
-template <bool NORMS>
-__global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params p) {
+// F[chunk][t][half][p] (uint4 = 8 fields): stream p = codes chunk*1024 + NS*u + p (u = 0..L-1), delayed by (p mod P)+1
+template <int P>
+__global__ void skew_fields_kernel(const uint8_t* __restrict__ codes, uint4* __restrict__ F, int64_t n, int m,
+                                   int64_t nchunks) {
+  using X = ScanX<P>;
+  const int64_t total = nchunks * X::PERIODS * X::HALVES * X::NS;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % X::NS);
+    const int hf = (int)((i / X::NS) % X::HALVES);
+    const int t = (int)((i / (X::NS * X::HALVES)) % X::PERIODS);
+    const int64_t chunk = i / ((int64_t)X::NS * X::HALVES * X::PERIODS);
+    const int delay = (p & (P - 1)) + 1;
+    uint32_t f[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int sb = P * t + hf * 8 + b - delay;       // byte index in the stream's undelayed sequence
+      const int k = sb & (P - 1);
+      uint32_t field = (uint32_t)k << 3;
+      if (sb >= 0 && sb < P * X::L) {
+        const int64_t id = chunk * kChunkCodes + (int64_t)X::NS * (sb / P) + p;
+        if (id < n && k < m) field |= (uint32_t)codes[id * m + k] << 7;
+      }
+      f[b] = field;
+    }
+    F[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+  }
+}
+
+struct ScanXParams {
+  const uint4* F;        // skewed offset fields
+  const float* norms;    // [n] or nullptr
+  const float* lut;      // tiled [qtiles][32768]
+  uint64_t* cand;        // [slices][qtiles*QB][cap]
+  uint64_t* part;        // [slices][nq][k]
+  const uint64_t* lb;    // [nq] or nullptr
+  int64_t n, nchunks, chunks_per_slice;
+  int nq, k, cap, soft;
+  int piggy;             // a service() also compacts every buffer already past this many keys
+};
+
+template <int P, bool NORMS>
+__global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams p) {
+  using X = ScanX<P>;
   constexpr int NT = kScan8Warps * 32;
+  constexpr int QB = X::QB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int cnt_s[16];
   __shared__ float tau_s[16];
+  __shared__ uint64_t lb_s[16];
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ int hist_s[256];
+  __shared__ int sel_s[4];
+  __shared__ int flag_s;     // some query's buffer needs compacting (set by the appending thread)
+  __shared__ int nfin_s;     // warps that have finished their chunks
 
-  const uint32_t lut_addr = smem_u32(smem_raw);
-  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(smem_raw + kLutTileBytes);
+  // dynamic shared memory: [sort buffer 64 KB][pad][LUT tile 128 KB, 32 KB-aligned] -- the alignment makes the
+  // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
+  // ((w & 0xFFFF) | base, or (w >> 16) + base)
+  uint64_t* sortbuf = reinterpret_cast<uint64_t*>(smem_raw);
+  const uint32_t lut_addr = (smem_u32(smem_raw) + kScan8SortKeys * 8 + 32767u) & ~32767u;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int j = lane & 7, g = (lane >> 3) & 1, pidx = (lane >> 4) * 8 + j;
-  const int q0 = blockIdx.x * 16;
+  const int j = lane & (P - 1);
+  const int g = (P == 8) ? ((lane >> 3) & 1) : 0;
+  const int pidx = (P == 8) ? ((lane >> 4) * 8 + j) : lane;
+  const int q0 = blockIdx.x * QB;
   const int slice = blockIdx.y;
-  uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * 16 + (size_t)blockIdx.x * 16) * p.cap;
+  uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * QB + (size_t)blockIdx.x * QB) * p.cap;
 
-  // ---- stage the LUT tile: 4 bulk async copies of 32 KB, completion on one mbarrier -----------------------
   const uint32_t mbar_addr = smem_u32(&mbar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_addr));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __shared__ uint64_t lb_s[16];
   if (tid < 16) {
     cnt_s[tid] = 0;
     tau_s[tid] = __int_as_float(0x7f800000);
-    lb_s[tid] = p.lb ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
+    lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
+  }
+  if (tid == 0) {
+    flag_s = 0;
+    nfin_s = 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -463,30 +355,24 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
     }
   }
 
-  // ---- per-lane constants -----------------------------------------------------------------------------------
-  uint32_t off[8];
-  uint64_t keep2[8], cap2[8];
+  // per-lane constants: restart (keep = 0) at step (j+1) mod P, capture at step j
+  const uint32_t base = lut_addr + (g << 6);
+  float keep[P], capf[P];
 #pragma unroll
-  for (int s = 0; s < 8; s++) {
-    off[s] = lut_addr + ((g * 8 + ((s - j - 1) & 7)) << 3);
-    const float kp = (s == ((j + 1) & 7)) ? 0.f : 1.f;
-    const float cp = (s == j) ? 1.f : 0.f;
-    keep2[s] = pack2(kp, kp);
-    cap2[s] = pack2(cp, cp);
+  for (int s = 0; s < P; s++) {
+    keep[s] = (s == ((j + 1) & (P - 1))) ? 0.f : 1.f;
+    capf[s] = (s == j) ? 1.f : 0.f;
   }
   float tau[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) tau[i] = __int_as_float(0x7f800000);
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
 
-  __shared__ int hist_s[256];
-  __shared__ int sel_s[4];
-  // Intermediate compaction: keep the k smallest keys (unordered) and set tau to the k-th distance.
   auto compact = [&](int q) {
     const int c = cnt_s[q];
     uint64_t* cq = cand + (size_t)q * p.cap;
-    if (c <= p.k) {            // nothing to drop; tau only if the buffer holds exactly k keys
-      if (c == p.k) {          // tau = the largest of the k keys
+    if (c <= p.k) {
+      if (c == p.k) {
         uint64_t mx = 0;
         for (int t = tid; t < c; t += NT) mx = max(mx, cq[t]);
 #pragma unroll
@@ -501,7 +387,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
       }
       return;
     }
-    if (c <= 512) {            // small buffers: a bitonic sort is cheaper than eight radix passes
+    if (c <= 512) {
       const int np2 = pow2ceil(c);
       for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
       __syncthreads();
@@ -521,7 +407,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
     __syncthreads();
     for (int t = tid; t < c; t += NT) {
       const uint64_t key = sortbuf[t];
-      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly k keys (keys are distinct)
+      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;
     }
     if (tid == 0) {
       cnt_s[q] = p.k;
@@ -529,7 +415,6 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
     }
     __syncthreads();
   };
-  // Final: the k smallest, sorted, left in sortbuf[0 .. min(c,k)).
   auto finalize = [&](int q) {
     compact(q);
     const int c = cnt_s[q];
@@ -540,121 +425,118 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scan8_kernel(Scan8Params 
     block_bitonic_sort(sortbuf, np2);
   };
 
-  // ---- this block's chunk range; warp w takes chunks c0 + w, c0 + w + 16, ... ---------------------------------
+  // Compaction is event-driven: the thread whose append pushes a buffer past the soft limit (or completes the first
+  // k candidates while tau is still +inf) raises flag_s; every warp polls the flag once per period and then joins
+  // service().  Between the raise and the last warp's poll a query gains at most ADDS keys (one period of every
+  // warp), which the capacity soft + 2*ADDS covers.  Finished warps wait in service() until all warps are done, so
+  // the block-wide barriers inside always see all 16 warps.
+  auto service = [&]() -> bool {
+    __syncthreads();                                   // nobody is appending past this point
+    const int nf = nfin_s;
+    const int fl = *(volatile int*)&flag_s;
+    if (fl) {
+      for (int q = 0; q < QB; q++) {
+        const int c = cnt_s[q];
+        if (c > p.piggy || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000))) compact(q);
+      }
+      if (tid == 0) flag_s = 0;
+    }
+    __syncthreads();
+    if (fl) {
+#pragma unroll
+      for (int tt = 0; tt < 4; tt++) {
+        tau[2 * tt] = tau_s[tt * 2 * X::G + g * 2];
+        tau[2 * tt + 1] = tau_s[tt * 2 * X::G + g * 2 + 1];
+      }
+    }
+    return nf == kScan8Warps;
+  };
+
   const int64_t c0 = (int64_t)slice * p.chunks_per_slice;
   const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
-  const int nci = (int)((c1 - c0 + kScan8Warps - 1) / kScan8Warps);
-
   const uint32_t n32 = (uint32_t)p.n;
-  const int hard = p.cap - kScan8Warps * 16 * p.rbmax;   // a round adds at most 256 keys per block-step
-  int sched = 1;                                          // warm-up: rounds of 1,1,2,4,... blocks so tau
-  bool first = true;                                      // stops being +inf as early as possible
+  const float inf = __int_as_float(0x7f800000);
 
-  for (int ci = 0; ci < nci; ci++) {
-    const int64_t chunk = c0 + (int64_t)ci * kScan8Warps + w;
-    const bool active = chunk < c1;                                    // warp-uniform
-    const uint64_t* wp = p.W + (active ? chunk : c0) * (kChunkBlocks * 16) + pidx;
-    const float* np = p.norms + chunk * kChunkCodes + pidx;            // norm of the code completed in block t+1
-    uint32_t id = (uint32_t)(chunk * kChunkCodes) + pidx - 16;         // code completed in block t (t >= 1)
-    uint64_t W0 = 0, W1 = 0;
-    if (active) {
-      W0 = __ldg(wp);
-      W1 = __ldg(wp + 16);
-    }
-    wp += 32;
+  for (int64_t chunk = c0 + w; chunk < c1; chunk += kScan8Warps) {
+    const uint4* fp = p.F + chunk * (X::PERIODS * X::HALVES * X::NS) + pidx;
+    const float* np = p.norms + chunk * kChunkCodes + pidx;            // norm of the code completed in period t+1
+    uint32_t id = (uint32_t)(chunk * kChunkCodes) + pidx - X::NS;      // code completed in period t (t >= 1)
+    uint4 W[X::HALVES], Wn[X::HALVES];
+#pragma unroll
+    for (int hf = 0; hf < X::HALVES; hf++) W[hf] = __ldg(fp + hf * X::NS);
+    fp += X::HALVES * X::NS;
     float nrm0 = 0.f;
-    int t = 0;
-    while (t < kChunkBlocks) {
-      const int len = min(sched, kChunkBlocks - t);
-      for (int b = 0; b < len; b++, t++) {
-        if (active) {
-          uint64_t W2 = 0;
-          if (t + 2 < kChunkBlocks) W2 = __ldg(wp);
-          float nrm1 = 0.f;
-          if (NORMS && t + 1 < kChunkBlocks && id + 16 < n32) nrm1 = __ldg(np);
-          const uint32_t lo = (uint32_t)W0, hi = (uint32_t)(W0 >> 32);
-#define RYL_STEP(S, WREG, SHL, SHR)                                                      \
-  {                                                                                      \
-    const uint32_t a = ((SHL ? (WREG << 7) : (WREG >> SHR)) & 0x7F80u) + off[S];         \
-    uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a); \
-    acc[0] = ffma2(acc[0], keep2[S], v0);                                                \
-    acc[1] = ffma2(acc[1], keep2[S], v1);                                                \
-    acc[2] = ffma2(acc[2], keep2[S], v2);                                                \
-    acc[3] = ffma2(acc[3], keep2[S], v3);                                                \
-    done[0] = ffma2(acc[0], cap2[S], done[0]);                                           \
-    done[1] = ffma2(acc[1], cap2[S], done[1]);                                           \
-    done[2] = ffma2(acc[2], cap2[S], done[2]);                                           \
-    done[3] = ffma2(acc[3], cap2[S], done[3]);                                           \
-  }
-          RYL_STEP(0, lo, 1, 0)
-          RYL_STEP(1, lo, 0, 1)
-          RYL_STEP(2, lo, 0, 9)
-          RYL_STEP(3, lo, 0, 17)
-          RYL_STEP(4, hi, 1, 0)
-          RYL_STEP(5, hi, 0, 1)
-          RYL_STEP(6, hi, 0, 9)
-          RYL_STEP(7, hi, 0, 17)
-#undef RYL_STEP
-          if (t >= 1 && id < n32) {
-            float dv[8];
-            const uint64_t n2 = pack2(nrm0, nrm0);
-            bool anyp = false;
+    for (int t = 0; t < X::PERIODS; t++) {
 #pragma unroll
-            for (int tt = 0; tt < 4; tt++) {
-              uint64_t dd = done[tt];
-              if (NORMS) dd = fadd2(dd, n2);                   // + dbnorms[i] last, pairwise_byte.cpp:74
-              dv[2 * tt] = __uint_as_float((uint32_t)dd);
-              dv[2 * tt + 1] = __uint_as_float((uint32_t)(dd >> 32));
-              anyp |= (dv[2 * tt] <= tau[2 * tt]) | (dv[2 * tt + 1] <= tau[2 * tt + 1]);
-            }
-            if (anyp) {
+      for (int hf = 0; hf < X::HALVES; hf++) {
+        Wn[hf] = make_uint4(0, 0, 0, 0);
+        if (t + 1 < X::PERIODS) Wn[hf] = __ldg(fp + hf * X::NS);
+      }
+      float nrm1 = 0.f;
+      if (NORMS && t + 1 < X::PERIODS && id + X::NS < n32) nrm1 = __ldg(np);
 #pragma unroll
-              for (int i = 0; i < 8; i++) {
-                if (dv[i] <= tau[i]) {
-                  const int q = (i >> 1) * 4 + g * 2 + (i & 1);
-                  const uint64_t key = make_key(dv[i], id);
-                  if (!p.lb || key > lb_s[q]) {
-                    int pos = atomicAdd(&cnt_s[q], 1);
-                    cand[(size_t)q * p.cap + pos] = key;
-                  }
-                }
+      for (int hf = 0; hf < X::HALVES; hf++) {
+        const uint32_t wr[4] = {W[hf].x, W[hf].y, W[hf].z, W[hf].w};
+#pragma unroll
+        for (int b8 = 0; b8 < 8; b8++) {
+          const int S = hf * 8 + b8;
+          const uint32_t a = (b8 & 1) ? (wr[b8 >> 1] >> 16) + base : ((wr[b8 >> 1] & 0xFFFFu) | base);
+          const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a);
+          const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
+          acc[0] = ffma2(acc[0], kp2, v0);
+          acc[1] = ffma2(acc[1], kp2, v1);
+          acc[2] = ffma2(acc[2], kp2, v2);
+          acc[3] = ffma2(acc[3], kp2, v3);
+          done[0] = ffma2(acc[0], cp2, done[0]);
+          done[1] = ffma2(acc[1], cp2, done[1]);
+          done[2] = ffma2(acc[2], cp2, done[2]);
+          done[3] = ffma2(acc[3], cp2, done[3]);
+        }
+      }
+      if (t >= 1 && id < n32) {
+        float dv[8];
+        const uint64_t n2 = pack2(nrm0, nrm0);
+        bool anyp = false;
+#pragma unroll
+        for (int tt = 0; tt < 4; tt++) {
+          uint64_t dd = done[tt];
+          if (NORMS) dd = fadd2(dd, n2);                   // + dbnorms[i] last, pairwise_byte.cpp:74
+          dv[2 * tt] = __uint_as_float((uint32_t)dd);
+          dv[2 * tt + 1] = __uint_as_float((uint32_t)(dd >> 32));
+          anyp |= (dv[2 * tt] <= tau[2 * tt]) | (dv[2 * tt + 1] <= tau[2 * tt + 1]);
+        }
+        if (anyp) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            if (dv[i] <= tau[i]) {
+              const int q = (i >> 1) * (2 * X::G) + g * 2 + (i & 1);
+              const uint64_t key = make_key(dv[i], id);
+              if (!p.lb || key > lb_s[q]) {
+                const int pos = atomicAdd(&cnt_s[q], 1);
+                cand[(size_t)q * p.cap + pos] = key;
+                if (pos >= p.soft || (tau[i] == inf && pos + 1 >= p.k)) *(volatile int*)&flag_s = 1;
               }
             }
           }
+        }
+      }
 #pragma unroll
-          for (int tt = 0; tt < 4; tt++) done[tt] = 0ull;
-          W0 = W1;
-          W1 = W2;
-          nrm0 = nrm1;
-          wp += 16;
-          np += 16;
-          id += 16;
-        }
-      }
-      sched = min(p.rbmax, first ? 1 : sched * 2);
-      first = false;
-      // a buffer is compacted when it exceeds the soft limit, could overflow in the next round, or holds its
-      // first k candidates (tau still +inf)
-      bool mine = false;
-      if (tid < 16) {
-        const int c = cnt_s[tid];
-        mine = c > p.soft || c > hard || (c >= p.k && tau_s[tid] == __int_as_float(0x7f800000));
-      }
-      if (__syncthreads_or(mine)) {
-        for (int q = 0; q < 16; q++) {
-          const int c = cnt_s[q];
-          if (c > p.soft || c > hard || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000))) compact(q);
-        }
+      for (int tt = 0; tt < 4; tt++) done[tt] = 0ull;
 #pragma unroll
-        for (int tt = 0; tt < 4; tt++) {
-          tau[2 * tt] = tau_s[tt * 4 + g * 2];
-          tau[2 * tt + 1] = tau_s[tt * 4 + g * 2 + 1];
-        }
-      }
+      for (int hf = 0; hf < X::HALVES; hf++) W[hf] = Wn[hf];
+      nrm0 = nrm1;
+      fp += X::HALVES * X::NS;
+      np += X::NS;
+      id += X::NS;
+      if (*(volatile int*)&flag_s) service();
     }
   }
+  __syncwarp();
+  if (lane == 0) atomicAdd(&nfin_s, 1);
+  while (!service()) {
+  }
 
-  for (int q = 0; q < 16; q++) {
+  for (int q = 0; q < QB; q++) {
     if (q0 + q >= p.nq) break;
     finalize(q);
     const int c = cnt_s[q];
@@ -711,37 +593,11 @@ __global__ void lower_bound_kernel(const float* __restrict__ d, const int32_t* _
 using namespace ryl;
 
 struct rayuela_index {
-  int kind = 0, m = 0, h = 0, mp = 0, device = 0;
+  int kind = 0, m = 0, h = 0, period = 0, device = 0;   // period: 8 (m <= 8) or 16 codebooks per lane cycle
   int64_t n = 0, id_offset = 0;
-  int64_t nchunks = 0;   // m <= 8: skewed layout for scan8_kernel
-  DevBuf codes, norms, skew;
+  int64_t nchunks = 0;   // 1024-code warp chunks of the skewed layout
+  DevBuf norms, skew;    // fp32 norms (LSQ); skewed offset fields (skew_fields_kernel)
 };
-
-template <int M, int QT>
-static int launch_scan_mq(const ScanParams& p, bool norms, dim3 grid, size_t smem, cudaStream_t s) {
-  if (norms) {
-    RYL_CUDA(cudaFuncSetAttribute(scan_kernel<M, QT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RYL_LAUNCH((scan_kernel<M, QT, true>), grid, kScanThreads, smem, s, p);
-  } else {
-    RYL_CUDA(cudaFuncSetAttribute(scan_kernel<M, QT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RYL_LAUNCH((scan_kernel<M, QT, false>), grid, kScanThreads, smem, s, p);
-  }
-  return RAYUELA_OK;
-}
-
-static constexpr int scan_qt(int m) { return m <= 8 ? 16 : 8; }
-
-static int launch_scan(int m, const ScanParams& p, bool norms, dim3 grid, size_t smem, cudaStream_t s) {
-  switch (m) {
-#define RYL_CASE(M) \
-  case M:           \
-    return launch_scan_mq<M, scan_qt(M)>(p, norms, grid, smem, s);
-    RYL_CASE(1) RYL_CASE(2) RYL_CASE(3) RYL_CASE(4) RYL_CASE(5) RYL_CASE(6) RYL_CASE(7) RYL_CASE(8)
-    RYL_CASE(9) RYL_CASE(10) RYL_CASE(11) RYL_CASE(12) RYL_CASE(13) RYL_CASE(14) RYL_CASE(15) RYL_CASE(16)
-#undef RYL_CASE
-  }
-  return fail(RAYUELA_ERR_ARG, "linscan: m must be in 1..16");
-}
 
 static int host_pow2ceil(int x) {
   int p = 2;
@@ -764,23 +620,24 @@ extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t
   ix->kind = kind;
   ix->m = m;
   ix->h = h;
-  ix->mp = m <= 8 ? 8 : 16;
+  ix->period = m <= 8 ? 8 : 16;
   ix->n = n;
   ix->id_offset = id_offset;
   cudaGetDevice(&ix->device);
   auto body = [&]() -> int {
     InArg<uint8_t> raw;
     RYL_TRY(raw.bind(codes, (size_t)n * m, dev, s));
-    if (m <= 8) {   // skewed streams for the conflict-free scan
-      ix->nchunks = (n + kChunkCodes - 1) / kChunkCodes;
-      const int64_t words = ix->nchunks * kChunkBlocks * 16;
-      RYL_TRY(ix->skew.alloc((size_t)words * sizeof(uint64_t), s));
+    ix->nchunks = (n + kChunkCodes - 1) / kChunkCodes;
+    if (ix->period == 8) {
+      const int64_t words = ix->nchunks * ScanX<8>::PERIODS * ScanX<8>::HALVES * ScanX<8>::NS;
+      RYL_TRY(ix->skew.alloc((size_t)words * sizeof(uint4), s));
       int blocks = (int)std::min<int64_t>((words + 255) / 256, 148 * 16);
-      RYL_LAUNCH(skew_codes_kernel, blocks, 256, 0, s, raw.d, ix->skew.as<uint64_t>(), n, m, ix->nchunks);
+      RYL_LAUNCH(skew_fields_kernel<8>, blocks, 256, 0, s, raw.d, ix->skew.as<uint4>(), n, m, ix->nchunks);
     } else {
-      RYL_TRY(ix->codes.alloc((size_t)n * ix->mp, s));
-      int blocks = (int)std::min<int64_t>((n * ix->mp + 255) / 256, 148 * 16);
-      RYL_LAUNCH(pad_codes_kernel, blocks, 256, 0, s, raw.d, ix->codes.as<uint8_t>(), n, m, ix->mp);
+      const int64_t words = ix->nchunks * ScanX<16>::PERIODS * ScanX<16>::HALVES * ScanX<16>::NS;
+      RYL_TRY(ix->skew.alloc((size_t)words * sizeof(uint4), s));
+      int blocks = (int)std::min<int64_t>((words + 255) / 256, 148 * 16);
+      RYL_LAUNCH(skew_fields_kernel<16>, blocks, 256, 0, s, raw.d, ix->skew.as<uint4>(), n, m, ix->nchunks);
     }
     if (kind == RAYUELA_SCAN_LSQ) {
       RYL_TRY(ix->norms.alloc((size_t)n * sizeof(float), s));
@@ -801,7 +658,6 @@ extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t
 
 extern "C" int rayuela_index_free(rayuela_index* ix) {
   if (ix) {
-    ix->codes.release();
     ix->norms.release();
     ix->skew.release();
     delete ix;
@@ -839,12 +695,13 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   RYL_TRY(d_out.bind(dists, (size_t)nq * k, dev, s));
   RYL_TRY(i_out.bind(idx, (size_t)nq * k, dev, s));
 
-  const bool v2 = m <= 8;                                   // conflict-free scan8_kernel
-  const int QT = v2 ? 16 : scan_qt(m);
+  const int period = ix->period;
+  const int QT = period == 16 ? ScanX<16>::QB : ScanX<8>::QB;               // queries per block
+  const int adds = period == 16 ? ScanX<16>::ADDS : ScanX<8>::ADDS;         // keys one query can gain per block-period
   // One pass returns at most kmax results per query (shared-memory selection buffer).  Larger k -- the reference's
   // default is k = 10000 (src/Linscan.jl:10) -- takes ceil(k / kmax) passes: pass p keeps only keys strictly
   // greater than the last key of pass p-1, which is exact because (dist, id) keys are a total order.
-  const int kmax = v2 ? 4096 : 3584;
+  const int kmax = 4096;
   const int64_t id_add = (pq ? 0 : 1) + ix->id_offset;  // linscan_aqd.cpp:88 vs pairwise_byte.cpp:76
   const float* norms = ix->kind == RAYUELA_SCAN_LSQ ? ix->norms.as<float>() : nullptr;
 
@@ -859,12 +716,11 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
     if (tiles_left > sms) nqc = std::min(nqc, std::min(tiles_left / sms * sms, max_tiles) * QT);
     const int qtiles = (nqc + QT - 1) / QT;
     DevBuf lut, lb;
-    const size_t lut_floats = v2 ? (size_t)qtiles * (kLutTileBytes / 4) : (size_t)nqc * mh;
-    RYL_TRY(lut.alloc(lut_floats * sizeof(float), s));
-    if (v2 && (m < 8 || nqc % 16)) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m
+    RYL_TRY(lut.alloc((size_t)qtiles * kLutTileBytes, s));
+    if (m < period || nqc % QT) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m
     dim3 lg(mh / 32, (nqc + 31) / 32);
     const float* qptr = q_in.d + (size_t)qb * d;
-    const int tiled = v2 ? 1 : 0;
+    const int tiled = period == 16 ? 2 : 1;
     if (ix->kind == RAYUELA_SCAN_LSQ)
       RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
     else if (ix->kind == RAYUELA_SCAN_CQ)
@@ -876,25 +732,22 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
     for (int koff = 0; koff < k; koff += kmax) {
       const int kp = std::min(kmax, k - koff);
       const uint64_t* lbp = koff > 0 ? lb.as<uint64_t>() : nullptr;
-      // v2: soft compaction limit 2k, hard limit = capacity minus what one round can add (256 codes per block-step)
-      // soft compaction limit: up to 4k (fewer, relatively cheaper selections) while a full round still fits
-      int soft = std::max(512, std::min(4 * kp, std::max(2 * kp, kScan8SortKeys - 256 * kScan8RBMax))), rbmax = kScan8RBMax;
-      if (soft + 256 * kScan8RBMax > kScan8SortKeys) {
-        soft = kp + (kScan8SortKeys - kp) / 2;
-        rbmax = std::max(1, (kScan8SortKeys - soft) / 256);
-      }
-      const int cap = v2 ? soft + 256 * rbmax : host_pow2ceil(std::max(2 * kRound, 2 * kp + kRound));
-      const size_t smem = v2 ? (size_t)kLutTileBytes + (size_t)kScan8SortKeys * sizeof(uint64_t)
-                             : (size_t)QT * mh * sizeof(float) + (size_t)cap * sizeof(uint64_t);
-      RYL_ARG(smem <= 227 * 1024, "index_search: shared-memory budget exceeded");
-      // DB slices: enough blocks for several waves, slices no shorter than 8 rounds, S*k within one merge pass
-      const int64_t unit = v2 ? (int64_t)kChunkCodes * kScan8Warps : kRound;   // codes per block round
-      // whole waves of query tiles run unsliced; fewer tiles than SMs -> slice the base to fill one wave (two for
-      // small k, where the per-slice warm-up is cheap)
+      // Event-driven compaction: a buffer is compacted (k smallest kept, tau tightened) once it holds more than
+      // `soft` keys -- up to 4k: fewer, relatively cheaper selections; measured optimum, gpurun r2_soft.log -- and
+      // the capacity leaves room for the two periods of appends that can land before every warp has seen the flag.
+      int soft = std::max(512, std::min(4 * kp, kScan8SortKeys - 2 * adds));
+      if (const char* e = getenv("RAYUELA_B200_SCAN_SOFT"))   // tuning knob
+        soft = std::max(kp, std::min(atoi(e), kScan8SortKeys - 2 * adds));
+      const int cap = soft + 2 * adds;
+      // sort buffer + up to 32 KB of padding so the LUT tile starts on a 32 KB boundary + the tile
+      const size_t smem = (size_t)kScan8SortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
+      // DB slices: whole waves of query tiles run unsliced; fewer tiles than SMs -> slice the base to fill one wave
+      // (two for small k, where the per-slice warm-up is cheap); S*k must fit one merge pass
+      const int64_t unit = (int64_t)kChunkCodes * kScan8Warps;   // codes per block round
       int S = 1;
-      if (qtiles % sms != 0) S = std::max(1, (v2 && kp <= 64 && qtiles * 2 <= sms ? 2 : 1) * sms / qtiles);
+      if (qtiles % sms != 0) S = std::max(1, (kp <= 64 && qtiles * 2 <= sms ? 2 : 1) * sms / qtiles);
       if (const char* e = getenv("RAYUELA_B200_SCAN_SLICES")) S = std::max(1, atoi(e));   // tuning knob
-      S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / (v2 ? unit : 8 * unit)));
+      S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / unit));
       S = std::min(S, std::max(1, 16384 / kp));
       int64_t slice_len = (ix->n + S - 1) / S;
       slice_len = (slice_len + unit - 1) / unit * unit;
@@ -903,44 +756,32 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       DevBuf cand, part;
       RYL_TRY(cand.alloc((size_t)S * qtiles * QT * cap * sizeof(uint64_t), s));
       RYL_TRY(part.alloc((size_t)S * nqc * kp * sizeof(uint64_t), s));
-      if (v2) {
-        Scan8Params p;
-        p.W = ix->skew.as<uint64_t>();
-        p.norms = norms;
-        p.lut = lut.as<float>();
-        p.cand = cand.as<uint64_t>();
-        p.part = part.as<uint64_t>();
-        p.lb = lbp;
-        p.n = ix->n;
-        p.nchunks = ix->nchunks;
-        p.chunks_per_slice = slice_len / kChunkCodes;
-        p.nq = nqc;
-        p.k = kp;
-        p.cap = cap;
-        p.soft = soft;
-        p.rbmax = rbmax;
-        if (norms) {
-          RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          RYL_LAUNCH(scan8_kernel<true>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
-        } else {
-          RYL_CUDA(cudaFuncSetAttribute(scan8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          RYL_LAUNCH(scan8_kernel<false>, dim3(qtiles, S), kScan8Warps * 32, smem, s, p);
-        }
+      ScanXParams p;
+      p.F = ix->skew.as<uint4>();
+      p.norms = norms;
+      p.lut = lut.as<float>();
+      p.cand = cand.as<uint64_t>();
+      p.part = part.as<uint64_t>();
+      p.lb = lbp;
+      p.n = ix->n;
+      p.nchunks = ix->nchunks;
+      p.chunks_per_slice = slice_len / kChunkCodes;
+      p.nq = nqc;
+      p.k = kp;
+      p.cap = cap;
+      p.soft = soft;
+      p.piggy = kp + (soft - kp) / 2;   // a service() also compacts buffers already half-way to the soft limit
+#define RYL_SCANX(PP, NN)                                                                                          \
+  {                                                                                                                \
+    RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+    RYL_LAUNCH((scanx_kernel<PP, NN>), dim3(qtiles, S), kScan8Warps * 32, smem, s, p);                             \
+  }
+      if (period == 16) {
+        if (norms) RYL_SCANX(16, true) else RYL_SCANX(16, false)
       } else {
-        ScanParams p;
-        p.codes = ix->codes.as<uint8_t>();
-        p.norms = norms;
-        p.lut = lut.as<float>();
-        p.cand = cand.as<uint64_t>();
-        p.part = part.as<uint64_t>();
-        p.lb = lbp;
-        p.n = ix->n;
-        p.slice_len = slice_len;
-        p.nq = nqc;
-        p.k = kp;
-        p.cap = cap;
-        RYL_TRY(launch_scan(m, p, norms != nullptr, dim3(qtiles, S), smem, s));
+        if (norms) RYL_SCANX(8, true) else RYL_SCANX(8, false)
       }
+#undef RYL_SCANX
       float* dq = d_out.d + (size_t)qb * k + koff;
       int32_t* iq = i_out.d + (size_t)qb * k + koff;
       RYL_TRY(merge_lists(part.as<uint64_t>(), nullptr, nullptr, S, nqc, kp, dq, iq, id_add, s, k));

@@ -177,6 +177,10 @@ def _scan_case(kind, n, nq, m, d, seed, ties=False):
     (300000, 5, 8, 50, True),          # few queries -> several DB slices + merge
     (1000, 3, 4, 1000, False),         # k == n
     (1500, 1, 1, 7, False),            # m = 1, single query
+    (100000, 33, 16, 1000, False),     # 16-codebook period of the skewed scan, several compactions
+    (50000, 7, 15, 100, True),         # 15 codebooks (+ norm byte, demos' m = 16); massive ties
+    (300000, 5, 12, 50, True),         # m = 12, few queries -> DB slices + merge
+    (2000, 3, 9, 2000, False),         # m = 9, k == n
 ])
 def test_scan_matches_reference(rb, kind, n, nq, m, k, ties):
     d = 16 * m if kind == orc.PQ else 64
@@ -202,6 +206,32 @@ def test_scan_large_k_multi_pass(rb, kind, m, k):
     d0, i0 = (orc.ref_linscan if orc.have_ref() else orc.linscan)(kind, B, Xq, cb, k, nrm)
     d1, i1 = rb.core.Index(kind, B, nrm).search(Xq, cb, k)
     assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0))
+
+
+@pytest.mark.parametrize("m,k", [(8, 300), (5, 1), (16, 300), (11, 2500)])
+def test_scan_compaction_schedule_does_not_change_results(rb, monkeypatch, m, k):
+    """The soft limit only decides WHEN a candidate buffer is compacted (event-driven, any warp may raise the
+    flag); the result must be the reference's bits for every schedule, on tie-heavy data."""
+    B, Xq, cb, nrm = _scan_case(orc.LSQ, 70000, 19, m, 64, seed=m, ties=True)
+    d0, i0 = (orc.ref_linscan if orc.have_ref() else orc.linscan)(orc.LSQ, B, Xq, cb, k, nrm)
+    for soft in ("1", "700", "100000"):
+        monkeypatch.setenv("RAYUELA_B200_SCAN_SOFT", soft)
+        d1, i1 = rb.core.Index(orc.LSQ, B, nrm).search(Xq, cb, k)
+        assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0)), soft
+
+
+def test_icm_unaries_in_smem_variant_agrees(rb, monkeypatch):
+    r = np.random.default_rng(3)
+    n, d, m = 5000, 48, 8
+    X = r.standard_normal((n, d)).astype(np.float32)
+    C = (r.standard_normal((m * 256, d)) / 3).astype(np.float32)
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    want = orc.encode_icm(X, C, B, 3, 4, 4, True, seed=9)
+    for val in ("0", "1"):
+        monkeypatch.setenv("RAYUELA_B200_ICM_USM", val)
+        got = rb.core.encode_icm(X, C, B, 3, 4, 4, True, seed=9, want_cost=True)
+        assert np.array_equal(got["B"], want["B"]), val
+        assert np.array_equal(bits(got["cost"]), bits(want["cost"])), val
 
 
 def test_scan_compat_symbols(rb):
