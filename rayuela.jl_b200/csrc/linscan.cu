@@ -128,6 +128,11 @@ __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
   return ((uint64_t)__float_as_uint(hi) << 32) | __float_as_uint(lo);
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_volatile(uint32_t addr) {
+  int v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 template <int IMM>
 __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
   uint64_t v;
@@ -302,6 +307,8 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   __shared__ int sel_s[4];
   __shared__ int flag_s;     // some query's buffer needs compacting (set by the appending thread)
   __shared__ int nfin_s;     // warps that have finished their chunks
+  __shared__ int warm_s;     // some query still has tau = +inf: react to the flag within the same period
+  __shared__ int finq_s[16]; // final phase: query already written by its warp
 
   // dynamic shared memory: [sort buffer 64 KB][pad][LUT tile 128 KB, 32 KB-aligned] -- the alignment makes the
   // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
@@ -330,6 +337,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   if (tid == 0) {
     flag_s = 0;
     nfin_s = 0;
+    warm_s = 1;
   }
   __syncthreads();
   if (tid == 0) {
@@ -367,6 +375,47 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
 #pragma unroll
   for (int i = 0; i < 8; i++) tau[i] = __int_as_float(0x7f800000);
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
+  int warm = 1;
+
+  // Small buffers (<= kWarpKeys keys) are handled by ONE warp each, all queries of the block at once: the warp
+  // sorts its query's keys in its own 4 KB slice of the sort area (warp-level bitonic network, no block barriers)
+  // and leaves them there sorted; returns the number of keys kept (min(c, k)).
+  constexpr int kWarpKeys = kScan8SortKeys / kScan8Warps;   // 512
+  uint64_t* wslice = sortbuf + w * kWarpKeys;
+  auto warp_sort_keep = [&](int q) -> int {
+    const int c = cnt_s[q];
+    uint64_t* cq = cand + (size_t)q * p.cap;
+    const int np2 = max(64, pow2ceil(c));
+    for (int t = lane; t < np2; t += 32) wslice[t] = t < c ? cq[t] : ~0ull;
+    __syncwarp();
+    for (int size = 2; size <= np2; size <<= 1) {
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        for (int t = lane; t < (np2 >> 1); t += 32) {
+          const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+          const int hi = lo | stride;
+          const bool up = (lo & size) == 0;
+          const uint64_t a = wslice[lo], b = wslice[hi];
+          if ((a > b) == up) {
+            wslice[lo] = b;
+            wslice[hi] = a;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    const int keep = min(c, p.k);
+    if (c > p.k)
+      for (int t = lane; t < keep; t += 32) cq[t] = wslice[t];
+    if (lane == 0) {
+      cnt_s[q] = keep;
+      if (c >= p.k) tau_s[q] = ordered_to_f32((uint32_t)(wslice[p.k - 1] >> 32));
+    }
+    return keep;
+  };
+  auto needs_compaction = [&](int q) -> bool {
+    const int c = cnt_s[q];
+    return c > p.piggy || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000));
+  };
 
   auto compact = [&](int q) {
     const int c = cnt_s[q];
@@ -426,23 +475,30 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   };
 
   // Compaction is event-driven: the thread whose append pushes a buffer past the soft limit (or completes the first
-  // k candidates while tau is still +inf) raises flag_s; every warp polls the flag once per period and then joins
-  // service().  Between the raise and the last warp's poll a query gains at most ADDS keys (one period of every
-  // warp), which the capacity soft + 2*ADDS covers.  Finished warps wait in service() until all warps are done, so
-  // the block-wide barriers inside always see all 16 warps.
+  // k candidates while tau is still +inf) raises flag_s; every warp reads the flag at the START of each period
+  // (so the load's latency hides behind the period's lookups), acts on it at the END, and then joins service().
+  // Between the raise and the last warp's reaction a query gains at most 2*ADDS keys (two periods of every warp),
+  // which the capacity soft + 3*ADDS covers.  Finished warps wait in service() until all warps are done, so the
+  // block-wide barriers inside always see all 16 warps.
   auto service = [&]() -> bool {
     __syncthreads();                                   // nobody is appending past this point
     const int nf = nfin_s;
     const int fl = *(volatile int*)&flag_s;
     if (fl) {
-      for (int q = 0; q < QB; q++) {
-        const int c = cnt_s[q];
-        if (c > p.piggy || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000))) compact(q);
+      if (w < QB && cnt_s[w] <= kWarpKeys && needs_compaction(w)) warp_sort_keep(w);   // warp w <-> query w
+      __syncthreads();
+      for (int q = 0; q < QB; q++)
+        if (needs_compaction(q)) compact(q);                                           // the large ones, block-wide
+      if (tid == 0) {
+        flag_s = 0;
+        int warm = 0;
+        for (int q = 0; q < QB; q++) warm |= tau_s[q] == __int_as_float(0x7f800000);
+        warm_s = warm;
       }
-      if (tid == 0) flag_s = 0;
     }
     __syncthreads();
     if (fl) {
+      warm = warm_s;
 #pragma unroll
       for (int tt = 0; tt < 4; tt++) {
         tau[2 * tt] = tau_s[tt * 2 * X::G + g * 2];
@@ -456,6 +512,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
   const uint32_t n32 = (uint32_t)p.n;
   const float inf = __int_as_float(0x7f800000);
+  const uint32_t flag_addr = smem_u32(&flag_s);
 
   for (int64_t chunk = c0 + w; chunk < c1; chunk += kScan8Warps) {
     const uint4* fp = p.F + chunk * (X::PERIODS * X::HALVES * X::NS) + pidx;
@@ -467,6 +524,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     fp += X::HALVES * X::NS;
     float nrm0 = 0.f;
     for (int t = 0; t < X::PERIODS; t++) {
+      const int raised = lds_volatile(flag_addr);
 #pragma unroll
       for (int hf = 0; hf < X::HALVES; hf++) {
         Wn[hf] = make_uint4(0, 0, 0, 0);
@@ -528,7 +586,8 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
       fp += X::HALVES * X::NS;
       np += X::NS;
       id += X::NS;
-      if (*(volatile int*)&flag_s) service();
+      // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
+      if (raised || (warm && lds_volatile(flag_addr))) service();
     }
   }
   __syncwarp();
@@ -536,8 +595,21 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   while (!service()) {
   }
 
+  // final phase: small buffers by their own warp (all at once), the rest block-wide
+  if (w < QB) {
+    const bool mine = q0 + w < p.nq && cnt_s[w] <= kWarpKeys;
+    if (mine) {
+      const int keep = warp_sort_keep(w);
+      __syncwarp();
+      uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + w) * p.k;
+      for (int i = lane; i < p.k; i += 32) out[i] = i < keep ? wslice[i] : ~0ull;
+    }
+    if (lane == 0) finq_s[w] = mine;
+  }
+  __syncthreads();
   for (int q = 0; q < QB; q++) {
     if (q0 + q >= p.nq) break;
+    if (finq_s[q]) continue;
     finalize(q);
     const int c = cnt_s[q];
     uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
@@ -734,11 +806,12 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       const uint64_t* lbp = koff > 0 ? lb.as<uint64_t>() : nullptr;
       // Event-driven compaction: a buffer is compacted (k smallest kept, tau tightened) once it holds more than
       // `soft` keys -- up to 4k: fewer, relatively cheaper selections; measured optimum, gpurun r2_soft.log -- and
-      // the capacity leaves room for the two periods of appends that can land before every warp has seen the flag.
-      int soft = std::max(512, std::min(4 * kp, kScan8SortKeys - 2 * adds));
+      // the capacity leaves room for the periods of appends that can land before every warp has reacted to the flag.
+      // (small k: 384, so that a buffer past the limit still fits the 512-key slice one warp can compact alone)
+      int soft = std::max(384, std::min(4 * kp, kScan8SortKeys - 3 * adds));
       if (const char* e = getenv("RAYUELA_B200_SCAN_SOFT"))   // tuning knob
-        soft = std::max(kp, std::min(atoi(e), kScan8SortKeys - 2 * adds));
-      const int cap = soft + 2 * adds;
+        soft = std::max(kp, std::min(atoi(e), kScan8SortKeys - 3 * adds));
+      const int cap = soft + 3 * adds;
       // sort buffer + up to 32 KB of padding so the LUT tile starts on a 32 KB boundary + the tile
       const size_t smem = (size_t)kScan8SortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
       // DB slices: whole waves of query tiles run unsliced; fewer tiles than SMs -> slice the base to fill one wave
