@@ -66,6 +66,11 @@ int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, in
  * did not change since its last evaluation is skipped (its result is provably unchanged). Measurement aid. */
 int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total);
 
+/* Of the executed steps of that call, how many took the exact fp32 rows: a step is first evaluated from a 16-bit
+ * quantised copy of the tables with a rigorous error window, and only steps with more than one candidate inside the
+ * window (near-ties) re-read the fp32 rows -- the result is bit-identical either way. Measurement aid. */
+int rayuela_encode_icm_exact_steps(uint64_t* exact);
+
 /* Replaces veccost (src/qerrors.jl:36-66).  mean_out (host double, may be NULL) receives qerror
  * (src/qerrors.jl:69-74). cost may be NULL when only the mean is wanted. */
 int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,

@@ -31,10 +31,12 @@ __global__ void sqnorm_kernel(const float* __restrict__ C, int d, int mh, float*
 
 // ---- K1: fp32 SIMT GEMM, 128 entries x 128 vectors per block, 8x8 per thread, BK = 8 --------------------
 // Each output is ONE sequential-t fmaf chain (no split-K), so it is bit-identical to the oracle's dot_seq.
+// umax (optional): umax[l] = max over all entries of |U[l][.]|, as float bits via atomicMax (|.| >= 0 orders like
+// an unsigned integer); it bounds the fp32 rounding slack of the quantised pre-filter in K3.
 template <bool VEC4>
 __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C, const float* __restrict__ X,
                                                     const float* __restrict__ nrm, float* __restrict__ U, int64_t n,
-                                                    int d, int mh) {
+                                                    int d, int mh, unsigned int* __restrict__ umax) {
   constexpr int BM = 128, BN = 128, BK = 8;
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Bs[BK][BN];
@@ -103,6 +105,17 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
       float* dst = U + (size_t)l * mh + e0 + ty * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      if (umax) {
+        float mx = 0.f;
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          mx = fmaxf(mx, fabsf(o[i]));
+          bad |= o[i] != o[i];
+        }
+        if (bad) mx = __int_as_float(0x7f800000);               // NaN unaries -> +inf slack -> exact path
+        atomicMax(umax + l, __float_as_uint(mx));
+      }
     }
   }
 }
@@ -141,6 +154,57 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ C
     int b = b0 + bg + 8 * i;
     T[(((size_t)j * m + k) * kH + b) * kH + c0 + c] = 2.0f * acc[i];
   }
+}
+
+// ---- K2q: 16-bit quantised copy of the tables for the K3 pre-filter -----------------------------------------
+// tmax[j] = max |T[j][k][.][.]| over k != j;  scale_j = tmax[j] / 32767;
+// Tq[j][k][b][pos] = rint(T[j][k][b][c] / scale_j) + 32768 (uint16, 1..65535), the row permuted so that the 16 bytes
+// lane L loads are the 32-bit words w = 0..3 = { lo: c = 4L + w, hi: c = 128 + 4L + w } -- the same candidates the
+// lane owns in the exact path.  |scale_j*(q-32768) - T| <= 0.51*scale_j (rint + one fp32 division rounding).
+static constexpr float kQ = 32767.0f;
+__global__ void __launch_bounds__(256) tmax_kernel(const float* __restrict__ T, int m, unsigned int* __restrict__ tmax) {
+  const int j = blockIdx.y / m, k = blockIdx.y % m;
+  if (j == k) return;
+  const float4* t = reinterpret_cast<const float4*>(T + ((size_t)j * m + k) * kH * kH);
+  float mx = 0.f;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < kH * kH / 4; i += gridDim.x * 256) {
+    const float4 v = t[i];
+    mx = fmaxf(fmaxf(fmaxf(mx, fabsf(v.x)), fmaxf(fabsf(v.y), fabsf(v.z))), fabsf(v.w));
+    if (v.x != v.x || v.y != v.y || v.z != v.z || v.w != v.w) mx = __int_as_float(0x7f800000);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  if ((threadIdx.x & 31) == 0) atomicMax(tmax + j, __float_as_uint(mx));
+}
+
+__global__ void __launch_bounds__(256) quant_tables_kernel(const float* __restrict__ T, int m,
+                                                           const unsigned int* __restrict__ tmax,
+                                                           uint32_t* __restrict__ Tq) {
+  const int j = blockIdx.z / m, k = blockIdx.z % m;
+  if (j == k) return;
+  const float tm = __uint_as_float(tmax[j]);
+  const float scale = (tm > 0.f && tm < __int_as_float(0x7f800000)) ? __fdiv_rn(tm, kQ) : 1.0f;
+  // one thread per 32-bit output word: row b = blockIdx.x*? ...  grid.x * 256 threads cover 256 rows * 128 words
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < kH * (kH / 2); i += gridDim.x * 256) {
+    const int b = i >> 7, word = i & 127, L = word >> 2, w = word & 3;
+    const float* row = T + (((size_t)j * m + k) * kH + b) * kH;
+    const float qlo = rintf(__fdiv_rn(row[4 * L + w], scale)), qhi = rintf(__fdiv_rn(row[128 + 4 * L + w], scale));
+    const uint32_t lo = (uint32_t)((int)fminf(fmaxf(qlo, -kQ), kQ) + 32768);
+    const uint32_t hi = (uint32_t)((int)fminf(fmaxf(qhi, -kQ), kQ) + 32768);
+    Tq[(((size_t)j * m + k) * kH + b) * (kH / 2) + word] = lo | (hi << 16);
+  }
+}
+
+// {1/scale_j, W0_j}: W0_j = 2.002 * ((m-1)*0.51 + 0.75 + 2^-20*(m-1)*32767) is the part of the pre-filter window
+// (in units of scale_j) that does not depend on the vector; degenerate tables (all zero, inf, NaN) get W0 = +inf,
+// which sends every step of that codebook down the exact path.
+__global__ void pf_consts_kernel(const unsigned int* __restrict__ tmax, int m, float2* __restrict__ pfc) {
+  const int j = threadIdx.x;
+  if (j >= m) return;
+  const float tm = __uint_as_float(tmax[j]);
+  const bool ok = m > 1 && tm > 0.f && tm < __int_as_float(0x7f800000);
+  const float w0 = 2.002f * ((float)(m - 1) * 0.51f + 0.75f + 9.5367431640625e-07f * (float)(m - 1) * kQ);
+  pfc[j] = ok ? make_float2(__fdiv_rn(kQ, tm), w0) : make_float2(0.f, __int_as_float(0x7f800000));
 }
 
 // ---- helpers for codes held in two 64-bit registers (m <= 16) -------------------------------------------
@@ -199,6 +263,9 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
 struct IcmParams {
   const float* U;       // [nc][m][256]  unaries of this chunk
   const float* T;       // [m][m][256][256]
+  const uint32_t* Tq;   // [m][m][256][128] quantised pairs (K2q), or null: exact path only
+  const float2* pfc;    // [m] {1/scale_j, W0_j} (pf_consts_kernel)
+  const unsigned int* umax;  // [nc] float bits of max |U[l][.]|
   const float* X;       // [nc][d]
   const float* C;       // [m*256][d]
   uint8_t* B;           // [nc][m] in/out
@@ -207,7 +274,8 @@ struct IcmParams {
   const int* snap_iters;  // [n_snap] (1-based ILS iteration counts)
   uint8_t* B_snap;      // [n_snap][n_total][m], already offset to this chunk's first vector
   int* stats;           // [ilsiter][2] (#equal, #better)
-  unsigned long long* steps;  // [1] conditioning steps actually executed (memoisation skips the rest)
+  unsigned long long* steps;  // [2] conditioning steps actually executed (memoisation skips the rest); of those,
+                              //     steps the quantised pre-filter could not decide (exact path taken)
   int64_t nc, n_total, g0;
   uint64_t seed;
   int d, ilsiter, icmiter, npert, n_snap;
@@ -220,7 +288,15 @@ struct IcmParams {
 // USM (m <= 8): the vector's m KB of unaries are staged once into the warp's shared-memory slot and every step reads
 // its unary row from there, which takes 1/m of the gather traffic off L2 (the binding resource, profiles/r1_v2_icm*);
 // 8 warps x (8 KB + d floats) per block -> 3 blocks = 24 warps per SM instead of 32.
-template <int M, bool USM>
+// PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the 16-bit
+// tables (half the bytes of the fp32 rows): S(c) = rint(U_j[c]/scale_j) + sum_k q_jk[b_k][c], with
+//   |scale_j*S(c) - exact(c)| <= scale_j * ((M-1)*0.51 + 0.75)      quantisation of the rows (K2q) and of the unary
+//                              + 2^-20 * (umax + (M-1)*tmax_j)       fp32 roundings of the exact chain
+// =: delta.  Every candidate that can be the exact first-minimum has S <= min(S) + 2*delta/scale_j.  If exactly ONE
+// candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~1-3 % of
+// the steps, scratch/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
+// construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
+template <int M, bool USM, bool PF>
 __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -232,12 +308,14 @@ __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p)
   __syncthreads();
 
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
-  unsigned long long nsteps = 0;
+  unsigned long long nsteps = 0, nexact = 0;
   for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < p.nc; l += wstride) {
     const float* x = p.X + (size_t)l * p.d;
     Code cur = load_code<M>(p.B + (size_t)l * M);
     float curcost = warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
     const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
+    float slack = 0.f;                                          // 2.002 * 2^-20 * umax (PF)
+    if (PF) slack = __uint_as_float(__ldg(p.umax + l)) * (2.002f * 9.5367431640625e-07f);
     if (USM) {
       __syncwarp();
 #pragma unroll
@@ -267,33 +345,79 @@ __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p)
             a0 = __ldg(Ul + j * 64 + lane);
             a1 = __ldg(Ul + j * 64 + 32 + lane);
           }
+          int bc = -1;
+          if (PF) {
+            const float2 pc = __ldg(p.pfc + j);                   // {1/scale_j, W0_j}
+            const float wf = fmaf(slack, pc.x, pc.y);             // window, in units of scale_j
+            if (wf < pc.y + 4.0f) {                               // umax/scale_j < 2^21: integer sums fit (else exact)
+              // ---- quantised pass: lane owns c = 4*lane + w (lo halves) and 128 + 4*lane + w (hi halves) ---------
+              uint32_t sl[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};   // sl = sum lo + (sum hi << 16) (mod 2^32)
+              const char* tqj = reinterpret_cast<const char*>(p.Tq) + (size_t)j * (M * kH * 512) + lane * 16;
+              asm volatile("" : "+l"(tqj));   // keep the base in a register pair: row address = one IMAD.WIDE
 #pragma unroll
-          for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j, encode_icm.cpp:28-45
-            const int k = kk + (kk >= j);
-            const float4* row =
-                reinterpret_cast<const float4*>(p.T + (((size_t)j * M + k) * kH + nb.get(k)) * kH);
-            float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
-            a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
-            a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
-            a1.x = __fadd_rn(a1.x, r1.x); a1.y = __fadd_rn(a1.y, r1.y);
-            a1.z = __fadd_rn(a1.z, r1.z); a1.w = __fadd_rn(a1.w, r1.w);
+              for (int k = 0; k < M; k++) {                        // k is a literal: byte extract + immediate offsets
+                if (k != j) {
+                  const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
+                  const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+                  const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+                  sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
+                  sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
+                }
+              }
+              // S(c) = rint(u(c)/scale_j) + sum_k (q_k(c) - 32768): the unary is rounded by the 1.5*2^23 trick inside
+              // one fma, whose integer image carries the constant 0x4B400000
+              constexpr int K = -0x4B400000 - (M - 1) * 32768;
+              const float uu[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+              int S[8];
+#pragma unroll
+              for (int w4 = 0; w4 < 4; w4++) {
+                S[w4] = (int)(sl[w4] - (sh[w4] << 16)) + (__float_as_int(fmaf(uu[w4], pc.x, 12582912.0f)) + K);
+                S[4 + w4] = (int)sh[w4] + (__float_as_int(fmaf(uu[4 + w4], pc.x, 12582912.0f)) + K);
+              }
+              const int lm = min(min(min(S[0], S[1]), min(S[2], S[3])), min(min(S[4], S[5]), min(S[6], S[7])));
+              const int key = __reduce_min_sync(0xffffffffu, (lm << 5) | lane);      // |S| < 2^22
+              const int thr = (key >> 5) + (int)wf + 1;
+              uint32_t mask = 0;
+#pragma unroll
+              for (int i = 0; i < 8; i++) mask |= (S[i] <= thr) ? (1u << i) : 0u;
+              const int total = __reduce_add_sync(0xffffffffu, __popc(mask));
+              if (total == 1) {                                    // the only candidate inside the window: the argmin
+                const int wl = key & 31;
+                const int i = __shfl_sync(0xffffffffu, __ffs(mask) - 1, wl);
+                bc = (i < 4 ? 0 : 128) + wl * 4 + (i & 3);
+              }
+            }
           }
-          // first-minimum argmin (encode_icm.cpp:47-58): ascending c inside the lane, then a
-          // (value, index)-lexicographic butterfly across lanes
-          float bv = a0.x;
-          int bc = lane * 4;
-          if (a0.y < bv) { bv = a0.y; bc = lane * 4 + 1; }
-          if (a0.z < bv) { bv = a0.z; bc = lane * 4 + 2; }
-          if (a0.w < bv) { bv = a0.w; bc = lane * 4 + 3; }
-          if (a1.x < bv) { bv = a1.x; bc = 128 + lane * 4; }
-          if (a1.y < bv) { bv = a1.y; bc = 128 + lane * 4 + 1; }
-          if (a1.z < bv) { bv = a1.z; bc = 128 + lane * 4 + 2; }
-          if (a1.w < bv) { bv = a1.w; bc = 128 + lane * 4 + 3; }
+          if (bc < 0) {
+            if (PF) nexact++;
 #pragma unroll
-          for (int off = 16; off > 0; off >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-            int oc = __shfl_xor_sync(0xffffffffu, bc, off);
-            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j, encode_icm.cpp:28-45
+              const int k = kk + (kk >= j);
+              const float4* row =
+                  reinterpret_cast<const float4*>(p.T + (((size_t)j * M + k) * kH + nb.get(k)) * kH);
+              float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
+              a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
+              a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
+              a1.x = __fadd_rn(a1.x, r1.x); a1.y = __fadd_rn(a1.y, r1.y);
+              a1.z = __fadd_rn(a1.z, r1.z); a1.w = __fadd_rn(a1.w, r1.w);
+            }
+            // first-minimum argmin (encode_icm.cpp:47-58): ascending c inside the lane, then a
+            // (value, index)-lexicographic butterfly across lanes
+            float bv = a0.x;
+            bc = lane * 4;
+            if (a0.y < bv) { bv = a0.y; bc = lane * 4 + 1; }
+            if (a0.z < bv) { bv = a0.z; bc = lane * 4 + 2; }
+            if (a0.w < bv) { bv = a0.w; bc = lane * 4 + 3; }
+            if (a1.x < bv) { bv = a1.x; bc = 128 + lane * 4; }
+            if (a1.y < bv) { bv = a1.y; bc = 128 + lane * 4 + 1; }
+            if (a1.z < bv) { bv = a1.z; bc = 128 + lane * 4 + 2; }
+            if (a1.w < bv) { bv = a1.w; bc = 128 + lane * 4 + 3; }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+              float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+              int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+              if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+            }
           }
           dirty &= ~(1u << j);
           if ((uint32_t)bc != nb.get(j)) {
@@ -319,6 +443,7 @@ __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p)
     if (p.cost && lane == 0) p.cost[l] = curcost;
   }
   if (lane == 0 && nsteps) atomicAdd(p.steps, nsteps);
+  if (lane == 0 && nexact) atomicAdd(p.steps + 1, nexact);
   __syncthreads();
   if (p.stats)
     for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x)
@@ -550,7 +675,12 @@ __global__ void __launch_bounds__(256) condition_kernel(uint8_t* __restrict__ B,
 // ======================================================================================================
 using namespace ryl;
 
-static thread_local uint64_t g_icm_steps_done = 0, g_icm_steps_total = 0;
+static thread_local uint64_t g_icm_steps_done = 0, g_icm_steps_total = 0, g_icm_steps_exact = 0;
+
+extern "C" int rayuela_encode_icm_exact_steps(uint64_t* exact) {
+  if (exact) *exact = g_icm_steps_exact;
+  return RAYUELA_OK;
+}
 
 extern "C" int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total) {
   if (executed) *executed = g_icm_steps_done;
@@ -558,10 +688,26 @@ extern "C" int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total) {
   return RAYUELA_OK;
 }
 
+static bool env_off(const char* name) {
+  const char* e = getenv(name);
+  return e && *e && atoi(e) == 0;
+}
+
+// tuning knobs: RAYUELA_B200_ICM_USM=0 reads the unaries from L2 instead of staging them in shared memory (m <= 8),
+// RAYUELA_B200_ICM_PF=0 disables the quantised pre-filter
 static bool icm_unaries_in_smem(int m, size_t smem_plain) {
-  const char* e = getenv("RAYUELA_B200_ICM_USM");       // tuning knob: 0 = unaries from L2 (default: staged in smem)
-  if (m > 8 || (e && *e && atoi(e) == 0)) return false;
+  if (m > 8 || env_off("RAYUELA_B200_ICM_USM")) return false;
   return smem_plain + (size_t)8 * m * kH * sizeof(float) <= 72 * 1024;   // 3 blocks per SM must still fit
+}
+
+template <int M, bool USM, bool PF>
+static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
+  const int warps = 8;
+  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, USM, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t need = (p.nc + warps - 1) / warps;
+  const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * (USM ? 3 : 4));  // blocks of 8 warps per SM
+  RYL_LAUNCH((icm_warp_kernel<M, USM, PF>), grid, warps * 32, smem, s, p);
+  return RAYUELA_OK;
 }
 
 template <int M>
@@ -569,20 +715,14 @@ static int launch_icm(const IcmParams& p, cudaStream_t s) {
   const int warps = 8;
   size_t smem = (size_t)warps * p.d * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
-  int64_t need = (p.nc + warps - 1) / warps;
+  const bool pf = p.Tq != nullptr;
   if constexpr (M <= 8) {
     if (icm_unaries_in_smem(M, smem)) {
       smem += (size_t)warps * M * kH * sizeof(float);
-      RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 3);  // 3 blocks of 8 warps per SM
-      RYL_LAUNCH((icm_warp_kernel<M, true>), grid, warps * 32, smem, s, p);
-      return RAYUELA_OK;
+      return pf ? launch_icm_v<M, true, true>(p, smem, s) : launch_icm_v<M, true, false>(p, smem, s);
     }
   }
-  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);  // 4 blocks of 8 warps per SM
-  RYL_LAUNCH((icm_warp_kernel<M, false>), grid, warps * 32, smem, s, p);
-  return RAYUELA_OK;
+  return pf ? launch_icm_v<M, false, true>(p, smem, s) : launch_icm_v<M, false, false>(p, smem, s);
 }
 
 template <int M>
@@ -679,7 +819,7 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   RYL_CUDA(cudaMemcpyAsync(ord_d.p, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   RYL_TRY(snapit_d.alloc((size_t)std::max(n_snap, 1) * sizeof(int), s));
   if (n_snap) RYL_CUDA(cudaMemcpyAsync(snapit_d.p, snap_iters, n_snap * sizeof(int), cudaMemcpyHostToDevice, s));
-  RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int) + 8, s));   // + 8: executed-step counter
+  RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int) + 16, s));   // + 16: executed / exact-path step counters
   RYL_CUDA(cudaMemsetAsync(stats_d.p, 0, stats_d.bytes, s));
   unsigned long long* steps_d = reinterpret_cast<unsigned long long*>(stats_d.as<int>() + (size_t)std::max(ilsiter, 1) * 2);
 
@@ -688,6 +828,21 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   RYL_LAUNCH(sqnorm_kernel, (mh + 255) / 256, 256, 0, s, c_in.d, d, mh, nrm_d.as<float>());
   RYL_TRY(T_d.alloc((size_t)m * m * kH * kH * sizeof(float), s));
   if (m > 1) RYL_LAUNCH(tables_kernel, dim3(kH / 32, kH / 32, m * m), 256, 0, s, c_in.d, T_d.as<float>(), d, m);
+  // K2q: quantised copy for the pre-filter
+  const bool pf = !env_off("RAYUELA_B200_ICM_PF");
+  DevBuf Tq_d, tmax_d, umax_d, pfc_d;
+  if (pf) {
+    RYL_TRY(Tq_d.alloc((size_t)m * m * kH * (kH / 2) * sizeof(uint32_t), s));
+    RYL_TRY(tmax_d.alloc((size_t)m * sizeof(unsigned int), s));
+    RYL_CUDA(cudaMemsetAsync(tmax_d.p, 0, tmax_d.bytes, s));
+    if (m > 1) {
+      RYL_LAUNCH(tmax_kernel, dim3(8, m * m), 256, 0, s, T_d.as<float>(), m, tmax_d.as<unsigned int>());
+      RYL_LAUNCH(quant_tables_kernel, dim3(32, 1, m * m), 256, 0, s, T_d.as<float>(), m, tmax_d.as<unsigned int>(),
+                 Tq_d.as<uint32_t>());
+    }
+    RYL_TRY(pfc_d.alloc((size_t)m * sizeof(float2), s));
+    RYL_LAUNCH(pf_consts_kernel, 1, 32, 0, s, tmax_d.as<unsigned int>(), m, pfc_d.as<float2>());
+  }
 
   // chunk the base set so the unary buffer (m KB per vector) stays within budget (nsplits of
   // src/LSQ_GPU.jl:226-255, done in space on one device instead of by the caller)
@@ -695,18 +850,23 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
   DevBuf U_d;
   RYL_TRY(U_d.alloc((size_t)std::min(chunk, n) * per_vec, s));
+  if (pf) RYL_TRY(umax_d.alloc((size_t)std::min(chunk, n) * sizeof(unsigned int), s));
   for (int64_t l0 = 0; l0 < n; l0 += chunk) {
     const int64_t nc = std::min(chunk, n - l0);
     dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
+    if (pf) RYL_CUDA(cudaMemsetAsync(umax_d.p, 0, (size_t)nc * sizeof(unsigned int), s));
     if (d % 4 == 0)
       RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh);
+                 U_d.as<float>(), nc, d, mh, umax_d.as<unsigned int>());
     else
       RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh);
+                 U_d.as<float>(), nc, d, mh, umax_d.as<unsigned int>());
     IcmParams p;
     p.U = U_d.as<float>();
     p.T = T_d.as<float>();
+    p.Tq = pf ? Tq_d.as<uint32_t>() : nullptr;
+    p.pfc = pfc_d.as<float2>();
+    p.umax = umax_d.as<unsigned int>();
     p.X = x_in.d + (size_t)l0 * d;
     p.C = c_in.d;
     p.B = b_io.d + (size_t)l0 * m;
@@ -747,11 +907,12 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   RYL_TRY(snap_out.flush(s));
   RYL_TRY(cost_o.flush(s));
   if (stats) {
-    unsigned long long done_steps = 0;
+    unsigned long long done_steps[2] = {0, 0};
     RYL_CUDA(cudaMemcpyAsync(stats, stats_d.p, (size_t)ilsiter * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    RYL_CUDA(cudaMemcpyAsync(&done_steps, steps_d, sizeof(done_steps), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaMemcpyAsync(done_steps, steps_d, sizeof(done_steps), cudaMemcpyDeviceToHost, s));
     RYL_CUDA(cudaStreamSynchronize(s));
-    g_icm_steps_done = done_steps;
+    g_icm_steps_done = done_steps[0];
+    g_icm_steps_exact = pf ? done_steps[1] : done_steps[0];
     g_icm_steps_total = (uint64_t)n * ilsiter * icmiter * m;
   }
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
@@ -864,10 +1025,10 @@ extern "C" int rayuela_quantize_chainq(const float* X, const float* C, int64_t n
     dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
     if (d % 4 == 0)
       RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh);
+                 U_d.as<float>(), nc, d, mh, (unsigned int*)nullptr);
     else
       RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh);
+                 U_d.as<float>(), nc, d, mh, (unsigned int*)nullptr);
     RYL_TRY(launch_viterbi(U_d.as<float>(), TT, tt_stride, nc, m, b_out.d + (size_t)l0 * m, s));
   }
   RYL_TRY(b_out.flush(s));

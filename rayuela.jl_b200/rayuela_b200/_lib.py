@@ -24,6 +24,7 @@ SIGNATURES = {
     "rayuela_encode_icm": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _int, ct.c_uint64, _i64,
                                   _vp, _vp, _int, _vp, _vp, _vp, _vp, ct.c_uint, _vp]),
     "rayuela_encode_icm_steps": (_int, [_vp, _vp]),
+    "rayuela_encode_icm_exact_steps": (_int, [_vp]),
     "rayuela_veccost": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, ct.c_uint, _vp]),
     "condition": (None, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int]),
     "linscan_aqd_query": (None, [_vp, _vp, _vp, _vp, _vp, _int, ct.c_uint, _int, _int, _int, _int, _int]),

@@ -142,6 +142,13 @@ def last_icm_steps():
     return int(a.value), int(b.value)
 
 
+def last_icm_exact_steps():
+    """Executed steps of that call that re-read the exact fp32 rows (the quantised pre-filter left a near-tie)."""
+    a = ct.c_uint64(0)
+    check(_lib.lib().rayuela_encode_icm_exact_steps(ct.addressof(a)))
+    return int(a.value)
+
+
 def veccost(X, B, C, want_mean=False):
     """veccost / qerror (src/qerrors.jl:36-74)."""
     L = _lib.lib()
