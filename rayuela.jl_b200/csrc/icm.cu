@@ -285,9 +285,6 @@ struct IcmParams {
 // Lane owns candidates c = r*128 + lane*4 + e (r<2, e<4): every 1 KB row (unary or pairwise) is two
 // coalesced 512 B float4 loads per warp.  Unaries are re-read per step but a vector's 8 KB stay L2-resident
 // for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
-// USM (m <= 8): the vector's m KB of unaries are staged once into the warp's shared-memory slot and every step reads
-// its unary row from there, which takes 1/m of the gather traffic off L2 (the binding resource, profiles/r1_v2_icm*);
-// 8 warps x (8 KB + d floats) per block -> 3 blocks = 24 warps per SM instead of 32.
 // PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the 16-bit
 // tables (half the bytes of the fp32 rows): S(c) = rint(U_j[c]/scale_j) + sum_k q_jk[b_k][c], with
 //   |scale_j*S(c) - exact(c)| <= scale_j * ((M-1)*0.51 + 0.75)      quantisation of the rows (K2q) and of the unary
@@ -296,14 +293,12 @@ struct IcmParams {
 // candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~1-3 % of
 // the steps, scratch/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
 // construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
-template <int M, bool USM, bool PF>
-__global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p) {
+template <int M, bool PF>
+__global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float4* us = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * (M * 64);      // [M][64] float4, USM only
-  float* smem_f = reinterpret_cast<float*>(smem_raw) + (USM ? (size_t)nwarps * M * kH : 0);
-  float* sq = smem_f + (size_t)warp * p.d;
-  int* stats_s = reinterpret_cast<int*>(smem_f + (size_t)nwarps * p.d);
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.d;
+  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * p.d);
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
   __syncthreads();
 
@@ -316,12 +311,6 @@ __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p)
     const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
     float slack = 0.f;                                          // 2.002 * 2^-20 * umax (PF)
     if (PF) slack = __uint_as_float(__ldg(p.umax + l)) * (2.002f * 9.5367431640625e-07f);
-    if (USM) {
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < M * 2; i++) us[i * 32 + lane] = __ldg(Ul + i * 32 + lane);
-      __syncwarp();
-    }
 
     for (int it = 0; it < p.ilsiter; it++) {
       Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
@@ -337,14 +326,8 @@ __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p)
           const int j = __ldg(order + s);
           if (!((dirty >> j) & 1u)) continue;
           nsteps++;
-          float4 a0, a1;
-          if (USM) {
-            a0 = us[j * 64 + lane];
-            a1 = us[j * 64 + 32 + lane];
-          } else {
-            a0 = __ldg(Ul + j * 64 + lane);
-            a1 = __ldg(Ul + j * 64 + 32 + lane);
-          }
+          float4 a0 = __ldg(Ul + j * 64 + lane);
+          float4 a1 = __ldg(Ul + j * 64 + 32 + lane);
           int bc = -1;
           if (PF) {
             const float2 pc = __ldg(p.pfc + j);                   // {1/scale_j, W0_j}
@@ -418,6 +401,8 @@ __global__ void __launch_bounds__(256, USM ? 3 : 4) icm_warp_kernel(IcmParams p)
               int oc = __shfl_xor_sync(0xffffffffu, bc, off);
               if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
             }
+            bc = __shfl_sync(0xffffffffu, bc, 0);   // NaN sums compare false everywhere: take lane 0's view (c = 0
+                                                    // first, like the sequential scan of encode_icm.cpp:47-58)
           }
           dirty &= ~(1u << j);
           if ((uint32_t)bc != nb.get(j)) {
@@ -693,36 +678,23 @@ static bool env_off(const char* name) {
   return e && *e && atoi(e) == 0;
 }
 
-// tuning knobs: RAYUELA_B200_ICM_USM=0 reads the unaries from L2 instead of staging them in shared memory (m <= 8),
-// RAYUELA_B200_ICM_PF=0 disables the quantised pre-filter
-static bool icm_unaries_in_smem(int m, size_t smem_plain) {
-  if (m > 8 || env_off("RAYUELA_B200_ICM_USM")) return false;
-  return smem_plain + (size_t)8 * m * kH * sizeof(float) <= 72 * 1024;   // 3 blocks per SM must still fit
-}
-
-template <int M, bool USM, bool PF>
+// tuning knob: RAYUELA_B200_ICM_PF=0 disables the quantised pre-filter (every step reads the exact fp32 rows)
+template <int M, bool PF>
 static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
   const int warps = 8;
-  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, USM, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t need = (p.nc + warps - 1) / warps;
-  const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * (USM ? 3 : 4));  // blocks of 8 warps per SM
-  RYL_LAUNCH((icm_warp_kernel<M, USM, PF>), grid, warps * 32, smem, s, p);
+  const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);  // 4 blocks of 8 warps per SM
+  RYL_LAUNCH((icm_warp_kernel<M, PF>), grid, warps * 32, smem, s, p);
   return RAYUELA_OK;
 }
 
 template <int M>
 static int launch_icm(const IcmParams& p, cudaStream_t s) {
   const int warps = 8;
-  size_t smem = (size_t)warps * p.d * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
+  const size_t smem = (size_t)warps * p.d * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
-  const bool pf = p.Tq != nullptr;
-  if constexpr (M <= 8) {
-    if (icm_unaries_in_smem(M, smem)) {
-      smem += (size_t)warps * M * kH * sizeof(float);
-      return pf ? launch_icm_v<M, true, true>(p, smem, s) : launch_icm_v<M, true, false>(p, smem, s);
-    }
-  }
-  return pf ? launch_icm_v<M, false, true>(p, smem, s) : launch_icm_v<M, false, false>(p, smem, s);
+  return p.Tq ? launch_icm_v<M, true>(p, smem, s) : launch_icm_v<M, false>(p, smem, s);
 }
 
 template <int M>

@@ -220,7 +220,7 @@ def test_scan_compaction_schedule_does_not_change_results(rb, monkeypatch, m, k)
         assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0)), soft
 
 
-def test_icm_unaries_in_smem_variant_agrees(rb, monkeypatch):
+def test_icm_prefilter_on_and_off_agree(rb, monkeypatch):
     r = np.random.default_rng(3)
     n, d, m = 5000, 48, 8
     X = r.standard_normal((n, d)).astype(np.float32)
@@ -228,10 +228,40 @@ def test_icm_unaries_in_smem_variant_agrees(rb, monkeypatch):
     B = r.integers(0, 256, (n, m), dtype=np.uint8)
     want = orc.encode_icm(X, C, B, 3, 4, 4, True, seed=9)
     for val in ("0", "1"):
-        monkeypatch.setenv("RAYUELA_B200_ICM_USM", val)
-        got = rb.core.encode_icm(X, C, B, 3, 4, 4, True, seed=9, want_cost=True)
+        monkeypatch.setenv("RAYUELA_B200_ICM_PF", val)
+        got = rb.core.encode_icm(X, C, B, 3, 4, 4, True, seed=9, want_cost=True, want_stats=True)
         assert np.array_equal(got["B"], want["B"]), val
         assert np.array_equal(bits(got["cost"]), bits(want["cost"])), val
+        ex, tot = rb.core.last_icm_steps()
+        exact = rb.core.last_icm_exact_steps()
+        assert 0 < ex <= tot and (exact == ex if val == "0" else exact < ex // 4), (val, ex, tot, exact)
+
+
+@pytest.mark.parametrize("case", ["ties", "zero_codebook", "huge_unaries", "nan_input"])
+def test_icm_prefilter_degenerate_inputs(rb, case):
+    """Inputs on which the quantised pre-filter cannot decide anything must fall back to the exact rows and still
+    give the oracle's codes: exact ties everywhere, an all-zero codebook (tmax = 0 for its partner tables), unaries
+    far above the table range (integer sums would overflow), NaN in the data."""
+    r = np.random.default_rng(11)
+    n, d, m = 3000, 16, 8
+    X = r.standard_normal((n, d)).astype(np.float32)
+    C = (r.standard_normal((m * 256, d)) / 3).astype(np.float32)
+    if case == "ties":
+        X, C = np.round(X), np.round(C * 2)                      # small integers: masses of exactly equal sums
+        C[256:512] = C[:256]                                     # two identical codebooks
+    elif case == "zero_codebook":
+        C[3 * 256:4 * 256] = 0
+    elif case == "huge_unaries":
+        X *= 1e9
+        C[:256] *= 1e-3
+    elif case == "nan_input":
+        X[7, 3] = np.nan
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    want = orc.encode_icm(X, C, B, 2, 3, 4, True, seed=5)
+    got = rb.core.encode_icm(X, C, B, 2, 3, 4, True, seed=5, want_cost=True)
+    ok = ~np.isnan(want["cost"])
+    assert np.array_equal(got["B"][ok], want["B"][ok])
+    assert np.array_equal(bits(got["cost"][ok]), bits(want["cost"][ok]))
 
 
 def test_scan_compat_symbols(rb):
