@@ -33,10 +33,10 @@ H = 256
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the SAME workload
-# (profiles/r1_v2_icm_warp_kernel_full_workload.txt, profiles/r1_v2_scan8_kernel.txt); bench.py cannot run ncu.
+# (profiles/r1_v3_icm_warp_kernel_full_workload.txt, profiles/r1_v3_scanx8_kernel.txt); bench.py cannot run ncu.
 NCU_TRAFFIC = {
-    ("icm", 1_000_000, 128, 8, 32): 13.426433e9 + 24.938240e6,
-    ("scan", 1_000_000, 10_000, 8, 1): 175.220736e6 + 53.773568e6,
+    ("icm", 1_000_000, 128, 8, 32): 10.561672e9 + 25.427456e6,
+    ("scan", 1_000_000, 10_000, 8, 1): 98.904064e6 + 14.063104e6,
 }
 
 
@@ -370,7 +370,11 @@ def run_ours(args, cfg):
     core.encode_icm(X, C, B0.clone(), cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0,
                     inplace=True, want_stats=True)          # untimed: executed-step count of the same workload
     steps_done, steps_total = core.last_icm_steps()
-    gather_bytes = float(steps_done) * (m - 1) * H * 4      # rows actually gathered (memoised steps read nothing)
+    steps_exact = core.last_icm_exact_steps()
+    # bytes the kernel actually gathers: a 512 B quantised row per (step, other codebook) + the step's 1 KB unary row,
+    # and the 1 KB fp32 rows again for the steps the pre-filter left undecided; memoised steps read nothing
+    gather_bytes = float(steps_done) * ((m - 1) * H * 2 + H * 4) + float(steps_exact) * (m - 1) * H * 4
+    # SURVEY 8d algorithmic figure: every reference step gathers (m-1) fp32 rows of 256 entries
     gather_bytes_ref = float(n) * cfg["ilsiter"] * cfg["icmiter"] * m * (m - 1) * H * 4
     qerr = core.qerror(X, Bwork, C)
     qerr0 = core.qerror(X, B0, C)
@@ -461,17 +465,18 @@ def run_ours(args, cfg):
 
     sm_mhz = clocks.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
     onchip_peak = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s of L1/shared load bandwidth at the sampled clock
-    icm_roof = {"bound": "hbm", "achieved": gather_bytes / (k3_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+    icm_roof = {"bound": "hbm", "achieved": gather_bytes_ref / (k3_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                 "unit": "GB/s", "traffic": NCU_TRAFFIC.get(("icm", n, d, m, cfg["ilsiter"])), "peak_source": pk_src,
-                "kernel": "icm_warp_kernel<%d>" % m, "kernel_ms": k3_ms,
+                "kernel": "icm_warp_kernel<%d,true>" % m, "kernel_ms": k3_ms,
                 "onchip_peak": onchip_peak,
-                "steps_executed": steps_done, "steps_reference": steps_total,
-                "reference_equiv_achieved": gather_bytes_ref / (k3_ms * 1e-3) / 1e9,
-                "note": "algorithmic bytes = pairwise-table rows actually gathered: executed steps*(m-1)*256*4 "
-                        "(SURVEY 8d per-step figure; steps whose conditioning codes did not change are memoised "
-                        "and read nothing -- reference_equiv_achieved counts them as the reference would). Rows are "
-                        "served by L2/L1, not HBM, so `frac` against the HBM copy peak exceeds 1; onchip_frac is "
-                        "the same figure against 148 SM x 128 B/clk x sampled SM clock"}
+                "steps_executed": steps_done, "steps_reference": steps_total, "steps_exact_rows": steps_exact,
+                "gathered_actual": gather_bytes / (k3_ms * 1e-3) / 1e9,
+                "note": "achieved = SURVEY 8d algorithmic bytes (n*ilsiter*icmiter*m*(m-1)*256*4, what the reference's "
+                        "steps gather) / K3 time. The kernel itself gathers less (gathered_actual): steps whose "
+                        "conditioning codes did not change are memoised, and a step reads 512 B 16-bit rows unless "
+                        "the pre-filter leaves a near-tie (steps_exact_rows). Rows are served by L2, not HBM, so "
+                        "`frac` against the HBM copy peak exceeds 1 by construction; onchip_frac is the same figure "
+                        "against 148 SM x 128 B/clk x sampled SM clock; `traffic` is the ncu DRAM figure"}
     icm_roof["frac"] = icm_roof["achieved"] / icm_roof["peak"]
     icm_roof["onchip_frac"] = icm_roof["achieved"] / onchip_peak
     scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base

@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
   constexpr int BM = 128, BN = 128, BK = 8;
   __shared__ __align__(16) float As[BK][BM];
   __shared__ __align__(16) float Bs[BK][BN];
+  __shared__ float Rs[16][BN];                       // per-vector |U| maxima of the 16 entry groups (umax epilogue)
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int e0 = blockIdx.x * BM;
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
 #pragma unroll
   for (int j = 0; j < 8; j++) {
     int64_t l = l0 + tx * 8 + j;
+    float mx = 0.f;
     if (l < n) {
       float o[8];
 #pragma unroll
@@ -105,17 +107,23 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
       float* dst = U + (size_t)l * mh + e0 + ty * 8;
       *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
       *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-      if (umax) {
-        float mx = 0.f;
-        bool bad = false;
+      bool bad = false;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          mx = fmaxf(mx, fabsf(o[i]));
-          bad |= o[i] != o[i];
-        }
-        if (bad) mx = __int_as_float(0x7f800000);               // NaN unaries -> +inf slack -> exact path
-        atomicMax(umax + l, __float_as_uint(mx));
+      for (int i = 0; i < 8; i++) {
+        mx = fmaxf(mx, fabsf(o[i]));
+        bad |= o[i] != o[i];
       }
+      if (bad) mx = __int_as_float(0x7f800000);                 // NaN unaries -> +inf slack -> exact path
+    }
+    if (umax) Rs[ty][tx * 8 + j] = mx;
+  }
+  if (umax) {   // one atomic per vector per block: max over the block's 128 entries
+    __syncthreads();
+    if (tid < BN) {
+      float mx = 0.f;
+#pragma unroll
+      for (int t = 0; t < 16; t++) mx = fmaxf(mx, Rs[t][tid]);
+      if (l0 + tid < n) atomicMax(umax + l0 + tid, __float_as_uint(mx));
     }
   }
 }
