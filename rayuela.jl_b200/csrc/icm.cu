@@ -52,16 +52,18 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < d; k0 += BK) {
-    float a[4], b[4];
-    const float* ap = C + (size_t)(e0 + lr) * d + k0 + lk;
-    const int64_t lv = l0 + lr;
-    const float* bp = X + (size_t)(lv < n ? lv : n - 1) * d + k0 + lk;
+  // software pipeline: the global loads of tile k0+BK are issued before the FMAs of tile k0 and land in registers
+  // while those run; each output is still ONE sequential-t fmaf chain
+  const float* arow = C + (size_t)(e0 + lr) * d + lk;
+  const int64_t lv = l0 + lr;
+  const float* brow = X + (size_t)(lv < n ? lv : n - 1) * d + lk;
+  float a[4], b[4];
+  auto fetch = [&](int k0) {
     if (VEC4) {
       float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
       if (k0 + lk < d) {  // d % 4 == 0: a quad is entirely inside or entirely outside
-        av = *reinterpret_cast<const float4*>(ap);
-        bv = *reinterpret_cast<const float4*>(bp);
+        av = *reinterpret_cast<const float4*>(arow + k0);
+        bv = *reinterpret_cast<const float4*>(brow + k0);
       }
       a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
       b[0] = bv.x; b[1] = bv.y; b[2] = bv.z; b[3] = bv.w;
@@ -69,27 +71,38 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
 #pragma unroll
       for (int i = 0; i < 4; i++) {
         bool ok = k0 + lk + i < d;
-        a[i] = ok ? ap[i] : 0.f;
-        b[i] = ok ? bp[i] : 0.f;
+        a[i] = ok ? arow[k0 + i] : 0.f;
+        b[i] = ok ? brow[k0 + i] : 0.f;
       }
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < d; k0 += BK) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       As[lk + i][lr] = a[i];
       Bs[lk + i][lr] = b[i];
     }
     __syncthreads();
-    const int kmax = min(BK, d - k0);  // the chain is exactly d long, like the oracle's dot_seq
-    for (int kk = 0; kk < kmax; kk++) {
+    if (k0 + BK < d) fetch(k0 + BK);
+    auto kstep = [&](int kk) {
       float av[8], bv[8];
       *reinterpret_cast<float4*>(&av[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
       *reinterpret_cast<float4*>(&av[4]) = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-      *reinterpret_cast<float4*>(&bv[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
-      *reinterpret_cast<float4*>(&bv[4]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      // vectors of thread tx: 4*tx .. 4*tx+3 and 64 + 4*tx .. 64 + 4*tx+3 -> consecutive lanes read consecutive
+      // 16 B chunks (no bank conflicts; 8 consecutive floats per lane collide 2-way)
+      *reinterpret_cast<float4*>(&bv[0]) = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      *reinterpret_cast<float4*>(&bv[4]) = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
 #pragma unroll
       for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    };
+    if (k0 + BK <= d) {                  // full tile: unrolled, so the shared loads run ahead of the FMAs
+#pragma unroll
+      for (int kk = 0; kk < BK; kk++) kstep(kk);
+    } else {                             // the chain is exactly d long, like the oracle's dot_seq
+      for (int kk = 0; kk < d - k0; kk++) kstep(kk);
     }
     __syncthreads();
   }
@@ -98,7 +111,8 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
   for (int i = 0; i < 8; i++) nr[i] = nrm[e0 + ty * 8 + i];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    int64_t l = l0 + tx * 8 + j;
+    const int vt = (j < 4 ? 0 : 60) + tx * 4 + j;               // vector within the tile (see the Bs reads)
+    int64_t l = l0 + vt;
     float mx = 0.f;
     if (l < n) {
       float o[8];
@@ -115,7 +129,7 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
       }
       if (bad) mx = __int_as_float(0x7f800000);                 // NaN unaries -> +inf slack -> exact path
     }
-    if (umax) Rs[ty][tx * 8 + j] = mx;
+    if (umax) Rs[ty][vt] = mx;
   }
   if (umax) {   // one atomic per vector per block: max over the block's 128 entries
     __syncthreads();
