@@ -6,6 +6,7 @@
 // Replaces deps/src/linscan_aqd.cpp:37-102 and deps/src/linscan_aqd_pairwise_byte.cpp:14-176.
 #include <algorithm>
 #include <cstring>
+#include <limits>
 
 #include "common.cuh"
 
@@ -291,6 +292,7 @@ struct ScanXParams {
   int64_t n, nchunks, chunks_per_slice;
   int nq, k, cap, soft;
   int piggy;             // a service() also compacts every buffer already past this many keys
+  float tau0;            // initial threshold (+inf; a finite value is a measurement aid, RAYUELA_B200_SCAN_TAU0)
 };
 
 template <int P, bool NORMS>
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   }
   if (tid < 16) {
     cnt_s[tid] = 0;
-    tau_s[tid] = __int_as_float(0x7f800000);
+    tau_s[tid] = p.tau0;
     lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
   }
   if (tid == 0) {
@@ -373,7 +375,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   }
   float tau[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) tau[i] = __int_as_float(0x7f800000);
+  for (int i = 0; i < 8; i++) tau[i] = p.tau0;
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
   int warm = 1;
 
@@ -844,6 +846,8 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       p.cap = cap;
       p.soft = soft;
       p.piggy = kp + (soft - kp) / 2;   // a service() also compacts buffers already half-way to the soft limit
+      p.tau0 = std::numeric_limits<float>::infinity();
+      if (const char* e = getenv("RAYUELA_B200_SCAN_TAU0")) p.tau0 = (float)atof(e);   // measurement aid only
 #define RYL_SCANX(PP, NN)                                                                                          \
   {                                                                                                                \
     RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
