@@ -282,6 +282,28 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
   return acc;
 }
 
+// L2 eviction-priority hints: with m = 16 the in-flight vectors' unaries (32 warps x 148 SMs x 16 KB = 78 MB) plus the
+// quantised tables (34 MB) only just fit the 126 MB L2, and plain LRU lets the streaming fp32 rows of the rare exact
+// steps push unary rows out (ncu: 307 GB of DRAM reads per 125k vectors).  Unaries are loaded evict_last, exact
+// fp32 rows evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+
 struct IcmParams {
   const float* U;       // [nc][m][256]  unaries of this chunk
   const float* T;       // [m][m][256][256]
@@ -326,6 +348,7 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
 
   const int64_t wstride = (int64_t)gridDim.x * nwarps;
   unsigned long long nsteps = 0, nexact = 0;
+  const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < p.nc; l += wstride) {
     const float* x = p.X + (size_t)l * p.d;
     Code cur = load_code<M>(p.B + (size_t)l * M);
@@ -348,8 +371,14 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
           const int j = __ldg(order + s);
           if (!((dirty >> j) & 1u)) continue;
           nsteps++;
-          float4 a0 = __ldg(Ul + j * 64 + lane);
-          float4 a1 = __ldg(Ul + j * 64 + 32 + lane);
+          float4 a0, a1;
+          if (M > 8) {
+            a0 = ldg_f4_hint(Ul + j * 64 + lane, pol_keep);
+            a1 = ldg_f4_hint(Ul + j * 64 + 32 + lane, pol_keep);
+          } else {
+            a0 = __ldg(Ul + j * 64 + lane);
+            a1 = __ldg(Ul + j * 64 + 32 + lane);
+          }
           int bc = -1;
           if (PF) {
             const float2 pc = __ldg(p.pfc + j);                   // {1/scale_j, W0_j}
@@ -400,7 +429,14 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
               const int k = kk + (kk >= j);
               const float4* row =
                   reinterpret_cast<const float4*>(p.T + (((size_t)j * M + k) * kH + nb.get(k)) * kH);
-              float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
+              float4 r0, r1;
+              if (PF && M > 8) {
+                r0 = ldg_f4_hint(row + lane, pol_stream);
+                r1 = ldg_f4_hint(row + 32 + lane, pol_stream);
+              } else {
+                r0 = __ldg(row + lane);
+                r1 = __ldg(row + 32 + lane);
+              }
               a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
               a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
               a1.x = __fadd_rn(a1.x, r1.x); a1.y = __fadd_rn(a1.y, r1.y);
@@ -706,7 +742,9 @@ static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
   const int warps = 8;
   RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t need = (p.nc + warps - 1) / warps;
-  const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * 4);  // 4 blocks of 8 warps per SM
+  int per_sm = 4;                                                           // 4 blocks of 8 warps per SM
+  if (const char* e = getenv("RAYUELA_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(4, atoi(e)));   // knob
+  const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * per_sm);
   RYL_LAUNCH((icm_warp_kernel<M, PF>), grid, warps * 32, smem, s, p);
   return RAYUELA_OK;
 }
