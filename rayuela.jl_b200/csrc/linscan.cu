@@ -293,9 +293,12 @@ struct ScanXParams {
   int nq, k, cap, soft;
   int piggy;             // a service() also compacts every buffer already past this many keys
   float tau0;            // initial threshold (+inf; a finite value is a measurement aid, RAYUELA_B200_SCAN_TAU0)
+  int spec;              // speculative thresholds on (verified at the end; a failed block is redone in pass 1)
+  int pass;              // 0: main launch; 1: redo launch -- only blocks whose redo flag is set run, without speculation
+  int* redo;             // [slices][qtiles] flags
 };
 
-template <int P, bool NORMS>
+template <int P, bool NORMS, bool SPEC>
 __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams p) {
   using X = ScanX<P>;
   constexpr int NT = kScan8Warps * 32;
@@ -311,6 +314,9 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   __shared__ int nfin_s;     // warps that have finished their chunks
   __shared__ int warm_s;     // some query still has tau = +inf: react to the flag within the same period
   __shared__ int finq_s[16]; // final phase: query already written by its warp
+  __shared__ int seen_s;     // codes of this block's slice scanned so far (all warps)
+  __shared__ int softq_s[16];// per-query soft limit (lower while a speculative threshold waits for confirmation)
+  __shared__ int fail_s;     // a speculative threshold turned out too tight for some query: redo the block
 
   // dynamic shared memory: [sort buffer 64 KB][pad][LUT tile 128 KB, 32 KB-aligned] -- the alignment makes the
   // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
@@ -336,10 +342,15 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     tau_s[tid] = p.tau0;
     lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
   }
+  if (SPEC && p.pass == 1 && p.redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // redo launch: nothing to redo
+  const bool spec = SPEC && p.pass == 0;           // SPEC = false instantiations carry none of the speculation code
+  if (SPEC && tid < 16) softq_s[tid] = p.soft;
   if (tid == 0) {
     flag_s = 0;
     nfin_s = 0;
     warm_s = 1;
+    seen_s = 0;
+    fail_s = 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -378,6 +389,25 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   for (int i = 0; i < 8; i++) tau[i] = p.tau0;
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
   int warm = 1;
+  const int64_t c0 = (int64_t)slice * p.chunks_per_slice;
+  const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
+  const float nslice = (float)(min(p.n, c1 * kChunkCodes) - c0 * kChunkCodes);     // codes in this block's slice
+
+  // Speculative threshold.  After a compaction the exact k-th smallest key seen so far is known; with a fraction
+  // f = seen/nslice of the slice scanned, the final k-th distance is close to the (k*f)-th smallest seen.  The
+  // filter threshold is therefore tightened to the key of rank r = x + z*sqrt(x) + z*z/2, x = k*f, z = 5.5 (the
+  // count of keys below it in the whole slice is >= k except with probability ~1e-7 on exchangeable data), which
+  // cuts the appends and compactions of large-k searches several-fold.  It is VERIFIED, not trusted: thresholds
+  // only ever decrease, every key <= the final threshold is in the buffer unless k smaller ones are, so the result
+  // is exact iff the k-th smallest key of the final buffer is <= the final threshold; otherwise the block raises
+  // its redo flag and is rerun without speculation by the second launch.
+  bool final_phase = false;                                    // no tightening once the scan is over
+  auto spec_rank = [&]() -> int {
+    if (!SPEC || !spec || final_phase) return p.k;
+    const float x = (float)p.k * fminf(1.0f, (float)seen_s / nslice);
+    const int r = (int)(x + 5.5f * sqrtf(x) + 15.125f) + 1;
+    return (r * 4 < p.k * 3) ? r : p.k;
+  };
 
   // Small buffers (<= kWarpKeys keys) are handled by ONE warp each, all queries of the block at once: the warp
   // sorts its query's keys in its own 4 KB slice of the sort area (warp-level bitonic network, no block barriers)
@@ -410,13 +440,23 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
       for (int t = lane; t < keep; t += 32) cq[t] = wslice[t];
     if (lane == 0) {
       cnt_s[q] = keep;
-      if (c >= p.k) tau_s[q] = ordered_to_f32((uint32_t)(wslice[p.k - 1] >> 32));
+      if (c >= p.k) {
+        const int r = spec_rank();
+        tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(wslice[r - 1] >> 32)));
+        if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
+      }
     }
     return keep;
   };
   auto needs_compaction = [&](int q) -> bool {
     const int c = cnt_s[q];
-    return c > p.piggy || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000));
+    return c > (SPEC ? min(p.piggy, softq_s[q]) : p.piggy) || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000));
+  };
+  // exactness check of a finished query (see spec_rank): kth = k-th smallest key of the final buffer, c its size
+  auto verify = [&](int q, int c, uint64_t kth) {
+    if (!SPEC) return;
+    const float t = tau_s[q];
+    if (c >= p.k ? ordered_to_f32((uint32_t)(kth >> 32)) > t : t < __int_as_float(0x7f800000)) fail_s = 1;
   };
 
   auto compact = [&](int q) {
@@ -432,12 +472,13 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
         __syncthreads();
         if (tid == 0) {
           for (int i = 1; i < kScan8Warps; i++) mx = max(mx, sortbuf[i]);
-          tau_s[q] = ordered_to_f32((uint32_t)(mx >> 32));
+          tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(mx >> 32)));
         }
         __syncthreads();
       }
       return;
     }
+    const int r = spec_rank();                                 // block-uniform (seen_s is stable inside service())
     if (c <= 512) {
       const int np2 = pow2ceil(c);
       for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
@@ -446,7 +487,8 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
       for (int t = tid; t < p.k; t += NT) cq[t] = sortbuf[t];
       if (tid == 0) {
         cnt_s[q] = p.k;
-        tau_s[q] = ordered_to_f32((uint32_t)(sortbuf[p.k - 1] >> 32));
+        tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(sortbuf[r - 1] >> 32)));
+        if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
       }
       __syncthreads();
       return;
@@ -454,15 +496,22 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     for (int t = tid; t < c; t += NT) sortbuf[t] = cq[t];
     __syncthreads();
     const uint64_t pivot = block_radix_select(sortbuf, c, p.k, hist_s, sel_s);
+    uint64_t pivot_r = pivot;
+    if (SPEC && r < p.k) {
+      __syncthreads();
+      pivot_r = block_radix_select(sortbuf, c, r, hist_s, sel_s);
+    }
+    __syncthreads();
     if (tid == 0) sel_s[2] = 0;
     __syncthreads();
     for (int t = tid; t < c; t += NT) {
       const uint64_t key = sortbuf[t];
-      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;
+      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly k keys (keys are distinct)
     }
     if (tid == 0) {
       cnt_s[q] = p.k;
-      tau_s[q] = ordered_to_f32((uint32_t)(pivot >> 32));
+      tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(pivot_r >> 32)));
+      if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
     }
     __syncthreads();
   };
@@ -474,6 +523,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
     __syncthreads();
     block_bitonic_sort(sortbuf, np2);
+    if (tid == 0) verify(q, c, sortbuf[min(c, p.k) - (c > 0)]);
   };
 
   // Compaction is event-driven: the thread whose append pushes a buffer past the soft limit (or completes the first
@@ -482,10 +532,14 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   // Between the raise and the last warp's reaction a query gains at most 2*ADDS keys (two periods of every warp),
   // which the capacity soft + 3*ADDS covers.  Finished warps wait in service() until all warps are done, so the
   // block-wide barriers inside always see all 16 warps.
-  auto service = [&]() -> bool {
+  auto service = [&](int progress) -> bool {            // progress: codes this warp has completed so far
     __syncthreads();                                   // nobody is appending past this point
     const int nf = nfin_s;
     const int fl = *(volatile int*)&flag_s;
+    if (SPEC && fl && spec) {                          // block-wide progress for spec_rank()
+      if (lane == 0) atomicAdd(&seen_s, progress);
+      __syncthreads();
+    }
     if (fl) {
       if (w < QB && cnt_s[w] <= kWarpKeys && needs_compaction(w)) warp_sort_keep(w);   // warp w <-> query w
       __syncthreads();
@@ -493,6 +547,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
         if (needs_compaction(q)) compact(q);                                           // the large ones, block-wide
       if (tid == 0) {
         flag_s = 0;
+        seen_s = 0;
         int warm = 0;
         for (int q = 0; q < QB; q++) warm |= tau_s[q] == __int_as_float(0x7f800000);
         warm_s = warm;
@@ -510,13 +565,12 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     return nf == kScan8Warps;
   };
 
-  const int64_t c0 = (int64_t)slice * p.chunks_per_slice;
-  const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
   const uint32_t n32 = (uint32_t)p.n;
   const float inf = __int_as_float(0x7f800000);
   const uint32_t flag_addr = smem_u32(&flag_s);
 
-  for (int64_t chunk = c0 + w; chunk < c1; chunk += kScan8Warps) {
+  int wdone = 0;                                         // codes of finished chunks of this warp
+  for (int64_t chunk = c0 + w; chunk < c1; chunk += kScan8Warps, wdone += kChunkCodes) {
     const uint4* fp = p.F + chunk * (X::PERIODS * X::HALVES * X::NS) + pidx;
     const float* np = p.norms + chunk * kChunkCodes + pidx;            // norm of the code completed in period t+1
     uint32_t id = (uint32_t)(chunk * kChunkCodes) + pidx - X::NS;      // code completed in period t (t >= 1)
@@ -574,7 +628,8 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
               if (!p.lb || key > lb_s[q]) {
                 const int pos = atomicAdd(&cnt_s[q], 1);
                 cand[(size_t)q * p.cap + pos] = key;
-                if (pos >= p.soft || (tau[i] == inf && pos + 1 >= p.k)) *(volatile int*)&flag_s = 1;
+                if (pos >= (SPEC ? softq_s[q] : p.soft) || (tau[i] == inf && pos + 1 >= p.k))
+                  *(volatile int*)&flag_s = 1;
               }
             }
           }
@@ -589,20 +644,23 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
       np += X::NS;
       id += X::NS;
       // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
-      if (raised || (warm && lds_volatile(flag_addr))) service();
+      if (raised || (warm && lds_volatile(flag_addr))) service(wdone + t * X::NS);
     }
   }
   __syncwarp();
   if (lane == 0) atomicAdd(&nfin_s, 1);
-  while (!service()) {
+  while (!service(wdone)) {
   }
 
   // final phase: small buffers by their own warp (all at once), the rest block-wide
+  final_phase = true;
   if (w < QB) {
     const bool mine = q0 + w < p.nq && cnt_s[w] <= kWarpKeys;
     if (mine) {
+      const int c = cnt_s[w];
       const int keep = warp_sort_keep(w);
       __syncwarp();
+      if (lane == 0) verify(w, c, wslice[max(keep, 1) - 1]);
       uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + w) * p.k;
       for (int i = lane; i < p.k; i += 32) out[i] = i < keep ? wslice[i] : ~0ull;
     }
@@ -617,6 +675,10 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
     for (int i = tid; i < p.k; i += NT) out[i] = i < c ? sortbuf[i] : ~0ull;
     __syncthreads();
+  }
+  if (SPEC) {
+    __syncthreads();
+    if (tid == 0) p.redo[blockIdx.y * gridDim.x + blockIdx.x] = (spec && fail_s) ? 1 : 0;
   }
 }
 
@@ -816,14 +878,28 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       const int cap = soft + 3 * adds;
       // sort buffer + up to 32 KB of padding so the LUT tile starts on a 32 KB boundary + the tile
       const size_t smem = (size_t)kScan8SortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
-      // DB slices: whole waves of query tiles run unsliced; fewer tiles than SMs -> slice the base to fill one wave
-      // (two for small k, where the per-slice warm-up is cheap); S*k must fit one merge pass
+      // DB slices.  A launch of qtiles x S blocks takes ceil(qtiles*S / SMs) waves of (1/S + c) base passes each,
+      // c = per-block fixed cost (LUT staging, threshold warm-up, final selection) ~ 0.065 + 0.0005 k of a pass
+      // (fit to scratch/slices_probe.py): whole waves of tiles stay unsliced, a partial wave is cut so that it fills
+      // the machine once (33 tiles -> 4 slices, 100 tiles -> 4 slices = 2.7 waves of quarter passes, 1 tile -> 61)
       const int64_t unit = (int64_t)kChunkCodes * kScan8Warps;   // codes per block round
+      const int smax = (int)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(1, ix->n / unit), 4 * sms),
+                                              std::max(1, 16384 / kp));
       int S = 1;
-      if (qtiles % sms != 0) S = std::max(1, (kp <= 64 && qtiles * 2 <= sms ? 2 : 1) * sms / qtiles);
+      {
+        const double c = 0.065 + 0.0005 * kp;
+        double best = 1e30;
+        for (int cand_s = 1; cand_s <= smax; cand_s++) {
+          const double waves = (double)(((int64_t)qtiles * cand_s + sms - 1) / sms);
+          const double t = waves * (1.0 / cand_s + c);
+          if (t < best * 0.999) {
+            best = t;
+            S = cand_s;
+          }
+        }
+      }
       if (const char* e = getenv("RAYUELA_B200_SCAN_SLICES")) S = std::max(1, atoi(e));   // tuning knob
-      S = (int)std::min<int64_t>(S, std::max<int64_t>(1, ix->n / unit));
-      S = std::min(S, std::max(1, 16384 / kp));
+      S = std::min(S, std::max(1, std::min(smax, 16384 / kp)));
       int64_t slice_len = (ix->n + S - 1) / S;
       slice_len = (slice_len + unit - 1) / unit * unit;
       S = (int)((ix->n + slice_len - 1) / slice_len);
@@ -848,15 +924,28 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       p.piggy = kp + (soft - kp) / 2;   // a service() also compacts buffers already half-way to the soft limit
       p.tau0 = std::numeric_limits<float>::infinity();
       if (const char* e = getenv("RAYUELA_B200_SCAN_TAU0")) p.tau0 = (float)atof(e);   // measurement aid only
-#define RYL_SCANX(PP, NN)                                                                                          \
-  {                                                                                                                \
-    RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-    RYL_LAUNCH((scanx_kernel<PP, NN>), dim3(qtiles, S), kScan8Warps * 32, smem, s, p);                             \
+      // speculative thresholds (verified; see scanx_kernel): worth it once a compaction is more than a warp's work
+      const char* spec_env = getenv("RAYUELA_B200_SCAN_SPEC");                          // tuning knob: 0 disables
+      p.spec = (kp >= 16 && lbp == nullptr && !(spec_env && atoi(spec_env) == 0)) ? 1 : 0;
+      p.pass = 0;
+      DevBuf redo;
+      RYL_TRY(redo.alloc((size_t)S * qtiles * sizeof(int), s));
+      p.redo = redo.as<int>();
+#define RYL_SCANX(PP, NN, SS)                                                                                        \
+  {                                                                                                                  \
+    RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScan8Warps * 32, smem, s, p);                           \
+    if (SS) { /* redo launch: blocks whose speculation failed rerun exactly, all others exit at once */             \
+      p.pass = 1;                                                                                                    \
+      RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScan8Warps * 32, smem, s, p);                         \
+    }                                                                                                                \
   }
       if (period == 16) {
-        if (norms) RYL_SCANX(16, true) else RYL_SCANX(16, false)
+        if (norms) { if (p.spec) RYL_SCANX(16, true, true) else RYL_SCANX(16, true, false) }
+        else { if (p.spec) RYL_SCANX(16, false, true) else RYL_SCANX(16, false, false) }
       } else {
-        if (norms) RYL_SCANX(8, true) else RYL_SCANX(8, false)
+        if (norms) { if (p.spec) RYL_SCANX(8, true, true) else RYL_SCANX(8, true, false) }
+        else { if (p.spec) RYL_SCANX(8, false, true) else RYL_SCANX(8, false, false) }
       }
 #undef RYL_SCANX
       float* dq = d_out.d + (size_t)qb * k + koff;

@@ -220,6 +220,31 @@ def test_scan_compaction_schedule_does_not_change_results(rb, monkeypatch, m, k)
         assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0)), soft
 
 
+@pytest.mark.parametrize("m,k", [(8, 1000), (8, 64), (16, 300)])
+def test_scan_speculative_threshold_failure_is_redone_exactly(rb, monkeypatch, m, k):
+    """The speculative filter threshold assumes nothing it does not verify: on a base ORDERED by distance to the
+    query (best codes first -- the sample the threshold is estimated from is as unrepresentative as it gets) the
+    verification must fail and the redo launch must return the reference's bits; same with the knob off."""
+    n, nq = 120000, 5
+    B, Xq, cb, nrm = _scan_case(orc.LSQ, n, nq, m, 64, seed=100 + m)
+    fn = orc.ref_linscan if orc.have_ref() else orc.linscan
+    _, order = fn(orc.LSQ, B, Xq[:1], cb, n, nrm)              # full ranking for query 0 (ids are 1-based)
+    perm = order[0].astype(np.int64) - 1
+    B, nrm = np.ascontiguousarray(B[perm]), np.ascontiguousarray(nrm[perm])
+    d0, i0 = fn(orc.LSQ, B, Xq, cb, k, nrm)
+    assert np.array_equal(i0[0], np.arange(1, k + 1))          # query 0's neighbours are now the first k codes
+    for val in ("1", "0"):
+        monkeypatch.setenv("RAYUELA_B200_SCAN_SPEC", val)
+        d1, i1 = rb.core.Index(orc.LSQ, B, nrm).search(Xq, cb, k)
+        assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0)), val
+    # and the mirror image: best codes last
+    B, nrm = np.ascontiguousarray(B[::-1]), np.ascontiguousarray(nrm[::-1])
+    d0, i0 = fn(orc.LSQ, B, Xq, cb, k, nrm)
+    monkeypatch.setenv("RAYUELA_B200_SCAN_SPEC", "1")
+    d1, i1 = rb.core.Index(orc.LSQ, B, nrm).search(Xq, cb, k)
+    assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0))
+
+
 def test_icm_prefilter_on_and_off_agree(rb, monkeypatch):
     r = np.random.default_rng(3)
     n, d, m = 5000, 48, 8
