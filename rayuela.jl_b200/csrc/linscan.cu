@@ -414,27 +414,30 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   // and leaves them there sorted; returns the number of keys kept (min(c, k)).
   constexpr int kWarpKeys = kScan8SortKeys / kScan8Warps;   // 512
   uint64_t* wslice = sortbuf + w * kWarpKeys;
-  auto warp_sort_keep = [&](int q) -> int {
-    const int c = cnt_s[q];
-    uint64_t* cq = cand + (size_t)q * p.cap;
-    const int np2 = max(64, pow2ceil(c));
-    for (int t = lane; t < np2; t += 32) wslice[t] = t < c ? cq[t] : ~0ull;
-    __syncwarp();
+  auto warp_bitonic = [&](uint64_t* buf, int np2) {            // np2 >= 64, a power of two; one warp
     for (int size = 2; size <= np2; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
         for (int t = lane; t < (np2 >> 1); t += 32) {
           const int lo = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
           const int hi = lo | stride;
           const bool up = (lo & size) == 0;
-          const uint64_t a = wslice[lo], b = wslice[hi];
+          const uint64_t a = buf[lo], b = buf[hi];
           if ((a > b) == up) {
-            wslice[lo] = b;
-            wslice[hi] = a;
+            buf[lo] = b;
+            buf[hi] = a;
           }
         }
         __syncwarp();
       }
     }
+  };
+  auto warp_sort_keep = [&](int q) -> int {
+    const int c = cnt_s[q];
+    uint64_t* cq = cand + (size_t)q * p.cap;
+    const int np2 = max(64, pow2ceil(c));
+    for (int t = lane; t < np2; t += 32) wslice[t] = t < c ? cq[t] : ~0ull;
+    __syncwarp();
+    warp_bitonic(wslice, np2);
     const int keep = min(c, p.k);
     if (c > p.k)
       for (int t = lane; t < keep; t += 32) cq[t] = wslice[t];
@@ -667,14 +670,34 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     if (lane == 0) finq_s[w] = mine;
   }
   __syncthreads();
-  for (int q = 0; q < QB; q++) {
-    if (q0 + q >= p.nq) break;
-    if (finq_s[q]) continue;
-    finalize(q);
-    const int c = cnt_s[q];
-    uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
-    for (int i = tid; i < p.k; i += NT) out[i] = i < c ? sortbuf[i] : ~0ull;
+  if (p.k <= 1024) {
+    // large buffers, k <= 1024: block-wide selection of the k smallest of each (one query after the other), then
+    // ALL queries are sorted at once, one warp each, in the (now dead) LUT tile: 16 x 8 KB
+    for (int q = 0; q < QB; q++)
+      if (q0 + q < p.nq && !finq_s[q]) compact(q);
     __syncthreads();
+    uint64_t* wsort = reinterpret_cast<uint64_t*>(smem_raw + (lut_addr - smem_u32(smem_raw))) + w * 1024;
+    if (w < QB && q0 + w < p.nq && !finq_s[w]) {
+      const int c = cnt_s[w];                                  // <= k
+      const uint64_t* cq = cand + (size_t)w * p.cap;
+      const int np2 = max(64, pow2ceil(c));
+      for (int t = lane; t < np2; t += 32) wsort[t] = t < c ? cq[t] : ~0ull;
+      __syncwarp();
+      warp_bitonic(wsort, np2);
+      if (lane == 0) verify(w, c, wsort[max(c, 1) - 1]);
+      uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + w) * p.k;
+      for (int i = lane; i < p.k; i += 32) out[i] = i < c ? wsort[i] : ~0ull;
+    }
+  } else {
+    for (int q = 0; q < QB; q++) {
+      if (q0 + q >= p.nq) break;
+      if (finq_s[q]) continue;
+      finalize(q);
+      const int c = cnt_s[q];
+      uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
+      for (int i = tid; i < p.k; i += NT) out[i] = i < c ? sortbuf[i] : ~0ull;
+      __syncthreads();
+    }
   }
   if (SPEC) {
     __syncthreads();
