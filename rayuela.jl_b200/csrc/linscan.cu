@@ -83,6 +83,12 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
   }
 }
 
+// Block-wide barrier as a NAMED barrier with an explicit thread count.  scanx_kernel's warps reach service() from two
+// textual call sites (working warps inside the period loop, finished warps in their wait loop); every warp of the
+// block does arrive, but the arrivals come from different instructions, which is what named barriers are for
+// (bar.sync identifies a barrier by id, not by program counter) and what tools expect them to be used for.
+__device__ __forceinline__ void block_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------------
 // Block-wide bitonic sort of np2 (power of two) 64-bit keys in shared memory, ascending.
 // ------------------------------------------------------------------------------------------------------
@@ -99,7 +105,7 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t* s, int np2) {
           s[hi] = a;
         }
       }
-      __syncthreads();
+      block_sync();
     }
   }
 }
@@ -158,12 +164,12 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
     sel[2] = 0;
     sel[3] = 0;
   }
-  __syncthreads();
+  block_sync();
   if (lane == 0 && diff) {
     atomicOr(&sel[2], (int)(uint32_t)diff);
     atomicOr(&sel[3], (int)(uint32_t)(diff >> 32));
   }
-  __syncthreads();
+  block_sync();
   diff = ((uint64_t)(uint32_t)sel[3] << 32) | (uint32_t)sel[2];
   const int first = diff ? (__clzll((long long)diff) >> 3) : 8;       // first pass that can discriminate
   uint64_t prefix = first ? (k0 >> (64 - 8 * first)) : 0;
@@ -171,7 +177,7 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
   for (int pass = first; pass < 8; pass++) {
     const int shift = 56 - 8 * pass;
     if (tid < 256) hist[tid] = 0;
-    __syncthreads();
+    block_sync();
     if (pass == first) {
       // the first discriminating byte usually takes few distinct values: aggregate equal digits per warp
       for (int t0 = 0; t0 < c; t0 += nt) {        // uniform trip count: match.any needs converged warps
@@ -187,7 +193,7 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
         if ((key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1);
       }
     }
-    __syncthreads();
+    block_sync();
     if (tid < 32) {
       int loc[8], sum = 0;
 #pragma unroll
@@ -213,7 +219,7 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
         }
       }
     }
-    __syncthreads();
+    block_sync();
     prefix = (prefix << 8) | (uint32_t)sel[0];
     krem = sel[1];
   }
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     seen_s = 0;
     fail_s = 0;
   }
-  __syncthreads();
+  block_sync();
   if (tid == 0) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(kLutTileBytes)
                  : "memory");
@@ -472,12 +478,12 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
         if (lane == 0) sortbuf[w] = mx;
-        __syncthreads();
+        block_sync();
         if (tid == 0) {
           for (int i = 1; i < kScan8Warps; i++) mx = max(mx, sortbuf[i]);
           tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(mx >> 32)));
         }
-        __syncthreads();
+        block_sync();
       }
       return;
     }
@@ -485,7 +491,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     if (c <= 512) {
       const int np2 = pow2ceil(c);
       for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
-      __syncthreads();
+      block_sync();
       block_bitonic_sort(sortbuf, np2);
       for (int t = tid; t < p.k; t += NT) cq[t] = sortbuf[t];
       if (tid == 0) {
@@ -493,20 +499,20 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
         tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(sortbuf[r - 1] >> 32)));
         if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
       }
-      __syncthreads();
+      block_sync();
       return;
     }
     for (int t = tid; t < c; t += NT) sortbuf[t] = cq[t];
-    __syncthreads();
+    block_sync();
     const uint64_t pivot = block_radix_select(sortbuf, c, p.k, hist_s, sel_s);
     uint64_t pivot_r = pivot;
     if (SPEC && r < p.k) {
-      __syncthreads();
+      block_sync();
       pivot_r = block_radix_select(sortbuf, c, r, hist_s, sel_s);
     }
-    __syncthreads();
+    block_sync();
     if (tid == 0) sel_s[2] = 0;
-    __syncthreads();
+    block_sync();
     for (int t = tid; t < c; t += NT) {
       const uint64_t key = sortbuf[t];
       if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly k keys (keys are distinct)
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
       tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(pivot_r >> 32)));
       if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
     }
-    __syncthreads();
+    block_sync();
   };
   auto finalize = [&](int q) {
     compact(q);
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     const int np2 = pow2ceil(c);
     uint64_t* cq = cand + (size_t)q * p.cap;
     for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
-    __syncthreads();
+    block_sync();
     block_bitonic_sort(sortbuf, np2);
     if (tid == 0) verify(q, c, sortbuf[min(c, p.k) - (c > 0)]);
   };
@@ -536,16 +542,16 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   // which the capacity soft + 3*ADDS covers.  Finished warps wait in service() until all warps are done, so the
   // block-wide barriers inside always see all 16 warps.
   auto service = [&](int progress) -> bool {            // progress: codes this warp has completed so far
-    __syncthreads();                                   // nobody is appending past this point
+    block_sync();                                   // nobody is appending past this point
     const int nf = nfin_s;
     const int fl = *(volatile int*)&flag_s;
     if (SPEC && fl && spec) {                          // block-wide progress for spec_rank()
       if (lane == 0) atomicAdd(&seen_s, progress);
-      __syncthreads();
+      block_sync();
     }
     if (fl) {
       if (w < QB && cnt_s[w] <= kWarpKeys && needs_compaction(w)) warp_sort_keep(w);   // warp w <-> query w
-      __syncthreads();
+      block_sync();
       for (int q = 0; q < QB; q++)
         if (needs_compaction(q)) compact(q);                                           // the large ones, block-wide
       if (tid == 0) {
@@ -556,7 +562,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
         warm_s = warm;
       }
     }
-    __syncthreads();
+    block_sync();
     if (fl) {
       warm = warm_s;
 #pragma unroll
@@ -631,8 +637,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
               if (!p.lb || key > lb_s[q]) {
                 const int pos = atomicAdd(&cnt_s[q], 1);
                 cand[(size_t)q * p.cap + pos] = key;
-                if (pos >= (SPEC ? softq_s[q] : p.soft) || (tau[i] == inf && pos + 1 >= p.k))
-                  *(volatile int*)&flag_s = 1;
+                if (pos >= (SPEC ? softq_s[q] : p.soft) || (tau[i] == inf && pos + 1 >= p.k)) atomicExch(&flag_s, 1);
               }
             }
           }
@@ -669,13 +674,13 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
     }
     if (lane == 0) finq_s[w] = mine;
   }
-  __syncthreads();
+  block_sync();
   if (p.k <= 1024) {
     // large buffers, k <= 1024: block-wide selection of the k smallest of each (one query after the other), then
     // ALL queries are sorted at once, one warp each, in the (now dead) LUT tile: 16 x 8 KB
     for (int q = 0; q < QB; q++)
       if (q0 + q < p.nq && !finq_s[q]) compact(q);
-    __syncthreads();
+    block_sync();
     uint64_t* wsort = reinterpret_cast<uint64_t*>(smem_raw + (lut_addr - smem_u32(smem_raw))) + w * 1024;
     if (w < QB && q0 + w < p.nq && !finq_s[w]) {
       const int c = cnt_s[w];                                  // <= k
@@ -696,11 +701,11 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
       const int c = cnt_s[q];
       uint64_t* out = p.part + ((size_t)slice * p.nq + q0 + q) * p.k;
       for (int i = tid; i < p.k; i += NT) out[i] = i < c ? sortbuf[i] : ~0ull;
-      __syncthreads();
+      block_sync();
     }
   }
   if (SPEC) {
-    __syncthreads();
+    block_sync();
     if (tid == 0) p.redo[blockIdx.y * gridDim.x + blockIdx.x] = (spec && fail_s) ? 1 : 0;
   }
 }
