@@ -117,8 +117,8 @@ __device__ __forceinline__ int pow2ceil(int x) {
 }
 
 static constexpr int kChunkCodes = 1024;              // codes per warp chunk
-static constexpr int kScan8Warps = 16;
-static constexpr int kScan8SortKeys = 8192;           // shared-memory selection buffer (64 KB)
+static constexpr int kScanWarps = 16;
+static constexpr int kScanSortKeys = 8192;           // shared-memory selection buffer (64 KB)
 static constexpr int kLutTileBytes = 131072;          // 16 (m <= 8) or 8 (m <= 16) queries' tables
 
 __device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
@@ -257,7 +257,7 @@ struct ScanX {
   static constexpr int PERIODS = L + 1;            // + one period for the skew tail
   static constexpr int HALVES = P / 8;             // uint4 words per lane per period
   static constexpr int QB = 8 * G;                 // queries per block (16 or 8)
-  static constexpr int ADDS = kScan8Warps * NS;    // most keys one query can gain per block-period
+  static constexpr int ADDS = kScanWarps * NS;    // most keys one query can gain per block-period
 };
 
 // F[chunk][t][half][p] (uint4 = 8 fields): stream p = codes chunk*1024 + NS*u + p (u = 0..L-1), delayed by (p mod P)+1
@@ -305,9 +305,9 @@ struct ScanXParams {
 };
 
 template <int P, bool NORMS, bool SPEC>
-__global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams p) {
+__global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p) {
   using X = ScanX<P>;
-  constexpr int NT = kScan8Warps * 32;
+  constexpr int NT = kScanWarps * 32;
   constexpr int QB = X::QB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int cnt_s[16];
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
   // ((w & 0xFFFF) | base, or (w >> 16) + base)
   uint64_t* sortbuf = reinterpret_cast<uint64_t*>(smem_raw);
-  const uint32_t lut_addr = (smem_u32(smem_raw) + kScan8SortKeys * 8 + 32767u) & ~32767u;
+  const uint32_t lut_addr = (smem_u32(smem_raw) + kScanSortKeys * 8 + 32767u) & ~32767u;
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int j = lane & (P - 1);
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   // Small buffers (<= kWarpKeys keys) are handled by ONE warp each, all queries of the block at once: the warp
   // sorts its query's keys in its own 4 KB slice of the sort area (warp-level bitonic network, no block barriers)
   // and leaves them there sorted; returns the number of keys kept (min(c, k)).
-  constexpr int kWarpKeys = kScan8SortKeys / kScan8Warps;   // 512
+  constexpr int kWarpKeys = kScanSortKeys / kScanWarps;   // 512
   uint64_t* wslice = sortbuf + w * kWarpKeys;
   auto warp_bitonic = [&](uint64_t* buf, int np2) {            // np2 >= 64, a power of two; one warp
     for (int size = 2; size <= np2; size <<= 1) {
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
         if (lane == 0) sortbuf[w] = mx;
         block_sync();
         if (tid == 0) {
-          for (int i = 1; i < kScan8Warps; i++) mx = max(mx, sortbuf[i]);
+          for (int i = 1; i < kScanWarps; i++) mx = max(mx, sortbuf[i]);
           tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(mx >> 32)));
         }
         block_sync();
@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
         tau[2 * tt + 1] = tau_s[tt * 2 * X::G + g * 2 + 1];
       }
     }
-    return nf == kScan8Warps;
+    return nf == kScanWarps;
   };
 
   const uint32_t n32 = (uint32_t)p.n;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(kScan8Warps * 32, 1) scanx_kernel(ScanXParams 
   const uint32_t flag_addr = smem_u32(&flag_s);
 
   int wdone = 0;                                         // codes of finished chunks of this warp
-  for (int64_t chunk = c0 + w; chunk < c1; chunk += kScan8Warps, wdone += kChunkCodes) {
+  for (int64_t chunk = c0 + w; chunk < c1; chunk += kScanWarps, wdone += kChunkCodes) {
     const uint4* fp = p.F + chunk * (X::PERIODS * X::HALVES * X::NS) + pidx;
     const float* np = p.norms + chunk * kChunkCodes + pidx;            // norm of the code completed in period t+1
     uint32_t id = (uint32_t)(chunk * kChunkCodes) + pidx - X::NS;      // code completed in period t (t >= 1)
@@ -900,17 +900,17 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
       // `soft` keys -- up to 4k: fewer, relatively cheaper selections; measured optimum, gpurun r2_soft.log -- and
       // the capacity leaves room for the periods of appends that can land before every warp has reacted to the flag.
       // (small k: 384, so that a buffer past the limit still fits the 512-key slice one warp can compact alone)
-      int soft = std::max(384, std::min(4 * kp, kScan8SortKeys - 3 * adds));
+      int soft = std::max(384, std::min(4 * kp, kScanSortKeys - 3 * adds));
       if (const char* e = getenv("RAYUELA_B200_SCAN_SOFT"))   // tuning knob
-        soft = std::max(kp, std::min(atoi(e), kScan8SortKeys - 3 * adds));
+        soft = std::max(kp, std::min(atoi(e), kScanSortKeys - 3 * adds));
       const int cap = soft + 3 * adds;
       // sort buffer + up to 32 KB of padding so the LUT tile starts on a 32 KB boundary + the tile
-      const size_t smem = (size_t)kScan8SortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
+      const size_t smem = (size_t)kScanSortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
       // DB slices.  A launch of qtiles x S blocks takes ceil(qtiles*S / SMs) waves of (1/S + c) base passes each,
       // c = per-block fixed cost (LUT staging, threshold warm-up, final selection) ~ 0.065 + 0.0005 k of a pass
       // (fit to scratch/slices_probe.py): whole waves of tiles stay unsliced, a partial wave is cut so that it fills
       // the machine once (33 tiles -> 4 slices, 100 tiles -> 4 slices = 2.7 waves of quarter passes, 1 tile -> 61)
-      const int64_t unit = (int64_t)kChunkCodes * kScan8Warps;   // codes per block round
+      const int64_t unit = (int64_t)kChunkCodes * kScanWarps;   // codes per block round
       const int smax = (int)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(1, ix->n / unit), 4 * sms),
                                               std::max(1, 16384 / kp));
       int S = 1;
@@ -962,10 +962,10 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
 #define RYL_SCANX(PP, NN, SS)                                                                                        \
   {                                                                                                                  \
     RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScan8Warps * 32, smem, s, p);                           \
+    RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScanWarps * 32, smem, s, p);                           \
     if (SS) { /* redo launch: blocks whose speculation failed rerun exactly, all others exit at once */             \
       p.pass = 1;                                                                                                    \
-      RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScan8Warps * 32, smem, s, p);                         \
+      RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScanWarps * 32, smem, s, p);                         \
     }                                                                                                                \
   }
       if (period == 16) {
