@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   // is exact iff the k-th smallest key of the final buffer is <= the final threshold; otherwise the block raises
   // its redo flag and is rerun without speculation by the second launch.
   bool final_phase = false;                                    // no tightening once the scan is over
-  auto spec_rank = [&]() -> int {
+  auto spec_rank = [=, &final_phase]() -> int {
     if (!SPEC || !spec || final_phase) return p.k;
     const float x = (float)p.k * fminf(1.0f, (float)seen_s / nslice);
     const int r = (int)(x + 5.5f * sqrtf(x) + 15.125f) + 1;
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   // and leaves them there sorted; returns the number of keys kept (min(c, k)).
   constexpr int kWarpKeys = kScanSortKeys / kScanWarps;   // 512
   uint64_t* wslice = sortbuf + w * kWarpKeys;
-  auto warp_bitonic = [&](uint64_t* buf, int np2) {            // np2 >= 64, a power of two; one warp
+  auto warp_bitonic = [=](uint64_t* buf, int np2) {            // np2 >= 64, a power of two; one warp
     for (int size = 2; size <= np2; size <<= 1) {
       for (int stride = size >> 1; stride > 0; stride >>= 1) {
         for (int t = lane; t < (np2 >> 1); t += 32) {
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       }
     }
   };
-  auto warp_sort_keep = [&](int q) -> int {
+  auto warp_sort_keep = [=](int q) -> int {
     const int c = cnt_s[q];
     uint64_t* cq = cand + (size_t)q * p.cap;
     const int np2 = max(64, pow2ceil(c));
@@ -457,18 +457,18 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     }
     return keep;
   };
-  auto needs_compaction = [&](int q) -> bool {
+  auto needs_compaction = [=](int q) -> bool {
     const int c = cnt_s[q];
     return c > (SPEC ? min(p.piggy, softq_s[q]) : p.piggy) || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000));
   };
   // exactness check of a finished query (see spec_rank): kth = k-th smallest key of the final buffer, c its size
-  auto verify = [&](int q, int c, uint64_t kth) {
+  auto verify = [=](int q, int c, uint64_t kth) {
     if (!SPEC) return;
     const float t = tau_s[q];
     if (c >= p.k ? ordered_to_f32((uint32_t)(kth >> 32)) > t : t < __int_as_float(0x7f800000)) fail_s = 1;
   };
 
-  auto compact = [&](int q) {
+  auto compact = [=](int q) {
     const int c = cnt_s[q];
     uint64_t* cq = cand + (size_t)q * p.cap;
     if (c <= p.k) {
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     }
     block_sync();
   };
-  auto finalize = [&](int q) {
+  auto finalize = [=](int q) {
     compact(q);
     const int c = cnt_s[q];
     const int np2 = pow2ceil(c);
@@ -541,7 +541,14 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   // Between the raise and the last warp's reaction a query gains at most 2*ADDS keys (two periods of every warp),
   // which the capacity soft + 3*ADDS covers.  Finished warps wait in service() until all warps are done, so the
   // block-wide barriers inside always see all 16 warps.
-  auto service = [&](int progress) -> bool {            // progress: codes this warp has completed so far
+  // service() is deliberately NOT inlined: it has two call sites (working warps inside the period loop, finished
+  // warps in their wait loop) and must exist once, so that all 16 warps of the block execute the very same barrier
+  // instructions; it hands the refreshed thresholds back through tau_x / warm_x (address-taken locals) so that the
+  // hot loop's own copies stay in registers; everything else is captured BY VALUE (also by the helpers it calls) so
+  // that taking the closure's address does not push the kernel's locals into local memory.
+  float tau_x[8];
+  int warm_x = 1;
+  auto service = [=, &tau_x, &warm_x](int progress) __attribute__((noinline)) -> bool {   // progress: codes this warp has completed
     block_sync();                                   // nobody is appending past this point
     const int nf = nfin_s;
     const int fl = *(volatile int*)&flag_s;
@@ -563,13 +570,11 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       }
     }
     block_sync();
-    if (fl) {
-      warm = warm_s;
+    warm_x = warm_s;
 #pragma unroll
-      for (int tt = 0; tt < 4; tt++) {
-        tau[2 * tt] = tau_s[tt * 2 * X::G + g * 2];
-        tau[2 * tt + 1] = tau_s[tt * 2 * X::G + g * 2 + 1];
-      }
+    for (int tt = 0; tt < 4; tt++) {
+      tau_x[2 * tt] = tau_s[tt * 2 * X::G + g * 2];
+      tau_x[2 * tt + 1] = tau_s[tt * 2 * X::G + g * 2 + 1];
     }
     return nf == kScanWarps;
   };
@@ -652,11 +657,17 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       np += X::NS;
       id += X::NS;
       // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
-      if (raised || (warm && lds_volatile(flag_addr))) service(wdone + t * X::NS);
+      if (raised || (warm && lds_volatile(flag_addr))) {
+        service(wdone + t * X::NS);
+#pragma unroll
+        for (int i = 0; i < 8; i++) tau[i] = tau_x[i];
+        warm = warm_x;
+      }
     }
   }
   __syncwarp();
   if (lane == 0) atomicAdd(&nfin_s, 1);
+  __syncwarp();
   while (!service(wdone)) {
   }
 
