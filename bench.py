@@ -36,7 +36,7 @@ H = 256
 # (profiles/r1_v3_icm_warp_kernel_full_workload.txt, profiles/r1_v3_scanx8_kernel.txt); bench.py cannot run ncu.
 NCU_TRAFFIC = {
     ("icm", 1_000_000, 128, 8, 32): 10.561672e9 + 25.427456e6,
-    ("scan", 1_000_000, 10_000, 8, 1): 98.904064e6 + 14.063104e6,
+    ("scan", 1_000_000, 10_000, 8, 1): 148.094976e6 + 155.424512e6,
 }
 
 
