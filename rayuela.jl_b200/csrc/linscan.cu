@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
     int q = q0 + qg + 8 * i;
     if (q < nq) {
       if (tiled == 1) {
-        // layout of scan8_kernel's shared-memory tile (see there): [q/16][(q%16)/4][c][((q%4)/2)*8 + k][q%2]
+        // layout of scanx_kernel<8>'s shared-memory tile (see there): [q/16][(q%16)/4][c][((q%4)/2)*8 + k][q%2]
         const int ent = e0 + e, k = ent >> 8, c = ent & 255;
         lut[(size_t)(q >> 4) * 32768 + ((q & 15) >> 2) * 8192 + c * 32 + ((((q & 3) >> 1) * 8 + k) << 1) + (q & 1)] =
             acc[i];
@@ -83,10 +83,10 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
   }
 }
 
-// Block-wide barrier as a NAMED barrier with an explicit thread count.  scanx_kernel's warps reach service() from two
-// textual call sites (working warps inside the period loop, finished warps in their wait loop); every warp of the
-// block does arrive, but the arrivals come from different instructions, which is what named barriers are for
-// (bar.sync identifies a barrier by id, not by program counter) and what tools expect them to be used for.
+// Block-wide barrier (named barrier 1 with an explicit thread count; same semantics as __syncthreads()).  In
+// scanx_kernel every block barrier between the prologue and the final phase lives inside service(), which is ONE
+// non-inlined function, so the warps that call it from the period loop and the finished warps that call it from
+// their wait loop execute the very same barrier instructions.
 __device__ __forceinline__ void block_sync() { asm volatile("bar.sync 1, %0;" ::"r"(blockDim.x) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------------
@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
 
 // ------------------------------------------------------------------------------------------------------
 // K6: merge of S sorted lists per query into the global top-k, by the (dist, id) total order.
-//   keys != null : lists are 64-bit keys [S][nq][k] from scan_kernel (ids local; id_add makes them final)
+//   keys != null : lists are 64-bit keys [S][nq][k] from scanx_kernel (ids local; id_add makes them final)
 //   else         : lists are (dists, idx) [S][nq][k] (already-final ids; the multi-GPU exchange format)
 // One block per query; S*k keys sorted in shared memory.
 // ------------------------------------------------------------------------------------------------------
