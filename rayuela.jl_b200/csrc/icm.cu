@@ -276,8 +276,14 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
     sq[t] = __fmul_rn(df, df);
   }
   __syncwarp();
+  // sequential sum over t (every lane computes the same chain; 16-byte broadcast loads, same order of additions)
   float acc = 0.f;
-  for (int t = 0; t < d; t++) acc = __fadd_rn(acc, sq[t]);
+  const int d4 = d & ~3;
+  for (int t = 0; t < d4; t += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(sq + t);
+    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
+  }
+  for (int t = d4; t < d; t++) acc = __fadd_rn(acc, sq[t]);
   __syncwarp();
   return acc;
 }
@@ -341,8 +347,9 @@ template <int M, bool PF>
 __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * p.d;
-  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * p.d);
+  const int dpad = (p.d + 3) & ~3;                         // per-warp slot, 16-byte aligned (warp_cost loads float4)
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * dpad;
+  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * dpad);
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
   __syncthreads();
 
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(256) veccost_kernel(const float* __restrict__ 
                                                       float* __restrict__ cost) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * d;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((d + 3) & ~3);
   for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < n; l += (int64_t)gridDim.x * nwarps) {
     Code c = load_code<M>(B + (size_t)l * M);
     float v = warp_cost<M>(X + (size_t)l * d, C, c, d, sq, lane);
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(256) norms_kernel(const uint8_t* __restrict__ 
                                                     uint8_t* __restrict__ codes, float* __restrict__ norms) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * d;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((d + 3) & ~3);
   for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < n; l += (int64_t)gridDim.x * nwarps) {
     Code code = load_code<M>(B + (size_t)l * M);
     for (int t = lane; t < d; t += 32) {
@@ -752,7 +759,7 @@ static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
 template <int M>
 static int launch_icm(const IcmParams& p, cudaStream_t s) {
   const int warps = 8;
-  const size_t smem = (size_t)warps * p.d * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
+  const size_t smem = (size_t)warps * ((p.d + 3) & ~3) * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
   return p.Tq ? launch_icm_v<M, true>(p, smem, s) : launch_icm_v<M, false>(p, smem, s);
 }
@@ -761,7 +768,7 @@ template <int M>
 static int launch_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, float* cost,
                           cudaStream_t s) {
   const int warps = 8;
-  size_t smem = (size_t)warps * d * sizeof(float);
+  size_t smem = (size_t)warps * ((d + 3) & ~3) * sizeof(float);
   RYL_ARG(smem <= 200 * 1024, "veccost: d too large for shared memory");
   RYL_CUDA(cudaFuncSetAttribute(veccost_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)std::min<int64_t>((n + warps - 1) / warps, (int64_t)sm_count() * 8);
@@ -983,7 +990,7 @@ template <int M>
 static int launch_norms(const uint8_t* B, const float* C, const float* cbnorms, int64_t n, int d, uint8_t* codes,
                         float* norms, cudaStream_t s) {
   const int warps = 8;
-  size_t smem = (size_t)warps * d * sizeof(float);
+  size_t smem = (size_t)warps * ((d + 3) & ~3) * sizeof(float);
   RYL_ARG(smem <= 200 * 1024, "quantize_norms: d too large for shared memory");
   RYL_CUDA(cudaFuncSetAttribute(norms_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = (int)std::min<int64_t>((n + warps - 1) / warps, (int64_t)sm_count() * 8);
