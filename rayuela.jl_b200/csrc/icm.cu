@@ -335,6 +335,22 @@ struct IcmParams {
 // Lane owns candidates c = r*128 + lane*4 + e (r<2, e<4): every 1 KB row (unary or pairwise) is two
 // coalesced 512 B float4 loads per warp.  Unaries are re-read per step but a vector's 8 KB stay L2-resident
 // for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
+// The (M-1) quantised rows of one step with the conditioned codebook J as a LITERAL: no per-row predicate, no
+// predicated-off row.  sl = sum lo + (sum hi << 16) (mod 2^32), sh = sum hi.
+template <int M, int J>
+__device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_t (&sl)[4], uint32_t (&sh)[4]) {
+#pragma unroll
+  for (int k = 0; k < M; k++) {
+    if (k != J) {
+      const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
+      const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+      sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
+      sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
+    }
+  }
+}
+
 // PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the 16-bit
 // tables (half the bytes of the fp32 rows): S(c) = rint(U_j[c]/scale_j) + sum_k q_jk[b_k][c], with
 //   |scale_j*S(c) - exact(c)| <= scale_j * ((M-1)*0.51 + 0.75)      quantisation of the rows (K2q) and of the unary
@@ -343,7 +359,7 @@ struct IcmParams {
 // candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~1-3 % of
 // the steps, scratch/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
 // construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
-template <int M, bool PF>
+template <int M, bool PF, bool JSPEC = false>
 __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -395,14 +411,27 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
               uint32_t sl[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};   // sl = sum lo + (sum hi << 16) (mod 2^32)
               const char* tqj = reinterpret_cast<const char*>(p.Tq) + (size_t)j * (M * kH * 512) + lane * 16;
               asm volatile("" : "+l"(tqj));   // keep the base in a register pair: row address = one IMAD.WIDE
+              if constexpr (M <= 8 && JSPEC) {                     // one copy of the row loop per j (jump table)
+                switch (j) {
+                  case 0: pf_rows<M, 0>(tqj, nb, sl, sh); break;
+                  case 1: pf_rows<M, 1>(tqj, nb, sl, sh); break;
+                  case 2: pf_rows<M, 2>(tqj, nb, sl, sh); break;
+                  case 3: pf_rows<M, 3>(tqj, nb, sl, sh); break;
+                  case 4: pf_rows<M, 4>(tqj, nb, sl, sh); break;
+                  case 5: pf_rows<M, 5>(tqj, nb, sl, sh); break;
+                  case 6: pf_rows<M, 6>(tqj, nb, sl, sh); break;
+                  default: pf_rows<M, 7>(tqj, nb, sl, sh); break;
+                }
+              } else {
 #pragma unroll
-              for (int k = 0; k < M; k++) {                        // k is a literal: byte extract + immediate offsets
-                if (k != j) {
-                  const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
-                  const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
-                  const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
-                  sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
-                  sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
+                for (int k = 0; k < M; k++) {                      // k is a literal: byte extract + immediate offsets
+                  if (k != j) {
+                    const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
+                    const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+                    sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
+                    sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
+                  }
                 }
               }
               // S(c) = rint(u(c)/scale_j) + sum_k (q_k(c) - 32768): the unary is rounded by the 1.5*2^23 trick inside
@@ -743,16 +772,17 @@ static bool env_off(const char* name) {
   return e && *e && atoi(e) == 0;
 }
 
-// tuning knob: RAYUELA_B200_ICM_PF=0 disables the quantised pre-filter (every step reads the exact fp32 rows)
-template <int M, bool PF>
+// tuning knobs: RAYUELA_B200_ICM_PF=0 disables the quantised pre-filter (every step reads the exact fp32 rows),
+// RAYUELA_B200_ICM_JSPEC=0 the per-j specialised row loop (m <= 8: -3 % at m = 8, -7 % at m = 7)
+template <int M, bool PF, bool JSPEC>
 static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
   const int warps = 8;
-  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, PF, JSPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t need = (p.nc + warps - 1) / warps;
   int per_sm = 4;                                                           // 4 blocks of 8 warps per SM
   if (const char* e = getenv("RAYUELA_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(4, atoi(e)));   // knob
   const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * per_sm);
-  RYL_LAUNCH((icm_warp_kernel<M, PF>), grid, warps * 32, smem, s, p);
+  RYL_LAUNCH((icm_warp_kernel<M, PF, JSPEC>), grid, warps * 32, smem, s, p);
   return RAYUELA_OK;
 }
 
@@ -761,7 +791,11 @@ static int launch_icm(const IcmParams& p, cudaStream_t s) {
   const int warps = 8;
   const size_t smem = (size_t)warps * ((p.d + 3) & ~3) * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
-  return p.Tq ? launch_icm_v<M, true>(p, smem, s) : launch_icm_v<M, false>(p, smem, s);
+  if (!p.Tq) return launch_icm_v<M, false, false>(p, smem, s);
+  if constexpr (M <= 8) {
+    if (!env_off("RAYUELA_B200_ICM_JSPEC")) return launch_icm_v<M, true, true>(p, smem, s);
+  }
+  return launch_icm_v<M, true, false>(p, smem, s);
 }
 
 template <int M>
