@@ -8,7 +8,8 @@
 module RayuelaB200
 
 export encoding_icm, encode_icm_cuda, veccost, qerror, quantize_pq, quantize_opq,
-       linscan_pq, linscan_opq, linscan_lsq, linscan_cq, seed_b200!
+       linscan_pq, linscan_opq, linscan_lsq, linscan_cq, seed_b200!,
+       quantize_norms, quantize_chainq, fast_bin_matmul, update_codebooks_fast_bin
 
 using Printf, Statistics, LinearAlgebra
 
@@ -132,5 +133,47 @@ function linscan_cq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat
   return dists, res
 end
 linscan_cq(B::Matrix{<:Integer}, X, C, k::Int=10000) = linscan_cq(codes0(B), X, C, k)
+
+# --- "next" rows (SURVEY 8f): norm quantization, ChainQ Viterbi encode, codebook update ------------------------
+"quantize_norms(B, C, cbnorms) -> dbnormsB, dbnormsX   (src/utils.jl:29-59)"
+function quantize_norms(B::Matrix{T1}, C::Vector{Matrix{Float32}}, cbnorms::Vector{Float32}) where T1<:Integer
+  m, n = size(B); d, h = size(C[1])
+  codes = zeros(UInt8, n); norms = zeros(Cfloat, n)
+  check(ccall((:rayuela_quantize_norms, librayuela_b200), Cint,
+    (Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Int64, Cint, Cint, Cint, Ptr{Cuchar}, Ptr{Cfloat}, Cuint, Ptr{Cvoid}),
+    codes0(B), hcat(C...), cbnorms, n, d, m, h, codes, norms, 0, C_NULL))
+  return convert(Vector{T1}, codes) .+ one(T1), norms                         # findmin index is 1-based, :55
+end
+
+"quantize_chainq(X, C, use_cuda=false, use_cpp=false) -> B, ellapsed   (src/ChainQ.jl:287-348)"
+function quantize_chainq(X::Matrix{Float32}, C::Vector{Matrix{Float32}}, use_cuda::Bool=false, use_cpp::Bool=false)
+  d, n = size(X); m = length(C); _, h = size(C[1])
+  B = zeros(UInt8, m, n)
+  st = time()
+  check(ccall((:rayuela_quantize_chainq, librayuela_b200), Cint,
+    (Ptr{Cfloat}, Ptr{Cfloat}, Int64, Cint, Cint, Cint, Ptr{Cuchar}, Cuint, Ptr{Cvoid}),
+    X, hcat(C...), n, d, m, h, B, 0, C_NULL))
+  return codes1(B), time() - st
+end
+
+"fast_bin_matmul(X, B, h, V=false, rho=1e-4) -> A, b   (src/codebook_update.jl:96-171)"
+function fast_bin_matmul(X::Matrix{Float32}, B::Matrix{Int16}, h::Integer, V::Bool=false, rho::Float64=1e-4)
+  d, n = size(X); m, _ = size(B)
+  A = zeros(Cdouble, m*h, m*h); b = zeros(Cdouble, m*h, d)
+  check(ccall((:rayuela_fast_bin_matmul, librayuela_b200), Cint,
+    (Ptr{Cfloat}, Ptr{Cuchar}, Int64, Cint, Cint, Cint, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Cuint, Ptr{Cvoid}),
+    X, codes0(B), n, d, m, h, rho, A, b, 0, C_NULL))
+  return A, b
+end
+
+"update_codebooks_fast_bin(X, B, h, V=false, rho=1e-4) -> C   (src/codebook_update.jl:175-204; the solve stays LAPACK)"
+function update_codebooks_fast_bin(X::Matrix{Float32}, B::Matrix{Int16}, h::Integer, V::Bool=false, rho::Float64=1e-4)
+  m, n = size(B)
+  A, b = fast_bin_matmul(X, B, h, V, rho)
+  lpt = LAPACK.getrf!(A)
+  Cm  = convert(Matrix{Float32}, LAPACK.getrs!('N', lpt[1], lpt[2], b))       # (m*h)-by-d
+  Ct  = collect(Cm')                                                          # d-by-(m*h)
+  return [Ct[:, (i-1)*h+1:i*h] for i = 1:m]                                   # K2vec, src/utils.jl
+end
 
 end # module
