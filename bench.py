@@ -10,9 +10,13 @@ src/LSQ_GPU.jl:351-352).  One step = one rayuela_encode_icm call over the whole 
 buffers (H2D of X/C/B and D2H of the codes inside the timed region).  The JSON line also carries a `linscan`
 object: queries/s and Recall@1 of linscan_lsq (10k queries over the just-encoded base) with its own roofline.
 --impl reference times the reference's CPU algorithm (oracle restatement of the Julia host logic driving the
-reference's own compiled `condition` / linscan symbols from oracle/_ref) on a bounded sample per step.
+reference's own compiled `condition` / linscan symbols from oracle/_ref; unaries and pairwise tables by BLAS sgemm
+as src/utils.jl:135-136,164 compute them) on a bounded sample per step, with the OpenMP / BLAS pools forced to
+the host core count (torchrun exports OMP_NUM_THREADS=1) and the effective thread count printed.
 Under torchrun (N > 1) every rank works on its own shard (weak scaling, no data-path collective for the
-encode; one all-gather + merge for the base-sharded scan).
+encode; one all-gather + merge for the base-sharded scan).  The line also carries two STRONG-scaling objects,
+`config4` (BASELINE.json configs[3]: m=16, 1M vectors in total split over the N ranks) and `config5`
+(configs[4]: 100M codes in total, base-sharded, k in {1, 1000}); --no-strong skips them.
 """
 import argparse
 import json
@@ -22,7 +26,22 @@ import sys
 import tempfile
 import time
 
-import numpy as np
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# The CPU arm (--impl reference, and the cpu_baseline leg of a 1-GPU run) must use every host core.  torchrun exports
+# OMP_NUM_THREADS=1 to its workers; libgomp and OpenBLAS read the variable when they are LOADED, so it is corrected
+# here, before numpy / the oracle are imported (force_host_threads() then verifies what the runtimes report).
+if "reference" in sys.argv[1:] or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(host_threads())
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "rayuela.jl_b200")):
@@ -32,12 +51,15 @@ for _p in (ROOT, os.path.join(ROOT, "rayuela.jl_b200")):
 H = 256
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` captures of the SAME workload
-# (profiles/r1_v3_icm_warp_kernel_full_workload.txt, profiles/r1_v3_scanx8_kernel.txt); bench.py cannot run ncu.
-NCU_TRAFFIC = {
-    ("icm", 1_000_000, 128, 8, 32): 10.561672e9 + 25.427456e6,
-    ("scan", 1_000_000, 10_000, 8, 1): 148.094976e6 + 155.424512e6,
-}
+def ncu_traffic(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the `ncu --set full`
+    capture of the SAME workload committed under profiles/ (bench.py cannot run ncu): profiles/ncu_traffic.json
+    maps kind -> {"bytes": ..., "kernel": ..., "capture": file, "commit": ...}; null when there is no capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t.get(kind)
+    except Exception:
+        return None
 
 
 def peaks():
@@ -167,36 +189,44 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU algorithm on a bounded sample
 # ---------------------------------------------------------------------------------------------------------
-def host_threads():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
-
-
 def cpu_sized(fn, first, target_s=12.0, cap=None):
     """Run fn(size) once at `first`; if that took well under the target, run again at a size scaled to
     ~target_s (bounded by cap) and return the larger run."""
-    t, kind = fn(first)
+    t, kind, extra = fn(first)
     size = first
     if t < target_s / 3:
         size = int(min(cap or 10 ** 9, max(first, first * target_s / max(t, 1e-3))))
         if size > first:
-            t, kind = fn(size)
-    return size, t, kind
+            t, kind, extra = fn(size)
+    return size, t, kind, extra
+
+
+def force_host_threads():
+    """All host cores for the CPU arm, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1, and an
+    environment variable changed after libgomp / OpenBLAS are loaded is ignored): runtime calls, then read back."""
+    from oracle import oracle as orc
+    orc.build()
+    cores = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    got = orc.set_num_threads(cores)
+    assert got == cores, "OpenMP gives %d threads, wanted %d" % (got, cores)
+    return cores, got
 
 
 def cpu_icm_sample(cfg, n_s, seed=0):
-    """oracle.encode_icm (encode_icm_fully! restated, src/LSQ.jl:152-252) driving the reference's own compiled
-    `condition` when oracle/_ref is present.  Returns seconds for n_s vectors at cfg's ilsiter."""
+    """The reference's CPU encode on n_s vectors: oracle.encode_icm (encode_icm_fully! restated,
+    src/LSQ.jl:152-252) driving the reference's own compiled `condition` when oracle/_ref is present, with
+    unaries / tables from BLAS sgemm like src/utils.jl:135-136,164 (blas=True: the oracle's pinned fixed-order
+    chains are for parity, not for timing).  Returns (seconds, kind, phases)."""
     from oracle import oracle as orc
     r = np.random.default_rng(seed)
     X = r.standard_normal((n_s, cfg["d"])).astype(np.float32)
     C = (r.standard_normal((cfg["m"] * H, cfg["d"])) / np.sqrt(cfg["m"])).astype(np.float32)
     B = r.integers(0, H, (n_s, cfg["m"]), dtype=np.uint8)
     t0 = time.perf_counter()
-    orc.encode_icm(X, C, B, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=1, use_ref_step=orc.have_ref())
-    return time.perf_counter() - t0, ("reference" if orc.have_ref() else "port")
+    o = orc.encode_icm(X, C, B, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=1,
+                       use_ref_step=orc.have_ref(), blas=True, want_phases=True)
+    return time.perf_counter() - t0, ("reference" if orc.have_ref() else "port"), o["phases"]
 
 
 def cpu_scan_sample(cfg, nq_s, n, seed=0):
@@ -210,24 +240,26 @@ def cpu_scan_sample(cfg, nq_s, n, seed=0):
     fn = orc.ref_linscan if orc.have_ref() else orc.linscan
     t0 = time.perf_counter()
     fn(orc.LSQ, B, Xq, cb, cfg["k"], nrm)
-    return time.perf_counter() - t0, ("reference" if orc.have_ref() else "port")
+    return time.perf_counter() - t0, ("reference" if orc.have_ref() else "port"), None
+
+
+CPU_NOTE = ("reference C++ (oracle/_ref: `condition`, linscan_aqd*) + restated Julia host logic (Julia is not "
+            "installed); unaries and pairwise tables by OpenBLAS sgemm as the reference computes them")
 
 
 def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle as orc
-    orc.build()
-    cores = host_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    times = []
+    cores, omp = force_host_threads()
+    times, phases = [], None
     if args.path == "icm":
         n_s = args.ref_sample or 32768
         for i in range(args.warmup + args.steps):
-            t, kind = cpu_icm_sample(cfg, n_s, seed=i)
+            t, kind, ph = cpu_icm_sample(cfg, n_s, seed=i)
             if i >= args.warmup:
                 times.append(t)
+                phases = ph
         per = float(np.mean(times))
         value, unit, metric = n_s / per, "vectors/s", "lsq_icm_encode_vectors_per_sec"
         sample = "%d of %d vectors per step, same m/ilsiter/icmiter/npert; vectors/s is size-independent" % (
@@ -235,7 +267,7 @@ def run_reference(args, cfg):
     else:
         nq_s = args.ref_sample or 256 * cores
         for i in range(args.warmup + args.steps):
-            t, kind = cpu_scan_sample(cfg, nq_s, cfg["n"], seed=i)
+            t, kind, _ = cpu_scan_sample(cfg, nq_s, cfg["n"], seed=i)
             if i >= args.warmup:
                 times.append(t)
         per = float(np.mean(times))
@@ -246,8 +278,8 @@ def run_reference(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(cfg, args),
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample,
-                         "note": "reference C++ (oracle/_ref) + restated Julia host logic; Julia is not installed"},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "omp_max_threads": omp, "kind": kind,
+                         "sample": sample, "phases_s": phases, "note": CPU_NOTE},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -440,6 +472,41 @@ def run_ours(args, cfg):
         index.search(Qh, Ch2, k, out=(dh, ih))     # pinned host queries/codebooks in, pinned host results out
         res["dh"], res["ih"] = dh, ih
     scan_e2e_ms = wall_steps(scan_e2e, e2e_steps, 1, None, device) / e2e_steps
+
+    # the demos' knn = 1000 (demos/demos_train_query_base.jl:16) on the same index, same exchange
+    kk = 1000
+    scan_k1000 = None
+    if not args.no_strong and k != kk:
+        def scan_step_k():
+            dl, il = index.search(Q, C, kk)
+            if dist is not None:
+                gd = torch.empty((world * nq, kk), device=device, dtype=dl.dtype)
+                gi = torch.empty((world * nq, kk), device=device, dtype=il.dtype)
+                dist.all_gather_into_tensor(gd, dl)
+                dist.all_gather_into_tensor(gi, il)
+                dl, il = core.topk_merge(gd.view(world, nq, kk), gi.view(world, nq, kk))
+            res["ik"] = il
+        ks = max(2, args.steps // 2)
+        msk = timed_steps(scan_step_k, ks, 1, dist, device) / ks
+        hit = (res["ik"].long() - 1 == gt_global[:, None])
+        scan_k1000 = {"k": kk, "ms_per_step": msk, "queries_per_sec": nq / (msk * 1e-3),
+                      "recall_at_1000": float((hit.sum(1) == 1).float().mean().item()), "steps": ks}
+
+    # sub-range of the timed workload for the untimed oracle parity check (host copies, taken before X is freed)
+    off = (n // 2) // 8 * 8
+    cnt = min(1536, n - off)
+    parity_in = (X[off:off + cnt].cpu().numpy(), C.cpu().numpy(), B0[off:off + cnt].cpu().numpy(),
+                 Bwork[off:off + cnt].cpu().numpy(), off)
+
+    # ---- strong-scaling objects (every rank takes part; rank 0 keeps the result) ---------------------------------
+    index.free()
+    strong = {}
+    if not args.no_strong:
+        del X, Bwork, B0, Bscratch
+        torch.cuda.empty_cache()
+        strong["config4"] = run_config4(dist, device, world, rank)
+        torch.cuda.empty_cache()
+        strong["config5"] = run_config5(dist, device, world, rank)
     clocks = sampler.stop() if sampler else {}
 
     if rank != 0:
@@ -447,44 +514,54 @@ def run_ours(args, cfg):
             dist.destroy_process_group()
         return
 
+    # ---- untimed parity check of the timed configuration against the oracle (sub-range, full ilsiter) ---------------
+    parity = None
+    if not args.no_cpu_baseline:
+        parity = parity_subrange(cfg, parity_in, g0)
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample ---------------------------------------------------
     cpu = None
     cpu_scan = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.build()
-        cores = host_threads()
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        n_s, t, kind = cpu_sized(lambda s_: cpu_icm_sample(cfg, s_), 16384, cap=n)
-        cpu = {"value": n_s / t, "unit": "vectors/s", "cores": cores, "kind": kind,
+        cores, omp = force_host_threads()
+        n_s, t, kind, ph = cpu_sized(lambda s_: cpu_icm_sample(cfg, s_), 16384, cap=n)
+        cpu = {"value": n_s / t, "unit": "vectors/s", "cores": cores, "omp_max_threads": omp, "kind": kind,
                "sample": "%d of %d vectors, one encode at the same m/ilsiter/icmiter/npert (%.1f s)" % (n_s, n, t),
-               "note": "reference compiled `condition` + restated Julia host logic (Julia not installed)"}
-        nq_s, t2, kind2 = cpu_sized(lambda s_: cpu_scan_sample(cfg, s_, n), max(64, 4 * cores), cap=nq)
-        cpu_scan = {"value": nq_s / t2, "unit": "queries/s", "cores": cores, "kind": kind2,
+               "phases_s": ph, "note": CPU_NOTE}
+        nq_s, t2, kind2, _ = cpu_sized(lambda s_: cpu_scan_sample(cfg, s_, n), max(64, 4 * cores), cap=nq)
+        cpu_scan = {"value": nq_s / t2, "unit": "queries/s", "cores": cores, "omp_max_threads": omp, "kind": kind2,
                     "sample": "%d of %d queries over the full %d-code base (%.1f s)" % (nq_s, nq, n, t2)}
 
     sm_mhz = clocks.get("sm_mhz") or pk.get("sm_max_mhz", 1965.0)
     onchip_peak = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s of L1/shared load bandwidth at the sampled clock
-    icm_roof = {"bound": "hbm", "achieved": gather_bytes_ref / (k3_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "traffic": NCU_TRAFFIC.get(("icm", n, d, m, cfg["ilsiter"])), "peak_source": pk_src,
-                "kernel": "icm_warp_kernel<%d,true>" % m, "kernel_ms": k3_ms,
-                "onchip_peak": onchip_peak,
+    tr = ncu_traffic("icm_m%d_n%d_ils%d" % (m, n, cfg["ilsiter"]))
+    achieved = gather_bytes_ref / (k3_ms * 1e-3) / 1e9
+    icm_roof = {"bound": "issue/L2 (on-chip gather; DRAM < 1 % busy, so neither HBM nor tensor)",
+                "achieved": achieved, "peak": onchip_peak, "unit": "GB/s", "frac": achieved / onchip_peak,
+                "frac_actual": gather_bytes / (k3_ms * 1e-3) / 1e9 / onchip_peak,
+                "traffic": tr["bytes"] if tr else None, "traffic_source": tr,
+                "peak_source": "148 SM x 128 B/clk x sampled SM clock (SURVEY 8d: the path is not HBM-bound)",
+                "hbm_peak": pk["hbm_gbs"], "hbm_peak_source": pk_src, "hbm_frac_of_algorithmic": achieved / pk["hbm_gbs"],
+                "kernel": "icm_warp_kernel<%d,true,%s>" % (m, "true" if m <= 8 else "false"), "kernel_ms": k3_ms,
                 "steps_executed": steps_done, "steps_reference": steps_total, "steps_exact_rows": steps_exact,
                 "gathered_actual": gather_bytes / (k3_ms * 1e-3) / 1e9,
-                "note": "achieved = SURVEY 8d algorithmic bytes (n*ilsiter*icmiter*m*(m-1)*256*4, what the reference's "
-                        "steps gather) / K3 time. The kernel itself gathers less (gathered_actual): steps whose "
-                        "conditioning codes did not change are memoised, and a step reads 512 B 16-bit rows unless "
-                        "the pre-filter leaves a near-tie (steps_exact_rows). Rows are served by L2, not HBM, so "
-                        "`frac` against the HBM copy peak exceeds 1 by construction; onchip_frac is the same figure "
-                        "against 148 SM x 128 B/clk x sampled SM clock; `traffic` is the ncu DRAM figure"}
-    icm_roof["frac"] = icm_roof["achieved"] / icm_roof["peak"]
-    icm_roof["onchip_frac"] = icm_roof["achieved"] / onchip_peak
+                "note": "achieved = SURVEY 8d algorithmic (work-equivalent) bytes n*ilsiter*icmiter*m*(m-1)*256*4 -- what "
+                        "the reference's steps gather -- / K3 time, against the on-chip load ceiling.  frac_actual = "
+                        "the bytes the kernel really gathers (memoised steps skipped, 512 B 16-bit rows, fp32 rows "
+                        "only for near-ties) against the same ceiling; rows are served by L2 and the kernel is "
+                        "instruction-issue bound (profiles/).  `traffic` = ncu dram bytes of one K3 launch at HEAD"}
     scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base
+    tr2 = ncu_traffic("scan_m%d_n%d_nq%d_k%d" % (m, n, nq, k))
+    lookups = float(nq) * n * m / (scan_per * 1e-3)
     scan_roof = {"bound": "hbm", "achieved": scan_bytes / (scan_per * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                 "unit": "GB/s", "traffic": NCU_TRAFFIC.get(("scan", n, nq, m, k)), "peak_source": pk_src,
-                 "kernel": "scanx_kernel<%d,true>" % (8 if m <= 8 else 16),
+                 "unit": "GB/s", "traffic": tr2["bytes"] if tr2 else None, "traffic_source": tr2, "peak_source": pk_src,
+                 "kernel": "scanx_kernel<%d,true,%s>" % (8 if m <= 8 else 16, "true" if k >= 16 else "false"),
+                 "smem_lookups_per_s": lookups, "smem_lookup_peak": 148 * 32 * sm_mhz * 1e6,
+                 "smem_lookup_frac": lookups / (148 * 32 * sm_mhz * 1e6),
                  "note": "algorithmic bytes = nq*n*(m+4): what the reference streams per query "
-                         "(pairwise_byte.cpp:56-83); whole search step (LUT + scan + merge) in the denominator"}
+                         "(pairwise_byte.cpp:56-83); whole search step (LUT + scan + merge) in the denominator; frac "
+                         "can exceed 1 because codes are re-read from L2 across a query tile (see traffic); the "
+                         "ceiling that binds is the shared-memory gather rate (smem_lookup_frac, 32 lookups/clk/SM)"}
     scan_roof["frac"] = scan_roof["achieved"] / scan_roof["peak"]
 
     primary_icm = args.path == "icm"
@@ -507,6 +584,7 @@ def run_ours(args, cfg):
         "gpu_launches": icm_launches if primary_icm else scan_launches,
         "roofline": icm_roof if primary_icm else scan_roof,
         "cpu_baseline": cpu if primary_icm else cpu_scan,
+        "parity_checked": parity,
         "icm": {"vectors_per_sec": icm_value, "vector_ils_iters_per_sec": icm_value * cfg["ilsiter"],
                 "ms_per_step": icm_per, "setup_ms(K0+K1+K2+cost)": setup_ms, "qerror_before": qerr0,
                 "qerror_after": qerr, "e2e_vectors_per_sec": world * n / (icm_e2e_ms * 1e-3), "roofline": icm_roof,
@@ -515,11 +593,179 @@ def run_ours(args, cfg):
                     "k": k, "nq": nq, "n_base_total": world * n, "ms_per_step": scan_per,
                     "e2e_queries_per_sec": nq / (scan_e2e_ms * 1e-3), "roofline": scan_roof,
                     "cpu_baseline": cpu_scan, "gpu_launches": scan_launches,
-                    "sharding": "base-sharded, one all-gather of per-shard top-k + merge" if world > 1 else "none"},
+                    "sharding": "base-sharded, one all-gather of per-shard top-k + merge" if world > 1 else "none",
+                    "k1000": scan_k1000},
     }
+    line.update(strong)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def parity_subrange(cfg, parity_in, g0, count=1536):
+    """Untimed: the oracle (fixed-order restatement + the reference's compiled `condition`) encodes `count` vectors
+    of the TIMED workload at the timed ilsiter, and the GPU's codes for the same global indices must be identical."""
+    from oracle import oracle as orc
+    orc.build()
+    Xs, Cs, B0s, got, off = parity_in
+    want = orc.encode_icm(Xs, Cs, B0s, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0 + off,
+                          use_ref_step=orc.have_ref())
+    eq = bool(np.array_equal(want["B"], got))
+    return {"vectors": int(Xs.shape[0]), "first_global_index": int(g0 + off), "ilsiter": cfg["ilsiter"],
+            "codes_bit_identical_to_oracle": eq,
+            "mismatching_vectors": int((want["B"] != got).any(1).sum()),
+            "oracle": "oracle.encode_icm(use_ref_step=%s)" % orc.have_ref()}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# strong scaling: BASELINE.json configs[3] and configs[4]
+# ---------------------------------------------------------------------------------------------------------
+def _blocks_of(rank, world, nblocks=8):
+    per = nblocks // world
+    return list(range(rank * per, (rank + 1) * per))
+
+
+def _allsum_i64(v, dist, device):
+    import torch
+    t = torch.tensor([v], device=device, dtype=torch.int64)
+    if dist is not None:
+        dist.all_reduce(t)
+    return int(t.item())
+
+
+def run_config4(dist, device, world, rank, n_total=1_000_000, m=16, d=128, ilsiter=32, steps=2):
+    """configs[3]: LSQ++ m=16 h=256, 1M x 128 in total, encoding sharded over the N ranks (n/N vectors each, contiguous
+    splitarray slices, RNG keyed on the global index -> codes independent of N: `codes_checksum` must agree for
+    every N).  The base is generated in 8 fixed blocks of 125k vectors so every N sees the same data."""
+    import torch
+    from rayuela_b200 import core
+    assert 8 % world == 0 and n_total % 8 == 0
+    nb = n_total // 8
+    blocks = _blocks_of(rank, world)
+    Xt, _ = make_data(50000, 1, d, seed=4000, device=device, rank=0)
+    C = train_codebooks(Xt, m, device)                              # identical on every rank
+    X = torch.cat([make_data(nb, 1, d, seed=5000 + b, device=device, rank=0)[0] for b in blocks])
+    B0 = torch.cat([torch.randint(0, H, (nb, m), device=device, dtype=torch.uint8,
+                                  generator=torch.Generator(device=device).manual_seed(6000 + b)) for b in blocks])
+    g0 = blocks[0] * nb
+    Bw = B0.clone()
+
+    def step():
+        Bw.copy_(B0)
+        core.encode_icm(X, C, Bw, ilsiter, 4, 4, True, seed=2024, g0=g0, inplace=True)
+    ms = timed_steps(step, steps, 1, dist, device) / steps
+    idx = torch.arange(g0, g0 + Bw.shape[0], device=device, dtype=torch.int64)
+    local = int((Bw.long().sum(1) * (idx % 1000003 + 1)).sum().item())     # order-independent, position-sensitive
+    checksum = _allsum_i64(local, dist, device) % (1 << 61)
+    q0 = core.qerror(X, B0, C)
+    q1 = core.qerror(X, Bw, C)
+    qsum = torch.tensor([q0 * Bw.shape[0], q1 * Bw.shape[0]], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(qsum)
+    return {"workload": "BASELINE.json configs[3]: LSQ++ m=16 h=256 icmiter=4 npert=4 randord ilsiter=%d, %dx%d in "
+                        "total, %d vectors per GPU" % (ilsiter, n_total, d, n_total // world),
+            "scaling": "strong", "n_total": n_total, "n_per_gpu": n_total // world, "ms_per_step": ms,
+            "vectors_per_sec": n_total / (ms * 1e-3), "steps": steps, "warmup": 1,
+            "qerror_before": float(qsum[0].item() / n_total), "qerror_after": float(qsum[1].item() / n_total),
+            "codes_checksum": checksum, "collective": "none (disjoint code slices)"}
+
+
+def _exact_scan_topk(codes, norms, Q, C, m, k, id0):
+    """Independent restatement of linscan_aqd_query_extra_byte (deps/src/linscan_aqd_pairwise_byte.cpp:42-83) in
+    torch element-wise fp32 ops in the reference's operation order (LUT: t -= (2*q[s])*c[s] for ascending s;
+    distance ((t_0 + t_1) + ...) + norm), so it is bit-identical; returns the k smallest signed 64-bit keys
+    (ordered(dist) << 32 | 1-based global id) per query."""
+    import torch
+    nqv, d = Q.shape
+    lut = torch.zeros(nqv, m * H, device=Q.device)
+    for s in range(d):
+        lut = lut - (2.0 * Q[:, s:s + 1]) * C[None, :, s]
+    lut = lut.view(nqv, m, H)
+    best = None
+    step = 1 << 20
+    for a in range(0, codes.shape[0], step):
+        cb = codes[a:a + step].long()
+        acc = lut[:, 0, :][:, cb[:, 0]]
+        for j in range(1, m):
+            acc = acc + lut[:, j, :][:, cb[:, j]]
+        acc = acc + norms[None, a:a + step] + 0.0
+        bits = acc.view(torch.int32).long()
+        ordered = torch.where(bits < 0, bits ^ 0x7FFFFFFF, bits)                    # signed order == float order
+        ids = torch.arange(a, a + cb.shape[0], device=Q.device, dtype=torch.int64) + (id0 + 1)
+        keys = (ordered << 32) | ids[None, :]
+        cat = keys if best is None else torch.cat([best, keys], 1)
+        best = torch.topk(cat, min(k, cat.shape[1]), dim=1, largest=False, sorted=True).values
+    return best
+
+
+def run_config5(dist, device, world, rank, n_total=100_000_000, m=8, d=128, nq=10_000, steps=2, nverify=64):
+    """configs[4]: linscan_lsq over 100M x 8 B uniform random codes (+ fp32 norms), 10k queries, base sharded over the
+    N ranks (global ids), one all-gather of the per-shard top-k + merge; k = 1 and k = 1000 (the demos' knn).  The ids
+    of a 64-query subset are checked against an independent bit-exact restatement of the reference's scan."""
+    import torch
+    from rayuela_b200 import core
+    assert 8 % world == 0 and n_total % 8 == 0
+    nb = n_total // 8
+    blocks = _blocks_of(rank, world)
+    gq = torch.Generator(device=device).manual_seed(7000)
+    Q = torch.randn(nq, d, generator=gq, device=device)
+    C = (torch.randn(m * H, d, generator=gq, device=device) / m ** 0.5).contiguous()
+    codes = torch.cat([torch.randint(0, H, (nb, m), device=device, dtype=torch.uint8,
+                                     generator=torch.Generator(device=device).manual_seed(8000 + b)) for b in blocks])
+    norms = torch.cat([torch.randn(nb, device=device,
+                                   generator=torch.Generator(device=device).manual_seed(9000 + b)) * 4 + 30
+                       for b in blocks]).contiguous()
+    id0 = blocks[0] * nb
+    index = core.Index(core.SCAN_LSQ, codes, norms, id_offset=id0)
+    out = {"workload": "BASELINE.json configs[4]: linscan_lsq, %d x %d B uniform random codes + fp32 norms in total, "
+                       "%d queries, base sharded over the GPUs (%d codes each), all-gather of per-shard top-k + merge"
+                       % (n_total, m, nq, n_total // world),
+           "scaling": "strong", "n_total": n_total, "n_per_gpu": n_total // world, "nq": nq, "steps": steps,
+           "warmup": 1}
+    res = {}
+    for k in (1, 1000):
+        gd = torch.empty((world * nq, k), device=device, dtype=torch.float32)
+        gi = torch.empty((world * nq, k), device=device, dtype=torch.int32)
+
+        def search():
+            res["l"] = index.search(Q, C, k)
+
+        def gather():
+            if dist is not None:
+                dist.all_gather_into_tensor(gd, res["l"][0])
+                dist.all_gather_into_tensor(gi, res["l"][1])
+
+        def merge():
+            res["g"] = core.topk_merge(gd.view(world, nq, k), gi.view(world, nq, k)) if dist is not None else res["l"]
+
+        def step():
+            search()
+            gather()
+            merge()
+        ms = timed_steps(step, steps, 1, dist, device) / steps
+        # where the step goes (separately timed sections, same inputs)
+        ms_search = timed_steps(search, 1, 0, dist, device)
+        ms_gather = timed_steps(gather, 1, 0, dist, device) if dist is not None else 0.0
+        ms_merge = timed_steps(merge, 1, 0, dist, device) if dist is not None else 0.0
+        dg, ig = res["g"]
+        # verification: 64-query subset against the bit-exact restatement, merged over the ranks
+        qs = torch.arange(0, nq, nq // nverify, device=device)[:nverify]
+        keys = _exact_scan_topk(codes, norms, Q[qs], C, m, k, id0)
+        if dist is not None:
+            allk = torch.empty((world,) + tuple(keys.shape), device=device, dtype=keys.dtype)
+            dist.all_gather_into_tensor(allk.view(-1, keys.shape[1]), keys)
+            keys = torch.topk(allk.permute(1, 0, 2).reshape(keys.shape[0], -1), k, dim=1, largest=False,
+                              sorted=True).values
+        want_ids = (keys & 0xFFFFFFFF).to(torch.int32)
+        ok = bool(torch.equal(want_ids, ig[qs]))
+        out["k%d" % k] = {"ms_per_step": ms, "queries_per_sec": nq / (ms * 1e-3), "ms_search_local": ms_search,
+                          "ms_allgather": ms_gather, "ms_merge": ms_merge,
+                          "allgather_bytes_per_rank": nq * k * 8 if world > 1 else 0,
+                          "ids_checksum": int(ig.long().sum().item()) % (1 << 61),
+                          "ids_verified_queries": int(qs.numel()), "ids_equal_exact_restatement": ok,
+                          "algorithmic_GBps": float(nq) * n_total * (m + 4) / (ms * 1e-3) / 1e9}
+    index.free()
+    return out
 
 
 def main():
@@ -541,6 +787,7 @@ def main():
     ap.add_argument("--ilsiter", type=int, default=32)
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the config4 / config5 / k=1000 objects")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("BENCH_ALLOW_SHORT"), "warmup must be >= 3"
     cfg = dict(n=args.n, nq=args.nq, m=args.m, d=args.d, k=args.k, ilsiter=args.ilsiter, icmiter=4, npert=4)

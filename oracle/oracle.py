@@ -129,9 +129,73 @@ def qerror(X, B, C, h=256):
     return float(np.mean(veccost(X, B, C, h).astype(np.float64)))
 
 
+def set_num_threads(t):
+    """Force the OpenMP team size used by liboracle AND oracle/_ref (one libgomp per process) and the BLAS pool
+    numpy uses; returns what OpenMP reports afterwards.  torchrun exports OMP_NUM_THREADS=1, and an environment
+    variable set after the runtimes are loaded changes nothing, hence the runtime calls."""
+    lib().orc_set_num_threads(ct.c_int(int(t)))
+    try:
+        from threadpoolctl import threadpool_limits
+        global _blas_limit
+        _blas_limit = threadpool_limits(limits=int(t))      # kept alive: the limit lasts as long as the object
+    except Exception:
+        pass
+    # spin the BLAS pool up now, not inside a timed call: the first dozen sgemm calls of a process take ~0.1 s each
+    import time
+    w = np.ones((256, 128), dtype=np.float32)
+    fast = 0
+    for _ in range(64):
+        t0 = time.perf_counter()
+        np.matmul(w, w.T)
+        fast = fast + 1 if time.perf_counter() - t0 < 5e-3 else 0
+        if fast >= 3:
+            break
+    return max_threads()
+
+
+_blas_limit = None
+
+
+def max_threads():
+    return int(lib().orc_get_max_threads())
+
+
+def blas_unaries(X, C, m, h=256):
+    """get_unaries as the reference computes it (src/utils.jl:135-144): one sgemm per codebook,
+    unaries[i] = (-2*C[i]')*X, then + diag(C[i]'C[i]).  TIMING ARM ONLY: the BLAS summation order is not the
+    oracle's pinned order.  Returns U (m, n, h)."""
+    X, C = _f32(X), _f32(C)
+    n = X.shape[0]
+    U = np.empty((m, n, h), dtype=np.float32)
+    for i in range(m):
+        Ci = C[i * h:(i + 1) * h]
+        np.matmul(X, (np.float32(-2) * Ci).T, out=U[i])
+        U[i] += np.einsum("cd,cd->c", Ci, Ci)[None, :]
+    return U
+
+
+def blas_binaries(C, m, h=256):
+    """get_binaries + binaries_t via sgemm (src/utils.jl:164, src/LSQ.jl:180-183).  TIMING ARM ONLY."""
+    C = _f32(C)
+    ncbi = m * (m - 1) // 2
+    b = np.empty((max(ncbi, 1), h, h), dtype=np.float32)
+    bt = np.empty((max(ncbi, 1), h, h), dtype=np.float32)
+    idx = 0
+    for i in range(m):
+        for j in range(i + 1, m):
+            # column-major h-by-h 2*C_i'*C_j -> C-order image [b][a] = 2<C_i[:,a], C_j[:,b]>
+            np.matmul(np.float32(2) * C[j * h:(j + 1) * h], C[i * h:(i + 1) * h].T, out=b[idx])
+            bt[idx] = b[idx].T
+            idx += 1
+    return b, bt
+
+
 def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=None, h=256,
-               snap_iters=None, use_ref_step=False):
-    """encode_icm_fully! restatement.  Returns dict(B, cost, stats, B_snap, objs)."""
+               snap_iters=None, use_ref_step=False, blas=False, want_phases=False):
+    """encode_icm_fully! restatement.  Returns dict(B, cost, stats, B_snap, objs[, phases]).
+    blas=True (bench.py's CPU arm only): unaries and tables come from sgemm like the reference's, instead of the
+    pinned fixed-order chains; phases = seconds in {tables, unaries, icm_steps, veccost, other}."""
+    import time
     X, C = _f32(X), _f32(C)
     B = np.ascontiguousarray(B, dtype=np.uint8).copy()
     n, d = X.shape
@@ -148,16 +212,34 @@ def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=N
     step = None
     if use_ref_step:
         step = ct.cast(ref("encode_icm").condition, CONDITION_FN)
-    fn = lib().orc_encode_icm_fully
+    U = bn = bt = None
+    t_tab = t_un = 0.0
+    if blas:
+        t0 = time.perf_counter()
+        bn, bt = blas_binaries(C, m, h)
+        t_tab = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        U = blas_unaries(X, C, m, h)
+        t_un = time.perf_counter() - t0
+    ph = np.zeros(5, dtype=np.float64)
+    f64p = ct.POINTER(ct.c_double)
+    fn = lib().orc_encode_icm_fully_ex
     fn.argtypes = [_f32p, _f32p, _u8p, ct.c_int64, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int,
-                   ct.c_int, ct.c_uint64, ct.c_int64, _i32p, CONDITION_FN, _i32p, ct.c_int, _u8p, _f32p, _f32p, _i32p]
+                   ct.c_int, ct.c_uint64, ct.c_int64, _i32p, CONDITION_FN, _i32p, ct.c_int, _u8p, _f32p, _f32p, _i32p,
+                   _f32p, _f32p, _f32p, f64p]
     rc = fn(_p(X, _f32p), _p(C, _f32p), _p(B, _u8p), n, d, m, h, ilsiter, icmiter, npert, int(bool(randord)),
             seed, g0, _p(orders, _i32p) if orders is not None else None,
             step if step is not None else ct.cast(None, CONDITION_FN),
-            _p(snaps, _i32p) if ns else None, ns, _p(Bs, _u8p), _p(objs, _f32p), _p(cost, _f32p), _p(stats, _i32p))
+            _p(snaps, _i32p) if ns else None, ns, _p(Bs, _u8p), _p(objs, _f32p), _p(cost, _f32p), _p(stats, _i32p),
+            _p(U, _f32p) if blas else None, _p(bn, _f32p) if blas else None, _p(bt, _f32p) if blas else None,
+            ph.ctypes.data_as(f64p))
     if rc != 0:
         raise RuntimeError("orc_encode_icm_fully failed: %d" % rc)
-    return dict(B=B, cost=cost, stats=stats[:ilsiter], B_snap=Bs[:ns], objs=objs[:ns])
+    out = dict(B=B, cost=cost, stats=stats[:ilsiter], B_snap=Bs[:ns], objs=objs[:ns])
+    if want_phases:
+        out["phases"] = {"tables": float(ph[0] + t_tab), "unaries": float(ph[1] + t_un), "icm_steps": float(ph[2]),
+                         "veccost": float(ph[3]), "other": float(ph[4])}
+    return out
 
 
 LSQ, CQ, PQ = 0, 1, 2

@@ -28,6 +28,7 @@
  * -ffp-contract=off matters: every fused operation below is an explicit fmaf().
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -212,18 +213,26 @@ typedef void (*condition_fn)(unsigned char*, float*, float*, float*, int*, int*,
  *   stats    2*ilsiter ints or NULL: (#equal, #better) per ILS iteration (src/LSQ.jl:239-245)
  * The per-step copyto!(ub, unaries[j]) of src/LSQ.jl:69 is kept, so timing this function is
  * timing the reference's CPU algorithm, not a flattered variant. */
-int orc_encode_icm_fully(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
-                         int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
-                         const int* orders, condition_fn step,
-                         const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
-                         float* cost_out, int* stats) {
+/* _ex: the same loop with two TIMING-ONLY extras for bench.py's CPU arm (parity tests never pass them):
+ *   U_pre / bin_pre / bint_pre  unaries [m][n][h] and tables built by the caller with a BLAS sgemm, as the
+ *                               reference does (src/utils.jl:135-136,164) -- the fixed-order fmaf chains above
+ *                               pin the arithmetic for parity but would handicap a timed baseline;
+ *   phases[5]                   seconds spent in {tables, unaries, ICM steps incl. the per-step unary copy,
+ *                               veccost, perturb + accept + snapshots}. */
+int orc_encode_icm_fully_ex(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
+                            int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
+                            const int* orders, condition_fn step,
+                            const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
+                            float* cost_out, int* stats,
+                            const float* U_pre, const float* bin_pre, const float* bint_pre, double* phases) {
   if (h != H256) return -1; /* src/LSQ.jl:173-175 */
   if (!step) step = orc_condition;
   int ncbi = m * (m - 1) / 2;
   size_t hh = (size_t)h * h;
-  float* U = (float*)malloc(sizeof(float) * (size_t)m * n * h);
-  float* bin = (float*)malloc(sizeof(float) * hh * (ncbi > 0 ? ncbi : 1));
-  float* bin_t = (float*)malloc(sizeof(float) * hh * (ncbi > 0 ? ncbi : 1));
+  float* U = U_pre ? (float*)U_pre : (float*)malloc(sizeof(float) * (size_t)m * n * h);
+  float* bin = bin_pre ? (float*)bin_pre : (float*)malloc(sizeof(float) * hh * (ncbi > 0 ? ncbi : 1));
+  float* bin_t = bint_pre ? (float*)bint_pre : (float*)malloc(sizeof(float) * hh * (ncbi > 0 ? ncbi : 1));
+  double ph[5] = {0, 0, 0, 0, 0}, t0;
   int* cbi = (int*)malloc(sizeof(int) * 2 * (ncbi > 0 ? ncbi : 1));
   float* ub = (float*)malloc(sizeof(float) * (size_t)n * h);
   uint8_t* newB = (uint8_t*)malloc((size_t)n * m);
@@ -234,20 +243,31 @@ int orc_encode_icm_fully(const float* X, const float* C, uint8_t* B, int64_t n, 
   int* order = (int*)malloc(sizeof(int) * m);
   if (!U || !bin || !bin_t || !ub || !newB || !prevcost || !newcost) return -2;
 
-  orc_get_binaries(C, d, m, h, bin, bin_t, cbi);             /* src/LSQ.jl:288 */
-  orc_get_unaries(X, C, n, d, m, h, U);                      /* src/LSQ.jl:168 */
+  t0 = omp_get_wtime();
+  if (bin_pre && bint_pre) {
+    int idx = 0;
+    for (int i = 0; i < m; i++) for (int j = i + 1; j < m; j++, idx++) { cbi[2 * idx] = i; cbi[2 * idx + 1] = j; }
+  } else {
+    orc_get_binaries(C, d, m, h, bin, bin_t, cbi);           /* src/LSQ.jl:288 */
+  }
+  ph[0] = omp_get_wtime() - t0; t0 = omp_get_wtime();
+  if (!U_pre) orc_get_unaries(X, C, n, d, m, h, U);          /* src/LSQ.jl:168 */
+  ph[1] = omp_get_wtime() - t0;
   for (int i = 0; i < ncbi; i++) {                           /* src/LSQ.jl:186-190 */
     pair2idx[cbi[2 * i] * m + cbi[2 * i + 1]] = i;
     pair2idx[cbi[2 * i + 1] * m + cbi[2 * i]] = i;
   }
 
   for (int it = 0; it < ilsiter; it++) {
+    t0 = omp_get_wtime();
     orc_veccost(X, B, C, n, d, m, h, prevcost);              /* src/LSQ.jl:201 */
+    ph[3] += omp_get_wtime() - t0; t0 = omp_get_wtime();
     memcpy(newB, B, (size_t)n * m);                          /* src/LSQ.jl:207 */
     if (orders) memcpy(order, orders + (size_t)it * m, sizeof(int) * m);
     else if (randord) orc_randperm(seed, it, m, order);      /* src/LSQ.jl:218-221 */
     else for (int i = 0; i < m; i++) order[i] = i;
     orc_perturb_codes(newB, n, m, h, npert, seed, it, g0);   /* src/LSQ.jl:225 */
+    ph[4] += omp_get_wtime() - t0; t0 = omp_get_wtime();
     for (int i = 0; i < icmiter; i++)                        /* src/LSQ.jl:64-78 */
       for (int s = 0; s < m; s++) {
         int j = order[s];
@@ -256,7 +276,9 @@ int orc_encode_icm_fully(const float* X, const float* C, uint8_t* B, int64_t n, 
         memcpy(ub, U + (size_t)j * n * h, sizeof(float) * (size_t)n * h);  /* src/LSQ.jl:69 */
         step(newB, ub, bin, bin_t, pair2idx, to_cond, j, (int)n, m);
       }
+    ph[2] += omp_get_wtime() - t0; t0 = omp_get_wtime();
     orc_veccost(X, newB, C, n, d, m, h, newcost);            /* src/LSQ.jl:237 */
+    ph[3] += omp_get_wtime() - t0; t0 = omp_get_wtime();
     int neq = 0, nbet = 0;
     for (int64_t l = 0; l < n; l++) {
       if (newcost[l] == prevcost[l]) neq++;
@@ -268,12 +290,31 @@ int orc_encode_icm_fully(const float* X, const float* C, uint8_t* B, int64_t n, 
         if (B_snap) memcpy(B_snap + (size_t)s * n * m, B, (size_t)n * m);
         if (objs) objs[s] = (float)orc_qerror(X, B, C, n, d, m, h);
       }
+    ph[4] += omp_get_wtime() - t0;
   }
   if (cost_out) orc_veccost(X, B, C, n, d, m, h, cost_out);
-  free(U); free(bin); free(bin_t); free(cbi); free(ub); free(newB); free(prevcost); free(newcost);
+  if (phases) memcpy(phases, ph, sizeof ph);
+  if (!U_pre) free(U);
+  if (!bin_pre) free(bin);
+  if (!bint_pre) free(bin_t);
+  free(cbi); free(ub); free(newB); free(prevcost); free(newcost);
   free(pair2idx); free(to_cond); free(order);
   return 0;
 }
+
+int orc_encode_icm_fully(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
+                         int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
+                         const int* orders, condition_fn step,
+                         const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
+                         float* cost_out, int* stats) {
+  return orc_encode_icm_fully_ex(X, C, B, n, d, m, h, ilsiter, icmiter, npert, randord, seed, g0, orders, step,
+                                 snap_iters, n_snap, B_snap, objs, cost_out, stats, NULL, NULL, NULL, NULL);
+}
+
+/* OpenMP team size of this process (liboracle and oracle/_ref share one libgomp): bench.py's CPU arm forces it to
+ * the host core count -- torchrun exports OMP_NUM_THREADS=1 -- and reports what it got. */
+void orc_set_num_threads(int t) { if (t > 0) omp_set_num_threads(t); }
+int orc_get_max_threads(void) { return omp_get_max_threads(); }
 
 /* ------------------------------------------------------------------------------------------
  * Linear scan.  (dist, idx) pairs ordered lexicographically, as std::partial_sort over
