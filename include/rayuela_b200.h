@@ -39,6 +39,21 @@ int rayuela_set_device(int device);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches claim). */
 uint64_t rayuela_launch_count(void);
 
+/* Multi-GPU inside ONE process -- how a single Julia process drives the whole base (encode_icm_cuda is called once
+ * for all of it, src/LSQ_GPU.jl:218-264, with `nsplits` serial chunks through device 0, :41,45,236-255).
+ * rayuela_init(devices, n) configures a device set (a device may be listed twice: two shards on one GPU); without it
+ * the list is read once from the environment variable RAYUELA_B200_DEVICES ("0,1,2,3").  With more than one slot,
+ * every HOST-pointer call of rayuela_encode_icm splits the base in contiguous splitarray slices (src/utils.jl:179-203),
+ * one per slot, encoded concurrently (codes bit-identical to the single-device call: vectors are independent and the
+ * RNG is keyed on the global index), and rayuela_index_create builds a base-sharded index whose rayuela_index_search
+ * scans every shard for all queries, copies the per-shard top-k peer-to-peer to the first slot and merges them by the
+ * (dist, id) total order (ids and distances identical to the single-device search).  Device-pointer calls always run
+ * on the pointers' device.  n_devices <= 1 (or never calling it, with the variable unset) = single-device mode.
+ * rayuela_shutdown releases the per-slot streams; free multi-device indexes first. */
+int rayuela_init(const int* devices, int n_devices);
+int rayuela_shutdown(void);
+int rayuela_device_count(void); /* slots of the configured set (1 in single-device mode) */
+
 /* ---- path (1): LSQ / LSQ++ ICM-ILS encoding ------------------------------------------------------ */
 
 /* Replaces encode_icm_fully! (src/LSQ.jl:152-252) together with its callee loop
@@ -105,14 +120,19 @@ typedef struct rayuela_index rayuela_index;
 /* id_offset is added to every returned id (global ids for a base shard of a multi-GPU index). */
 int rayuela_index_create(rayuela_index** out, int kind, const uint8_t* codes, const float* dbnorms, int64_t n,
                          int m, int h, int64_t id_offset, unsigned flags, void* stream);
-/* codebooks: d-by-(m*h) (LSQ/CQ) or sub-by-h-by-m (PQ, d = m*sub).  dists/idx: k-by-nq. */
+/* codebooks: d-by-(m*h) (LSQ/CQ) or sub-by-h-by-m (PQ, d = m*sub).  dists/idx: k-by-nq.
+ * Lookup-table entries must be finite and below 1e37 in magnitude (inf / NaN in the queries or codebooks, or
+ * overflowing products): otherwise host-pointer calls fail with RAYUELA_ERR_ARG and device-pointer calls (which
+ * cannot report without synchronising) return NaN distances and id -1 for every query. */
 int rayuela_index_search(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d, int k,
                          float* dists, int32_t* idx, unsigned flags, void* stream);
 int rayuela_index_free(rayuela_index* ix);
 
 /* Merge S per-shard result lists (each k-by-nq, sorted by (dist, id)) into the global top-k by the same
  * total order std::partial_sort uses on pair<float,int> (pairwise_byte.cpp:82).  Used after the all-gather
- * of per-GPU results; in/out layouts [S][nq][k] and [nq][k]. */
+ * of per-GPU results; in/out layouts [S][nq][k] and [nq][k].  Any S and k: up to 16384 keys per query are sorted
+ * in shared memory, larger merges (2 shards at the reference's default k = 10000) run as a tree of pairwise
+ * rank merges in global memory (needs S*nq*k*12 bytes of scratch). */
 int rayuela_topk_merge(const float* dists_in, const int32_t* idx_in, int S, int nq, int k, float* dists_out,
                        int32_t* idx_out, unsigned flags, void* stream);
 

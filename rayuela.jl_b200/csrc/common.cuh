@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -144,6 +145,26 @@ inline int sm_count() {
   }
   return n;
 }
+
+// ---- device set (rayuela_init / RAYUELA_B200_DEVICES) -------------------------------------------------------
+// Slots of the configured device list; a device may be listed more than once (two shards on one GPU -- how the
+// single-GPU tests exercise the sharded paths).  Empty list = single-device mode on the caller's current device.
+struct DeviceSlot {
+  int device = 0;
+  cudaStream_t stream = nullptr;   // non-blocking stream owned by the library, one per slot
+};
+const std::vector<DeviceSlot>& device_slots();   // lazily initialised from RAYUELA_B200_DEVICES when rayuela_init was not called
+
+// reference rule for splitting n items in nparts (src/utils.jl:179-203): the first n % nparts parts get one extra
+inline void split_range(int64_t n, int nparts, int part, int64_t* a, int64_t* b) {
+  const int64_t per = n / nparts, xtra = n % nparts;
+  *a = part * per + std::min<int64_t>(part, xtra);
+  *b = *a + per + (part < xtra ? 1 : 0);
+}
+
+// Runs fn(slot_index) on one host thread per device slot (each thread makes its slot's device current) and returns
+// the first non-OK status, with that thread's error message copied to the caller's error channel.
+int for_each_slot(const std::vector<DeviceSlot>& slots, const std::function<int(int)>& fn);
 
 // ---- Philox4x32-10 (host + device): the RNG contract shared with the oracle (DESIGN.md "RNG") --------
 __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {

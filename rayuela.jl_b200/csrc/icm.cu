@@ -326,6 +326,7 @@ struct IcmParams {
   int* stats;           // [ilsiter][2] (#equal, #better)
   unsigned long long* steps;  // [2] conditioning steps actually executed (memoisation skips the rest); of those,
                               //     steps the quantised pre-filter could not decide (exact path taken)
+  unsigned long long* next;   // work counter of this launch (zeroed by the host): warps draw vectors from it
   int64_t nc, n_total, g0;
   uint64_t seed;
   int d, ilsiter, icmiter, npert, n_snap;
@@ -369,10 +370,16 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
   __syncthreads();
 
-  const int64_t wstride = (int64_t)gridDim.x * nwarps;
   unsigned long long nsteps = 0, nexact = 0;
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-  for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < p.nc; l += wstride) {
+  // Dynamic schedule: a vector's time depends on how many of its steps the memoisation skips, so a fixed stride
+  // leaves the slowest warp ~7 % behind the mean (1M vectors over 4736 warps); every warp draws its next vector
+  // from one global counter instead (one atomic per vector).  Results do not depend on the schedule.
+  for (;;) {
+    unsigned long long lnext = 0;
+    if (lane == 0) lnext = atomicAdd(p.next, 1ull);
+    const int64_t l = (int64_t)__shfl_sync(0xffffffffu, lnext, 0);
+    if (l >= p.nc) break;
     const float* x = p.X + (size_t)l * p.d;
     Code cur = load_code<M>(p.B + (size_t)l * M);
     float curcost = warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
@@ -849,29 +856,79 @@ static size_t unary_budget_bytes() {
   return (size_t)16 << 30;
 }
 
-extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
-                                  int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
-                                  const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap,
-                                  float* objs, float* cost_out, int* stats, unsigned flags, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  RYL_ARG(h == kH, "encode_icm: only codebooks with 256 entries are supported (src/LSQ.jl:173-175)");
-  RYL_ARG(m >= 1 && m <= 16, "encode_icm: m must be in 1..16");
-  RYL_ARG(n >= 0 && d >= 1, "encode_icm: bad n or d");
-  RYL_ARG(ilsiter >= 0 && icmiter >= 0 && npert >= 0, "encode_icm: negative iteration count");
-  RYL_ARG(n_snap >= 0 && (n_snap == 0 || snap_iters), "encode_icm: snap_iters missing");
-  RYL_ARG(X && C && B, "encode_icm: null array");
-  if (n == 0) return RAYUELA_OK;
+// sum of a device float array in double, deterministic (256 fixed partial ranges); synchronises the stream
+static int device_sum(const float* v, int64_t n, double* out, cudaStream_t s) {
+  double mean = 0;
+  RYL_TRY(device_mean(v, n, &mean, s));
+  *out = mean * (double)n;
+  return RAYUELA_OK;
+}
+
+// small RAII helpers for the chunk pipeline of encode_icm_single
+struct StreamBox {
+  cudaStream_t s = nullptr;
+  ~StreamBox() { if (s) cudaStreamDestroy(s); }
+  int create() { RYL_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); return RAYUELA_OK; }
+};
+struct EventBox {
+  cudaEvent_t e = nullptr;
+  ~EventBox() { if (e) cudaEventDestroy(e); }
+  int create() { RYL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return RAYUELA_OK; }
+};
+
+// One device, one call: everything rayuela_encode_icm documents.  snap_sums (host, n_snap doubles, may be null)
+// receives the SUM of the per-vector costs at each snapshot, so a multi-device caller can form the global mean.
+static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int ilsiter,
+                             int icmiter, int npert, int randord, uint64_t seed, int64_t g0, const int* orders,
+                             const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs, double* snap_sums,
+                             float* cost_out, int* stats, unsigned flags, cudaStream_t s) {
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
   const int mh = m * kH;
 
+  // chunking of the base set: the unary buffer (m KB per vector) stays within budget (nsplits of
+  // src/LSQ_GPU.jl:226-255, done inside the library); gridDim.y of K1 caps a chunk at 65535 * 128 vectors; with HOST
+  // arrays the base is cut in >= 4 chunks so that the upload of chunk c+1 overlaps the kernels of chunk c
+  const int64_t per_vec = (int64_t)mh * sizeof(float);
+  int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
+  chunk = std::min<int64_t>(chunk, (int64_t)65535 * 128);
+  if (!dev && n >= 4 * 65536 && !env_off("RAYUELA_B200_ICM_OVERLAP"))
+    chunk = std::min<int64_t>(chunk, ((n + 3) / 4 + 1023) / 1024 * 1024);
+  if (const char* e = getenv("RAYUELA_B200_ICM_CHUNKS"))      // tuning knob: force a chunk count
+    if (atoi(e) >= 1) chunk = std::min<int64_t>(chunk, ((n + atoi(e) - 1) / atoi(e) + 1023) / 1024 * 1024);
+  const int nchunks = (int)((n + chunk - 1) / chunk);
+  const bool piped = nchunks > 1;
+
+  // streams: chunks alternate between the caller's stream and s_alt (the tail of chunk c overlaps the head of chunk
+  // c+1; chunks c and c+2 share a stream and a unary buffer, so the reuse is ordered for free); uploads on s_copy
+  StreamBox alt_box, copy_box;
+  EventBox ev_setup, ev_alt_done;
+  std::vector<EventBox> ev_up(piped && !dev ? nchunks : 0);
+  cudaStream_t s_alt = s, s_copy = s;
+  if (piped) {
+    RYL_TRY(alt_box.create());
+    s_alt = alt_box.s;
+    RYL_TRY(ev_setup.create());
+    RYL_TRY(ev_alt_done.create());
+    if (!dev) {
+      RYL_TRY(copy_box.create());
+      s_copy = copy_box.s;
+      for (auto& e : ev_up) RYL_TRY(e.create());
+    }
+  }
+
   InArg<float> x_in, c_in;
-  RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  if (dev || !piped) {
+    RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  } else {
+    RYL_TRY(x_in.own.alloc((size_t)n * d * sizeof(float), s));
+    x_in.d = x_in.own.as<float>();
+  }
   RYL_TRY(c_in.bind(C, (size_t)mh * d, dev, s));
   OutArg<uint8_t> b_io, snap_out;
   RYL_TRY(b_io.bind(B, (size_t)n * m, dev, s, /*copy_in=*/true));
   RYL_TRY(snap_out.bind(n_snap ? B_snap : nullptr, (size_t)n_snap * n * m, dev, s));
   DevBuf snap_tmp;  // objs wanted without B_snap: keep the snapshots on the device only
-  if (n_snap && !snap_out.d && objs) {
+  if (n_snap && !snap_out.d && (objs || snap_sums)) {
     RYL_TRY(snap_tmp.alloc((size_t)n_snap * n * m, s));
     snap_out.d = snap_tmp.as<uint8_t>();
   }
@@ -903,7 +960,7 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   if (m > 1) RYL_LAUNCH(tables_kernel, dim3(kH / 32, kH / 32, m * m), 256, 0, s, c_in.d, T_d.as<float>(), d, m);
   // K2q: quantised copy for the pre-filter
   const bool pf = !env_off("RAYUELA_B200_ICM_PF");
-  DevBuf Tq_d, tmax_d, umax_d, pfc_d;
+  DevBuf Tq_d, tmax_d, pfc_d;
   if (pf) {
     RYL_TRY(Tq_d.alloc((size_t)m * m * kH * (kH / 2) * sizeof(uint32_t), s));
     RYL_TRY(tmax_d.alloc((size_t)m * sizeof(unsigned int), s));
@@ -917,29 +974,48 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
     RYL_LAUNCH(pf_consts_kernel, 1, 32, 0, s, tmax_d.as<unsigned int>(), m, pfc_d.as<float2>());
   }
 
-  // chunk the base set so the unary buffer (m KB per vector) stays within budget (nsplits of
-  // src/LSQ_GPU.jl:226-255, done in space on one device instead of by the caller)
-  const int64_t per_vec = (int64_t)mh * sizeof(float);
-  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
-  DevBuf U_d;
-  RYL_TRY(U_d.alloc((size_t)std::min(chunk, n) * per_vec, s));
-  if (pf) RYL_TRY(umax_d.alloc((size_t)std::min(chunk, n) * sizeof(unsigned int), s));
-  for (int64_t l0 = 0; l0 < n; l0 += chunk) {
+  const int nbuf = piped ? 2 : 1;
+  DevBuf U_d[2], umax_d[2], next_d;
+  RYL_TRY(next_d.alloc((size_t)nchunks * sizeof(unsigned long long), s));
+  RYL_CUDA(cudaMemsetAsync(next_d.p, 0, next_d.bytes, s));
+  for (int i = 0; i < nbuf; i++) {
+    RYL_TRY(U_d[i].alloc((size_t)std::min(chunk, n) * per_vec, s));
+    if (pf) RYL_TRY(umax_d[i].alloc((size_t)std::min(chunk, n) * sizeof(unsigned int), s));
+  }
+  if (piped) {
+    RYL_CUDA(cudaEventRecord(ev_setup.e, s));               // allocations + tables are ordered before the other streams
+    RYL_CUDA(cudaStreamWaitEvent(s_alt, ev_setup.e, 0));
+    if (!dev) {
+      RYL_CUDA(cudaStreamWaitEvent(s_copy, ev_setup.e, 0));
+      for (int c = 0; c < nchunks; c++) {
+        const int64_t l0 = (int64_t)c * chunk, nc = std::min(chunk, n - l0);
+        RYL_CUDA(cudaMemcpyAsync(const_cast<float*>(x_in.d) + (size_t)l0 * d, X + (size_t)l0 * d,
+                                 (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, s_copy));
+        RYL_CUDA(cudaEventRecord(ev_up[c].e, s_copy));
+      }
+    }
+  }
+  for (int c = 0; c < nchunks; c++) {
+    const int64_t l0 = (int64_t)c * chunk;
     const int64_t nc = std::min(chunk, n - l0);
+    cudaStream_t cs = (c & 1) ? s_alt : s;
+    float* U = U_d[c & (nbuf - 1)].as<float>();
+    unsigned int* umax = umax_d[c & (nbuf - 1)].as<unsigned int>();
+    if (piped && !dev) RYL_CUDA(cudaStreamWaitEvent(cs, ev_up[c].e, 0));
     dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
-    if (pf) RYL_CUDA(cudaMemsetAsync(umax_d.p, 0, (size_t)nc * sizeof(unsigned int), s));
+    if (pf) RYL_CUDA(cudaMemsetAsync(umax, 0, (size_t)nc * sizeof(unsigned int), cs));
     if (d % 4 == 0)
-      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh, umax_d.as<unsigned int>());
+      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
+                 umax);
     else
-      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh, umax_d.as<unsigned int>());
+      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
+                 umax);
     IcmParams p;
-    p.U = U_d.as<float>();
+    p.U = U;
     p.T = T_d.as<float>();
     p.Tq = pf ? Tq_d.as<uint32_t>() : nullptr;
     p.pfc = pfc_d.as<float2>();
-    p.umax = umax_d.as<unsigned int>();
+    p.umax = umax;
     p.X = x_in.d + (size_t)l0 * d;
     p.C = c_in.d;
     p.B = b_io.d + (size_t)l0 * m;
@@ -949,6 +1025,7 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
     p.B_snap = snap_out.d ? snap_out.d + (size_t)l0 * m : nullptr;
     p.stats = stats_d.as<int>();
     p.steps = steps_d;
+    p.next = next_d.as<unsigned long long>() + c;
     p.nc = nc;
     p.n_total = n;
     p.g0 = g0 + l0;
@@ -959,21 +1036,26 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
     p.npert = npert;
     p.n_snap = snap_out.d ? n_snap : 0;
     int rc = RAYUELA_OK;
-#define CALL(M) rc = launch_icm<M>(p, s)
+#define CALL(M) rc = launch_icm<M>(p, cs)
     RYL_M_SWITCH(m, CALL)
 #undef CALL
     RYL_TRY(rc);
   }
+  if (piped) {                                              // join: everything below is ordered after both streams
+    RYL_CUDA(cudaEventRecord(ev_alt_done.e, s_alt));
+    RYL_CUDA(cudaStreamWaitEvent(s, ev_alt_done.e, 0));
+  }
 
   // objective at each snapshot: qerror(RX, B, C), src/LSQ_GPU.jl:197
-  if (n_snap && objs && snap_out.d) {
+  if (n_snap && (objs || snap_sums) && snap_out.d) {
     DevBuf tmp;
     RYL_TRY(tmp.alloc((size_t)n * sizeof(float), s));
     for (int si = 0; si < n_snap; si++) {
       RYL_TRY(device_veccost(x_in.d, snap_out.d + (size_t)si * n * m, c_in.d, n, d, m, tmp.as<float>(), s));
-      double mean = 0;
-      RYL_TRY(device_mean(tmp.as<float>(), n, &mean, s));
-      objs[si] = (float)mean;
+      double sum = 0;
+      RYL_TRY(device_sum(tmp.as<float>(), n, &sum, s));
+      if (objs) objs[si] = (float)(sum / (double)n);
+      if (snap_sums) snap_sums[si] = sum;
     }
   }
   RYL_TRY(b_io.flush(s));
@@ -990,6 +1072,82 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
   }
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
   return RAYUELA_OK;
+}
+
+// Host arrays + a configured device set (rayuela_init / RAYUELA_B200_DEVICES): the base is cut in contiguous
+// splitarray slices (src/utils.jl:179-203 -- the rule of the reference's serial `nsplits`, src/LSQ_GPU.jl:238-255),
+// one per device slot, encoded concurrently by one host thread per slot.  Vectors are independent and the RNG is
+// keyed on the global index g0 + l, so the codes are bit-identical to the single-device call; no collective.
+static int encode_icm_multi(const std::vector<DeviceSlot>& slots, const float* X, const float* C, uint8_t* B, int64_t n,
+                            int d, int m, int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
+                            const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
+                            float* cost_out, int* stats) {
+  const int D = (int)slots.size();
+  std::vector<std::vector<uint8_t>> snaps(D);
+  std::vector<std::vector<double>> sums(D, std::vector<double>((size_t)std::max(n_snap, 1), 0.0));
+  std::vector<std::vector<int>> st(D, std::vector<int>((size_t)std::max(ilsiter, 1) * 2, 0));
+  std::vector<uint64_t> done(D, 0), exact(D, 0);
+  RYL_TRY(for_each_slot(slots, [&](int i) -> int {
+    int64_t a, b;
+    split_range(n, D, i, &a, &b);
+    const int64_t ni = b - a;
+    if (ni == 0) return RAYUELA_OK;
+    if (n_snap && B_snap) snaps[i].resize((size_t)n_snap * ni * m);
+    RYL_TRY(encode_icm_single(X + (size_t)a * d, C, B + (size_t)a * m, ni, d, m, ilsiter, icmiter, npert, randord, seed,
+                              g0 + a, orders, snap_iters, n_snap, (n_snap && B_snap) ? snaps[i].data() : nullptr, nullptr,
+                              (n_snap && objs) ? sums[i].data() : nullptr, cost_out ? cost_out + a : nullptr,
+                              stats ? st[i].data() : nullptr, 0, slots[i].stream));
+    if (stats) {
+      done[i] = g_icm_steps_done;        // this worker thread's counters
+      exact[i] = g_icm_steps_exact;
+    }
+    return RAYUELA_OK;
+  }));
+  for (int i = 0; i < D; i++) {
+    int64_t a, b;
+    split_range(n, D, i, &a, &b);
+    if (n_snap && B_snap)
+      for (int si = 0; si < n_snap; si++)
+        memcpy(B_snap + ((size_t)si * n + a) * m, snaps[i].data() + (size_t)si * (b - a) * m, (size_t)(b - a) * m);
+  }
+  if (n_snap && objs)
+    for (int si = 0; si < n_snap; si++) {
+      double t = 0;
+      for (int i = 0; i < D; i++) t += sums[i][si];
+      objs[si] = (float)(t / (double)n);
+    }
+  if (stats) {
+    g_icm_steps_done = g_icm_steps_exact = 0;
+    for (int i = 0; i < 2 * ilsiter; i++) stats[i] = 0;
+    for (int i = 0; i < D; i++) {
+      for (int t = 0; t < 2 * ilsiter; t++) stats[t] += st[i][t];
+      g_icm_steps_done += done[i];
+      g_icm_steps_exact += exact[i];
+    }
+    g_icm_steps_total = (uint64_t)n * ilsiter * icmiter * m;
+  }
+  return RAYUELA_OK;
+}
+
+extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
+                                  int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
+                                  const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap,
+                                  float* objs, float* cost_out, int* stats, unsigned flags, void* stream) {
+  RYL_ARG(h == kH, "encode_icm: only codebooks with 256 entries are supported (src/LSQ.jl:173-175)");
+  RYL_ARG(m >= 1 && m <= 16, "encode_icm: m must be in 1..16");
+  RYL_ARG(n >= 0 && d >= 1, "encode_icm: bad n or d");
+  RYL_ARG(ilsiter >= 0 && icmiter >= 0 && npert >= 0, "encode_icm: negative iteration count");
+  RYL_ARG(n_snap >= 0 && (n_snap == 0 || snap_iters), "encode_icm: snap_iters missing");
+  RYL_ARG(X && C && B, "encode_icm: null array");
+  if (n == 0) return RAYUELA_OK;
+  if (!(flags & RAYUELA_DEVICE_PTRS)) {
+    const std::vector<DeviceSlot> slots = device_slots();
+    if (slots.size() > 1 && n >= (int64_t)slots.size() * 1024)
+      return encode_icm_multi(slots, X, C, B, n, d, m, ilsiter, icmiter, npert, randord, seed, g0, orders, snap_iters,
+                              n_snap, B_snap, objs, cost_out, stats);
+  }
+  return encode_icm_single(X, C, B, n, d, m, ilsiter, icmiter, npert, randord, seed, g0, orders, snap_iters, n_snap,
+                           B_snap, objs, nullptr, cost_out, stats, flags, (cudaStream_t)stream);
 }
 
 extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,
@@ -1088,7 +1246,8 @@ extern "C" int rayuela_quantize_chainq(const float* X, const float* C, int64_t n
   RYL_TRY(T_d.alloc((size_t)m * m * kH * kH * sizeof(float), s));
   if (m > 1) RYL_LAUNCH(tables_kernel, dim3(kH / 32, kH / 32, m * m), 256, 0, s, c_in.d, T_d.as<float>(), d, m);
   const int64_t per_vec = (int64_t)mh * sizeof(float);
-  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
+  const int64_t chunk = std::min<int64_t>((int64_t)65535 * 128,   // gridDim.y of K1
+      std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec))));
   RYL_TRY(U_d.alloc((size_t)std::min(chunk, n) * per_vec, s));
   // chain table i -> i+1 with k (state of i) major: T[(i+1)*m + i][b = k][c = j] = 2<C_{i+1}[:,j], C_i[:,k]>
   const float* TT = T_d.as<float>() + (size_t)(1 * m + 0) * kH * kH;

@@ -26,7 +26,7 @@ static constexpr int kH = 256;
 template <int KIND>
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ queries, const float* __restrict__ cb,
                                                   float* __restrict__ lut, int nq, int d, int len, int mh,
-                                                  int tiled) {
+                                                  int tiled, int* __restrict__ bad) {
   constexpr int CH = 64;
   __shared__ float cs[32][CH + 1];
   __shared__ float qs[32][CH];
@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
   for (int i = 0; i < 4; i++) {
     int q = q0 + qg + 8 * i;
     if (q < nq) {
+      // The scan restarts a lane's accumulator by multiplying it by zero, so one non-finite partial sum would turn
+      // every later code of that lane into NaN.  Entries are therefore required to be finite and small enough that a
+      // sum of 16 cannot overflow; a violation fails the whole search instead of silently dropping neighbours.
+      if (!(fabsf(acc[i]) <= 1e37f)) *bad = 1;
       if (tiled == 1) {
         // layout of scanx_kernel<8>'s shared-memory tile (see there): [q/16][(q%16)/4][c][((q%4)/2)*8 + k][q%2]
         const int ent = e0 + e, k = ent >> 8, c = ent & 255;
@@ -345,7 +349,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   }
   if (tid < 16) {
     cnt_s[tid] = 0;
-    tau_s[tid] = p.tau0;
+    // padded dummy queries of the last tile (all-zero LUT) must never append: their threshold is -inf for good
+    tau_s[tid] = (q0 + tid < p.nq) ? p.tau0 : -__int_as_float(0x7f800000);
     lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
   }
   if (SPEC && p.pass == 1 && p.redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // redo launch: nothing to redo
@@ -392,7 +397,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   }
   float tau[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) tau[i] = p.tau0;
+  for (int i = 0; i < 8; i++)
+    tau[i] = (q0 + (i >> 1) * (2 * X::G) + g * 2 + (i & 1) < p.nq) ? p.tau0 : -__int_as_float(0x7f800000);
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
   int warm = 1;
   const int64_t c0 = (int64_t)slice * p.chunks_per_slice;
@@ -753,6 +759,63 @@ __global__ void __launch_bounds__(256) merge_kernel(const uint64_t* __restrict__
   }
 }
 
+// ---- general merge (any S*k): pairwise rank merges of sorted key lists in global memory --------------------------
+// (dists, ids) -> 64-bit keys of the (dist, id) total order
+__global__ void pairs_to_keys_kernel(const float* __restrict__ d, const int32_t* __restrict__ i,
+                                     uint64_t* __restrict__ keys, size_t total) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x)
+    keys[t] = make_key(d[t], (uint32_t)i[t]);
+}
+// out[q] = the k smallest of A[q] U B[q] (both sorted ascending, k keys each), sorted.  Element t of A goes to position
+// t + #{b < a}; element t of B to t + #{a <= b} (A wins ties, so equal keys from two lists keep list order); positions
+// >= k are dropped.  grid (ceil(k/256), nq).
+__global__ void __launch_bounds__(256) merge2_kernel(const uint64_t* __restrict__ A, const uint64_t* __restrict__ B,
+                                                     uint64_t* __restrict__ out, int k) {
+  const size_t q = blockIdx.y;
+  const uint64_t* a = A + q * k;
+  const uint64_t* b = B + q * k;
+  uint64_t* o = out + q * k;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k) return;
+  {
+    const uint64_t key = a[t];
+    int lo = 0, hi = min(k, k - t);                   // more than k-t-1 smaller keys in B: position >= k anyway
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (b[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (t + lo < k) o[t + lo] = key;
+  }
+  {
+    const uint64_t key = b[t];
+    int lo = 0, hi = min(k, k - t);
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (a[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    if (t + lo < k) o[t + lo] = key;
+  }
+}
+__global__ void keys_to_pairs_kernel(const uint64_t* __restrict__ keys, float* __restrict__ dout,
+                                     int32_t* __restrict__ iout, int64_t id_add, int k, int ldo) {
+  const size_t q = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k) return;
+  const uint64_t key = keys[q * k + t];
+  dout[q * ldo + t] = ordered_to_f32((uint32_t)(key >> 32));
+  iout[q * ldo + t] = (int32_t)((int64_t)(uint32_t)key + id_add);
+}
+
+// a search whose LUT held a non-finite / overflowing entry returns NaN distances and id -1 everywhere (device-pointer
+// calls cannot return a status without synchronising; host-pointer calls also fail with RAYUELA_ERR_ARG)
+__global__ void poison_kernel(const int* __restrict__ bad, float* __restrict__ d, int32_t* __restrict__ i, size_t total) {
+  if (*bad == 0) return;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    d[t] = __int_as_float(0x7fc00000);
+    i[t] = -1;
+  }
+}
+
 // lower bound for the next pass of a k > one-pass search: the last key the previous pass returned
 __global__ void lower_bound_kernel(const float* __restrict__ d, const int32_t* __restrict__ i, int nq, int ldo,
                                    int col, int64_t id_add, uint64_t* __restrict__ lb) {
@@ -772,6 +835,9 @@ struct rayuela_index {
   int64_t n = 0, id_offset = 0;
   int64_t nchunks = 0;   // 1024-code warp chunks of the skewed layout
   DevBuf norms, skew;    // fp32 norms (LSQ); skewed offset fields (skew_fields_kernel)
+  // multi-device parent (rayuela_init / RAYUELA_B200_DEVICES, host arrays): one shard per device slot, no own buffers
+  std::vector<rayuela_index*> shards;
+  std::vector<DeviceSlot> slots;
 };
 
 static int host_pow2ceil(int x) {
@@ -780,16 +846,9 @@ static int host_pow2ceil(int x) {
   return p;
 }
 
-extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t* codes, const float* dbnorms,
-                                    int64_t n, int m, int h, int64_t id_offset, unsigned flags, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  RYL_ARG(out != nullptr, "index_create: out is null");
-  RYL_ARG(kind >= 0 && kind <= 2, "index_create: unknown kind");
-  RYL_ARG(h == kH, "index_create: only h = 256 is supported (one byte per codebook)");
-  RYL_ARG(m >= 1 && m <= 16, "index_create: m must be in 1..16");
+static int index_create_single(rayuela_index** out, int kind, const uint8_t* codes, const float* dbnorms, int64_t n,
+                               int m, int h, int64_t id_offset, unsigned flags, cudaStream_t s) {
   RYL_ARG(n >= 1 && n < (1ll << 32) - 4096, "index_create: n must be in 1..2^32-4097 per index shard");
-  RYL_ARG(codes != nullptr, "index_create: codes is null");
-  RYL_ARG(kind != RAYUELA_SCAN_LSQ || dbnorms != nullptr, "index_create: LSQ scan needs dbnorms");
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
   rayuela_index* ix = new rayuela_index();
   ix->kind = kind;
@@ -833,6 +892,14 @@ extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t
 
 extern "C" int rayuela_index_free(rayuela_index* ix) {
   if (ix) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (rayuela_index* sh : ix->shards) {
+      if (!sh) continue;
+      cudaSetDevice(sh->device);
+      rayuela_index_free(sh);
+    }
+    if (!ix->shards.empty()) cudaSetDevice(cur);
     ix->norms.release();
     ix->skew.release();
     delete ix;
@@ -840,36 +907,90 @@ extern "C" int rayuela_index_free(rayuela_index* ix) {
   return RAYUELA_OK;
 }
 
+extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t* codes, const float* dbnorms,
+                                    int64_t n, int m, int h, int64_t id_offset, unsigned flags, void* stream) {
+  RYL_ARG(out != nullptr, "index_create: out is null");
+  RYL_ARG(kind >= 0 && kind <= 2, "index_create: unknown kind");
+  RYL_ARG(h == kH, "index_create: only h = 256 is supported (one byte per codebook)");
+  RYL_ARG(m >= 1 && m <= 16, "index_create: m must be in 1..16");
+  RYL_ARG(n >= 1, "index_create: n must be positive");
+  RYL_ARG(codes != nullptr, "index_create: codes is null");
+  RYL_ARG(kind != RAYUELA_SCAN_LSQ || dbnorms != nullptr, "index_create: LSQ scan needs dbnorms");
+  if (!(flags & RAYUELA_DEVICE_PTRS)) {
+    const std::vector<DeviceSlot> slots = device_slots();
+    const int D = (int)slots.size();
+    if (D > 1 && n >= (int64_t)D * 1024) {
+      // base-sharded index: slot i holds rows splitarray(n, D)[i] and returns global ids (id_offset + slice start)
+      rayuela_index* ix = new rayuela_index();
+      ix->kind = kind; ix->m = m; ix->h = h; ix->period = m <= 8 ? 8 : 16; ix->n = n; ix->id_offset = id_offset;
+      cudaGetDevice(&ix->device);
+      ix->slots = slots;
+      ix->shards.assign(D, nullptr);
+      int rc = for_each_slot(slots, [&](int i) -> int {
+        int64_t a, b;
+        split_range(n, D, i, &a, &b);
+        return index_create_single(&ix->shards[i], kind, codes + (size_t)a * m, dbnorms ? dbnorms + a : nullptr, b - a,
+                                   m, h, id_offset + a, 0, slots[i].stream);
+      });
+      if (rc != RAYUELA_OK) {
+        rayuela_index_free(ix);
+        return rc;
+      }
+      *out = ix;
+      return RAYUELA_OK;
+    }
+  }
+  return index_create_single(out, kind, codes, dbnorms, n, m, h, id_offset, flags, (cudaStream_t)stream);
+}
+
+// Merge of S sorted lists per query.  Up to 16384 keys per query: one block per query sorts them in shared memory
+// (merge_kernel).  Beyond that (e.g. 2 shards at the reference's default k = 10000, 8 shards at k > 2048): a tree of
+// pairwise rank merges in global memory (merge2_kernel), any S and k.
 static int merge_lists(const uint64_t* keys, const float* din, const int32_t* iin, int S, int nq, int k, float* dout,
                        int32_t* iout, int64_t id_add, cudaStream_t s, int ldo = 0) {
   if (ldo == 0) ldo = k;
-  size_t smem = (size_t)host_pow2ceil(S * k) * sizeof(uint64_t);
-  RYL_ARG(smem <= 200 * 1024, "topk merge: S*k too large for a single pass (max 16384 keys... 25600)");
-  RYL_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RYL_LAUNCH(merge_kernel, nq, 256, smem, s, keys, din, iin, S, nq, k, dout, iout, id_add, ldo);
+  const size_t smem = (size_t)host_pow2ceil(S * k) * sizeof(uint64_t);
+  if ((int64_t)S * k <= 16384 && smem <= 200 * 1024) {
+    RYL_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RYL_LAUNCH(merge_kernel, nq, 256, smem, s, keys, din, iin, S, nq, k, dout, iout, id_add, ldo);
+    return RAYUELA_OK;
+  }
+  const size_t per = (size_t)nq * k;                       // keys per list
+  DevBuf k0, ping, pong;
+  const uint64_t* cur = keys;
+  if (!cur) {
+    RYL_TRY(k0.alloc((size_t)S * per * sizeof(uint64_t), s));
+    RYL_LAUNCH(pairs_to_keys_kernel, sm_count() * 8, 256, 0, s, din, iin, k0.as<uint64_t>(), (size_t)S * per);
+    cur = k0.as<uint64_t>();
+  }
+  int L = S;
+  RYL_TRY(ping.alloc((size_t)((L + 1) / 2) * per * sizeof(uint64_t), s));
+  if (L > 2) RYL_TRY(pong.alloc((size_t)((L + 3) / 4) * per * sizeof(uint64_t), s));
+  uint64_t* dst = ping.as<uint64_t>();
+  uint64_t* other = pong.as<uint64_t>();
+  const dim3 grid((k + 255) / 256, nq);
+  while (L > 1) {
+    const int pairs = L / 2;
+    for (int i = 0; i < pairs; i++)
+      RYL_LAUNCH(merge2_kernel, grid, 256, 0, s, cur + (size_t)(2 * i) * per, cur + (size_t)(2 * i + 1) * per,
+                 dst + (size_t)i * per, k);
+    if (L & 1)
+      RYL_CUDA(cudaMemcpyAsync(dst + (size_t)pairs * per, cur + (size_t)(L - 1) * per, per * sizeof(uint64_t),
+                               cudaMemcpyDeviceToDevice, s));
+    L = (L + 1) / 2;
+    cur = dst;
+    std::swap(dst, other);
+  }
+  RYL_LAUNCH(keys_to_pairs_kernel, grid, 256, 0, s, cur, dout, iout, id_add, k, ldo);
   return RAYUELA_OK;
 }
 
-extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d,
-                                    int k, float* dists, int32_t* idx, unsigned flags, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  RYL_ARG(ix != nullptr, "index_search: null index");
-  RYL_ARG(nq >= 1 && d >= 1, "index_search: nq and d must be positive");
-  RYL_ARG(k >= 1 && (int64_t)k <= ix->n, "index_search: k must be in 1..n");
+// all arrays on the current device; bad: device int, set when a LUT entry is unusable (see lut_kernel)
+static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* cb_dev, int nq, int d, int k,
+                            float* d_dev, int32_t* i_dev, int* bad, cudaStream_t s) {
   const int m = ix->m, mh = m * kH;
   const bool pq = ix->kind == RAYUELA_SCAN_PQ;
-  RYL_ARG(!pq || d % m == 0, "index_search: PQ scan needs d divisible by m");
   const int len = pq ? d / m : d;
-  const bool dev = flags & RAYUELA_DEVICE_PTRS;
-
-  InArg<float> q_in, cb_in;
-  RYL_TRY(q_in.bind(queries, (size_t)nq * d, dev, s));
-  RYL_TRY(cb_in.bind(codebooks, (size_t)mh * len, dev, s));
-  OutArg<float> d_out;
-  OutArg<int32_t> i_out;
-  RYL_TRY(d_out.bind(dists, (size_t)nq * k, dev, s));
-  RYL_TRY(i_out.bind(idx, (size_t)nq * k, dev, s));
-
   const int period = ix->period;
   const int QT = period == 16 ? ScanX<16>::QB : ScanX<8>::QB;               // queries per block
   const int adds = period == 16 ? ScanX<16>::ADDS : ScanX<8>::ADDS;         // keys one query can gain per block-period
@@ -894,14 +1015,14 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
     RYL_TRY(lut.alloc((size_t)qtiles * kLutTileBytes, s));
     if (m < period || nqc % QT) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m
     dim3 lg(mh / 32, (nqc + 31) / 32);
-    const float* qptr = q_in.d + (size_t)qb * d;
+    const float* qptr = q_dev + (size_t)qb * d;
     const int tiled = period == 16 ? 2 : 1;
     if (ix->kind == RAYUELA_SCAN_LSQ)
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
     else if (ix->kind == RAYUELA_SCAN_CQ)
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
     else
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_in.d, lut.as<float>(), nqc, d, len, mh, tiled);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
     if (k > kmax) RYL_TRY(lb.alloc((size_t)nqc * sizeof(uint64_t), s));
 
     for (int koff = 0; koff < k; koff += kmax) {
@@ -987,16 +1108,112 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
         else { if (p.spec) RYL_SCANX(8, false, true) else RYL_SCANX(8, false, false) }
       }
 #undef RYL_SCANX
-      float* dq = d_out.d + (size_t)qb * k + koff;
-      int32_t* iq = i_out.d + (size_t)qb * k + koff;
+      float* dq = d_dev + (size_t)qb * k + koff;
+      int32_t* iq = i_dev + (size_t)qb * k + koff;
       RYL_TRY(merge_lists(part.as<uint64_t>(), nullptr, nullptr, S, nqc, kp, dq, iq, id_add, s, k));
       if (koff + kp < k)
         RYL_LAUNCH(lower_bound_kernel, (nqc + 255) / 256, 256, 0, s, dq, iq, nqc, k, kp - 1, id_add, lb.as<uint64_t>());
     }
   }
+  RYL_LAUNCH(poison_kernel, 64, 256, 0, s, bad, d_dev, i_dev, (size_t)nq * k);
+  return RAYUELA_OK;
+}
+
+static const char* kBadLutMsg =
+    "index_search: a lookup-table entry is not finite (or exceeds 1e37): queries / codebooks contain inf or NaN, or "
+    "their products overflow";
+
+// multi-device parent: every slot scans its shard for ALL queries (LUTs replicated), the per-shard top-k lists are
+// copied peer-to-peer to the first slot's device and merged there by the (dist, id) total order -- the single exchange
+// step of SURVEY 8e, done with peer copies inside one process instead of an NCCL all-gather between processes.
+static int index_search_multi(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d, int k,
+                              float* dists, int32_t* idx) {
+  const int D = (int)ix->shards.size();
+  const int len = ix->kind == RAYUELA_SCAN_PQ ? d / ix->m : d;
+  const size_t per = (size_t)nq * k;
+  for (int i = 0; i < D; i++)
+    RYL_ARG((int64_t)k <= ix->shards[i]->n, "index_search: k exceeds the size of a base shard");
+  int cur = 0;
+  RYL_CUDA(cudaGetDevice(&cur));
+  const DeviceSlot root = ix->slots[0];
+  RYL_CUDA(cudaSetDevice(root.device));
+  auto body = [&]() -> int {
+    DevBuf gd, gi, bad_all;
+    RYL_TRY(gd.alloc((size_t)D * per * sizeof(float), root.stream));
+    RYL_TRY(gi.alloc((size_t)D * per * sizeof(int32_t), root.stream));
+    RYL_CUDA(cudaStreamSynchronize(root.stream));            // the gather buffers exist before any peer writes to them
+    std::vector<int> bad(D, 0);
+    RYL_TRY(for_each_slot(ix->slots, [&](int i) -> int {
+      cudaStream_t s = ix->slots[i].stream;
+      InArg<float> q_in, cb_in;
+      RYL_TRY(q_in.bind(queries, (size_t)nq * d, false, s));
+      RYL_TRY(cb_in.bind(codebooks, (size_t)ix->m * kH * len, false, s));
+      DevBuf dl, il, bd;
+      RYL_TRY(dl.alloc(per * sizeof(float), s));
+      RYL_TRY(il.alloc(per * sizeof(int32_t), s));
+      RYL_TRY(bd.alloc(sizeof(int), s));
+      RYL_CUDA(cudaMemsetAsync(bd.p, 0, sizeof(int), s));
+      RYL_TRY(index_search_dev(ix->shards[i], q_in.d, cb_in.d, nq, d, k, dl.as<float>(), il.as<int32_t>(), bd.as<int>(), s));
+      RYL_CUDA(cudaMemcpyPeerAsync(gd.as<float>() + (size_t)i * per, root.device, dl.p, ix->slots[i].device,
+                                   per * sizeof(float), s));
+      RYL_CUDA(cudaMemcpyPeerAsync(gi.as<int32_t>() + (size_t)i * per, root.device, il.p, ix->slots[i].device,
+                                   per * sizeof(int32_t), s));
+      RYL_CUDA(cudaMemcpyAsync(&bad[i], bd.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      RYL_CUDA(cudaStreamSynchronize(s));
+      return RAYUELA_OK;
+    }));
+    for (int i = 0; i < D; i++)
+      if (bad[i]) return fail(RAYUELA_ERR_ARG, kBadLutMsg);
+    OutArg<float> d_out;
+    OutArg<int32_t> i_out;
+    RYL_TRY(d_out.bind(dists, per, false, root.stream));
+    RYL_TRY(i_out.bind(idx, per, false, root.stream));
+    RYL_TRY(merge_lists(nullptr, gd.as<float>(), gi.as<int32_t>(), D, nq, k, d_out.d, i_out.d, 0, root.stream));
+    RYL_TRY(d_out.flush(root.stream));
+    RYL_TRY(i_out.flush(root.stream));
+    RYL_CUDA(cudaStreamSynchronize(root.stream));
+    return RAYUELA_OK;
+  };
+  const int rc = body();
+  cudaSetDevice(cur);
+  return rc;
+}
+
+extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d,
+                                    int k, float* dists, int32_t* idx, unsigned flags, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  RYL_ARG(ix != nullptr, "index_search: null index");
+  RYL_ARG(nq >= 1 && d >= 1, "index_search: nq and d must be positive");
+  RYL_ARG(k >= 1 && (int64_t)k <= ix->n, "index_search: k must be in 1..n");
+  const int m = ix->m, mh = m * kH;
+  const bool pq = ix->kind == RAYUELA_SCAN_PQ;
+  RYL_ARG(!pq || d % m == 0, "index_search: PQ scan needs d divisible by m");
+  const int len = pq ? d / m : d;
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  if (!ix->shards.empty()) {
+    RYL_ARG(!dev, "index_search: a multi-device index takes host arrays");
+    return index_search_multi(ix, queries, codebooks, nq, d, k, dists, idx);
+  }
+
+  InArg<float> q_in, cb_in;
+  RYL_TRY(q_in.bind(queries, (size_t)nq * d, dev, s));
+  RYL_TRY(cb_in.bind(codebooks, (size_t)mh * len, dev, s));
+  OutArg<float> d_out;
+  OutArg<int32_t> i_out;
+  RYL_TRY(d_out.bind(dists, (size_t)nq * k, dev, s));
+  RYL_TRY(i_out.bind(idx, (size_t)nq * k, dev, s));
+  DevBuf bad;
+  RYL_TRY(bad.alloc(sizeof(int), s));
+  RYL_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
+  RYL_TRY(index_search_dev(ix, q_in.d, cb_in.d, nq, d, k, d_out.d, i_out.d, bad.as<int>(), s));
   RYL_TRY(d_out.flush(s));
   RYL_TRY(i_out.flush(s));
-  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  if (!dev) {
+    int bad_h = 0;
+    RYL_CUDA(cudaMemcpyAsync(&bad_h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaStreamSynchronize(s));
+    if (bad_h) return fail(RAYUELA_ERR_ARG, kBadLutMsg);
+  }
   return RAYUELA_OK;
 }
 

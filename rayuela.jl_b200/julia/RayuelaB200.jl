@@ -2,14 +2,23 @@
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The Python mirror
 # (rayuela_b200/julia_api.py) passes the library exactly the buffers these ccalls pass and is what the parity
-# tests drive.  Usage inside Rayuela.jl: `include("RayuelaB200.jl"); using .RayuelaB200` after src/Rayuela.jl's
-# own includes -- the methods below replace encoding_icm / encode_icm_cuda / linscan_* / quantize_pq / veccost
-# with the same positional signatures and return values (citations: file:line in the Rayuela.jl tree).
+# tests drive.  Usage:
+#     using Rayuela
+#     include("RayuelaB200.jl")
+#     RayuelaB200.install!(Rayuela)            # Rayuela's OWN functions now run on the GPU
+#     RayuelaB200.init_devices!(0:7)           # optional: one process drives 8 GPUs
+# install! defines, inside module Rayuela, methods of encoding_icm / encode_icm_cuda / veccost / qerror /
+# quantize_pq / quantize_opq / linscan_* / quantize_norms / quantize_chainq / update_codebooks_fast_bin with the
+# reference's own signatures that forward to this module, so train_lsq, train_lsq_cuda, train_sr_cuda,
+# experiment_lsq_cuda, experiment_sr_cuda (src/LSQ_GPU.jl:267-368, src/SR.jl:88-306) and
+# demos/demos_train_query_base.jl run UNMODIFIED on top of librayuela_b200.so.  The functions below can also be
+# called directly (same positional signatures and return values; citations: file:line in the Rayuela.jl tree).
 module RayuelaB200
 
 export encoding_icm, encode_icm_cuda, veccost, qerror, quantize_pq, quantize_opq,
        linscan_pq, linscan_opq, linscan_lsq, linscan_cq, seed_b200!,
-       quantize_norms, quantize_chainq, fast_bin_matmul, update_codebooks_fast_bin
+       quantize_norms, quantize_chainq, fast_bin_matmul, update_codebooks_fast_bin,
+       install!, init_devices!, shutdown_devices!
 
 using Printf, Statistics, LinearAlgebra
 
@@ -28,6 +37,19 @@ function check(rc::Cint)
   msg = unsafe_string(ccall((:rayuela_last_error, librayuela_b200), Cstring, ()))
   error("librayuela_b200 error $rc: $msg")
 end
+
+"""
+    init_devices!(devices)
+
+One Julia process, several GPUs (the reference hard-codes device 0, src/LSQ_GPU.jl:41,45, and splits the base in
+time with `nsplits`): after this call every encode splits the base over `devices` and every linscan shards it, with
+bit-identical results.  The environment variable RAYUELA_B200_DEVICES="0,1,..." does the same without code.
+"""
+function init_devices!(devices)
+  devs = convert(Vector{Cint}, collect(devices))
+  check(ccall((:rayuela_init, librayuela_b200), Cint, (Ptr{Cint}, Cint), devs, length(devs)))
+end
+shutdown_devices!() = check(ccall((:rayuela_shutdown, librayuela_b200), Cint, ()))
 
 codes0(B::Matrix{<:Integer}) = convert(Matrix{UInt8}, B .- one(eltype(B)))   # src/LSQ.jl:228
 codes1(B::Matrix{UInt8})     = convert(Matrix{Int16}, B) .+ one(Int16)        # src/LSQ.jl:232
@@ -174,6 +196,50 @@ function update_codebooks_fast_bin(X::Matrix{Float32}, B::Matrix{Int16}, h::Inte
   Cm  = convert(Matrix{Float32}, LAPACK.getrs!('N', lpt[1], lpt[2], b))       # (m*h)-by-d
   Ct  = collect(Cm')                                                          # d-by-(m*h)
   return [Ct[:, (i-1)*h+1:i*h] for i = 1:m]                                   # K2vec, src/utils.jl
+end
+
+# --- make Rayuela's own functions call the GPU ------------------------------------------------------------------
+"""
+    install!(mod)          # mod = Rayuela
+
+Defines in `mod` methods with the reference's signatures (same or more specific: Float32 data) that forward to this
+module.  Julia dispatches `Rayuela.train_lsq_cuda`'s internal call of `encode_icm_cuda(...)` etc. to them, so the
+trainers and experiment_* drivers need no source change.  `nsplits` arguments are accepted and ignored.
+"""
+function install!(mod::Module)
+  G = @__MODULE__
+  Core.eval(mod, quote
+    # path (1)   src/LSQ.jl:272-281, src/LSQ_GPU.jl:218-227, src/qerrors.jl:36-39,69-72
+    encoding_icm(X::Matrix{Float32}, oldB::Matrix{Int16}, C::Vector{Matrix{Float32}}, ilsiter::Integer,
+                 icmiter::Integer, randord::Bool, npert::Integer, cpp::Bool=true, V::Bool=true) =
+      $G.encoding_icm(X, oldB, C, ilsiter, icmiter, randord, npert, cpp, V)
+    encode_icm_cuda(RX::Matrix{Float32}, B::Matrix{Int16}, C::Vector{Matrix{Float32}}, ilsiters::Vector{Int64},
+                    icmiter::Integer, npert::Integer, randord::Bool, nsplits::Integer=2, V::Bool=false) =
+      $G.encode_icm_cuda(RX, B, C, ilsiters, icmiter, npert, randord, nsplits, V)
+    veccost(X::Matrix{Float32}, B::Matrix{T2}, C::Vector{Matrix{Float32}}) where {T2 <: Integer} = $G.veccost(X, B, C)
+    qerror(X::Matrix{Float32}, B::Matrix{T2}, C::Vector{Matrix{Float32}}) where {T2 <: Integer} = $G.qerror(X, B, C)
+    # PQ / OPQ encode   src/PQ.jl:18-21, src/OPQ.jl:19-23
+    quantize_pq(X::Matrix{Float32}, C::Vector{Matrix{Float32}}, V::Bool=false) = $G.quantize_pq(X, C, V)
+    quantize_opq(X::Matrix{Float32}, R::Matrix{Float32}, C::Vector{Matrix{Float32}}, V::Bool=false) =
+      $G.quantize_opq(X, R, C, V)
+    # path (2)   src/Linscan.jl:5-10,93-99,118-124,160-164 (the Integer-code methods :28-37 etc. call these)
+    linscan_pq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, b::Int, k::Int=10000) =
+      $G.linscan_pq(B, X, C, b, k)
+    linscan_opq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, b::Int, R::Matrix{Cfloat},
+                k::Int=10000) = $G.linscan_opq(B, X, C, b, R, k)
+    linscan_lsq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, dbnorms::Vector{Cfloat},
+                R::Matrix{Cfloat}, k::Int=10000) = $G.linscan_lsq(B, X, C, dbnorms, R, k)
+    linscan_cq(B::Matrix{UInt8}, X::Matrix{Cfloat}, C::Vector{Matrix{Cfloat}}, k::Int=10000) =
+      $G.linscan_cq(B, X, C, k)
+    # "next" rows   src/utils.jl:29-32, src/ChainQ.jl:305-309, src/codebook_update.jl:175-180
+    quantize_norms(B::Matrix{T1}, C::Vector{Matrix{Float32}}, cbnorms::Vector{Float32}) where {T1 <: Integer} =
+      $G.quantize_norms(B, C, cbnorms)
+    quantize_chainq(X::Matrix{Float32}, C::Vector{Matrix{Float32}}, use_cuda::Bool=false, use_cpp::Bool=false) =
+      $G.quantize_chainq(X, C, use_cuda, use_cpp)
+    update_codebooks_fast_bin(X::Matrix{Float32}, B::Matrix{Int16}, h::Integer, V::Bool=false, rho::Float64=1e-4) =
+      $G.update_codebooks_fast_bin(X, B, h, V, rho)
+  end)
+  return nothing
 end
 
 end # module

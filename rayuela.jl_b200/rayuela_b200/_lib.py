@@ -21,6 +21,9 @@ SIGNATURES = {
     "rayuela_last_error": (ct.c_char_p, []),
     "rayuela_set_device": (_int, [_int]),
     "rayuela_launch_count": (ct.c_uint64, []),
+    "rayuela_init": (_int, [_vp, _int]),
+    "rayuela_shutdown": (_int, []),
+    "rayuela_device_count": (_int, []),
     "rayuela_encode_icm": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _int, ct.c_uint64, _i64,
                                   _vp, _vp, _int, _vp, _vp, _vp, _vp, ct.c_uint, _vp]),
     "rayuela_encode_icm_steps": (_int, [_vp, _vp]),
@@ -73,3 +76,20 @@ def check(rc):
 
 def launch_count():
     return int(lib().rayuela_launch_count())
+
+
+def init(devices=None):
+    """rayuela_init: configure the device set used by HOST-array calls (encode_icm splits the base over the
+    devices, Index becomes base-sharded).  devices=None or a single device -> single-device mode.  A device may be
+    listed more than once (two shards on one GPU)."""
+    devs = list(devices or [])
+    arr = (ct.c_int * max(len(devs), 1))(*devs)
+    check(lib().rayuela_init(ct.cast(arr, ct.c_void_p), len(devs)))
+
+
+def shutdown():
+    check(lib().rayuela_shutdown())
+
+
+def device_count():
+    return int(lib().rayuela_device_count())

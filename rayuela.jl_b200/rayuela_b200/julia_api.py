@@ -326,6 +326,56 @@ def train_sr_cuda(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, met
     return C, B, objarray
 
 
+def _rand_codes(h, m, n):
+    """convert(Matrix{Int16}, rand(1:h, m, n)) (src/LSQ_GPU.jl:351) from the seeded stream."""
+    rng = np.random.default_rng(_next_seed() & 0xFFFFFFFF)
+    return np.asfortranarray(rng.integers(1, h + 1, (m, n)).astype(np.int16))
+
+
+def _encode_base_and_query(C, B, R, train_error, Xb, Xq, gt, m, h, ilsiter, icmiter, randord, npert, knn,
+                           nsplits_base, V):
+    """Shared tail of experiment_lsq_cuda / experiment_sr_cuda (src/LSQ_GPU.jl:347-367, src/SR.jl:280-305)."""
+    Xb = np.asarray(Xb, dtype=np.float32)
+    Xq = np.asarray(Xq, dtype=np.float32)
+    d = Xb.shape[0]
+    norms_B, norms_C = get_norms_codebook(B, C)                                                    # :347 / :280
+    B_base = _rand_codes(h, m, Xb.shape[1])                                                        # :351 / :283
+    Bs_base, _ = encode_icm_cuda(Xb, B_base, C, [ilsiter * 4], icmiter, npert, randord, nsplits_base, V)
+    B_base = Bs_base[-1]
+    base_error = qerror(Xb, B_base, C)
+    if V:
+        print("Error in base is %e" % base_error)
+    B_base_norms, db_norms_X = quantize_norms(B_base, C, norms_C)                                 # :358 / :295
+    db_norms = np.asarray(norms_C, dtype=np.float32)[np.asarray(B_base_norms, dtype=np.int64) - 1]  # vec(norms_C[...])
+    dists, idx = linscan_lsq(B_base, Xq, C, db_norms, np.eye(d, dtype=np.float32), knn)           # :362 / :300
+    recall = eval_recall(gt, idx, knn, V)
+    return C, B, R, train_error, B_base, recall
+
+
+def experiment_lsq_cuda(Xt, B, C, R, Xb, Xq, gt, m, h, niter=25, ilsiter=8, icmiter=4, randord=True, npert=4,
+                        knn=1000, nsplits_train=1, nsplits_base=1, V=False):
+    """experiment_lsq_cuda(Xt, B, C, R, Xb, Xq, gt, m, h, niter=25, ilsiter=8, icmiter=4, randord=true, npert=4,
+    knn=1000, nsplits_train=1, nsplits_base=1, V=false) -> C, B, R, train_error, B_base, recall
+    (src/LSQ_GPU.jl:322-368): train on Xt, encode the base from random codes with 4*ilsiter ILS iterations,
+    quantize the database norms, linscan_lsq, eval_recall."""
+    C, B, train_error = train_lsq_cuda(Xt, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, nsplits_train, V)
+    return _encode_base_and_query(C, B, R, train_error, Xb, Xq, gt, m, h, ilsiter, icmiter, randord, npert, knn,
+                                  nsplits_base, V)
+
+
+def experiment_sr_cuda(Xt, B, C, R, Xb, Xq, gt, m, h, niter=25, ilsiter=8, icmiter=4, randord=True, npert=4,
+                       knn=1000, nsplits_train=1, nsplits_base=1, sr_method="SR_D", schedule=1, p=0.5, V=False):
+    """experiment_sr_cuda(..., sr_method="SR_D", schedule=1, p=0.5, V=false) -> C, B, R, train_error, B_base, recall
+    (src/SR.jl:247-306): the LSQ++ experiment the demos run for SR-D and SR-C."""
+    if V:
+        print("\nRunning LSQ++ (%s) with %d codebooks, %d perturbations, %d icm iterations and random order = %s"
+              % (sr_method, m, npert, icmiter, randord))
+    C, B, train_error = train_sr_cuda(Xt, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, sr_method,
+                                      schedule, p, nsplits_train, V)
+    return _encode_base_and_query(C, B, R, train_error, Xb, Xq, gt, m, h, ilsiter, icmiter, randord, npert, knn,
+                                  nsplits_base, V)
+
+
 # ---- norm quantization ("next" row 2): produces the dbnorms linscan_lsq consumes ------------------------------
 def kmeans_1d(x, k, rng, maxiter=100):
     """1-D k-means (k-means++ seeding, Lloyd) -- the role Clustering.kmeans(dbnorms, h) plays at

@@ -205,3 +205,51 @@ def test_viterbi_matches_reference_bitwise(m):
                 alt = a[l].copy()
                 alt[i] = c
                 assert energy(alt, l) >= base - 1e-2
+
+
+# ---- the unpinned half: how far can the reference's (unknowable) BLAS summation order move the result? ----------
+# Julia is not installed, so the association order of OpenBLAS sgemm inside get_unaries / get_binaries
+# (src/utils.jl:135-136,164) cannot be reproduced; the oracle pins ONE order (sequential fmaf chains).  SURVEY 7:
+# the same encode driven by BLAS-order unaries and tables (numpy float32 sgemm -- a different, blocked order) must
+# give a code-mismatch rate far below 1e-3 and the same qerror within 1e-6 relative.
+def test_blas_order_vs_fixed_order_statistics():
+    orc.build()
+    n, d, m = 100_000, 128, 8
+    r = np.random.default_rng(2024)
+    centres = r.standard_normal((512, d)).astype(np.float32)
+    X = (centres[r.integers(0, 512, n)] + 0.5 * r.standard_normal((n, d))).astype(np.float32)
+    C = (r.standard_normal((m * 256, d)) / np.sqrt(m)).astype(np.float32)
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    U0, U1 = orc.get_unaries(X[:4096], C, m), orc.blas_unaries(X[:4096], C, m)
+    assert not np.array_equal(U0, U1), "the two orders coincide: the test would prove nothing"
+    assert np.abs(U0 - U1).max() < 1e-3 * np.abs(U0).max()
+    fixed = orc.encode_icm(X, C, B, 4, 4, 4, True, seed=5, use_ref_step=orc.have_ref())
+    blas = orc.encode_icm(X, C, B, 4, 4, 4, True, seed=5, use_ref_step=orc.have_ref(), blas=True)
+    mismatch = float((fixed["B"] != blas["B"]).any(axis=1).mean())
+    qf, qb = orc.qerror(X, fixed["B"], C), orc.qerror(X, blas["B"], C)
+    print("BLAS-order vs fixed-order: vector mismatch rate %.2e, qerror %.8g vs %.8g" % (mismatch, qf, qb))
+    assert mismatch < 2e-4                     # measured: 0 .. 3e-5 (a flipped near-tie cascades through the ILS)
+    assert abs(qf - qb) <= 1e-6 * qf
+
+
+def test_quantize_pq_vs_float64_argmin_bound():
+    """quantize_pq is parity-unpinned (Distances.jl / Clustering.jl are not vendored).  Bound on what any fp32 order
+    can change: against an exact float64 argmin the restated fp32 formula differs on < 2e-3 of the codes, and every
+    differing code is a near-tie (relative distance gap < 1e-5)."""
+    orc.build()
+    n, m, sub = 50_000, 8, 16
+    r = np.random.default_rng(3)
+    X = r.standard_normal((n, m * sub)).astype(np.float32)
+    Cpq = r.standard_normal((m * 256, sub)).astype(np.float32)
+    B = orc.quantize_pq(X, Cpq, m)
+    bad = 0
+    for j in range(m):
+        xs = X[:, j * sub:(j + 1) * sub].astype(np.float64)
+        cs = Cpq[j * 256:(j + 1) * 256].astype(np.float64)
+        d2 = (xs ** 2).sum(1)[:, None] + (cs ** 2).sum(1)[None, :] - 2 * xs @ cs.T
+        ref = d2.argmin(1)
+        diff = np.nonzero(ref != B[:, j])[0]
+        bad += diff.size
+        gap = d2[diff, B[diff, j]] - d2[diff, ref[diff]]
+        assert np.all(gap <= 1e-5 * np.maximum(d2[diff, ref[diff]], 1e-30))
+    assert bad < 2e-3 * n * m
