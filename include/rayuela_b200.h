@@ -22,7 +22,7 @@ extern "C" {
 
 /* ---- status ------------------------------------------------------------------------------------- */
 #define RAYUELA_OK 0
-#define RAYUELA_ERR_ARG (-1)   /* bad shape / unsupported parameter (e.g. h != 256, src/LSQ.jl:173-175) */
+#define RAYUELA_ERR_ARG (-1)   /* bad shape / unsupported parameter (e.g. h > 256: codes are bytes here) */
 #define RAYUELA_ERR_CUDA (-2)  /* CUDA runtime error (incl. no device) */
 #define RAYUELA_ERR_OOM (-3)
 
@@ -70,6 +70,9 @@ int rayuela_device_count(void); /* slots of the configured set (1 in single-devi
  *   cost_out   n floats or NULL: final veccost per vector
  *   stats      2*ilsiter ints (host memory) or NULL: (#equal, #better) per ILS iteration, the figures
  *              the reference prints at src/LSQ.jl:243-245
+ *   h          256 takes the tuned kernels (the reference's cpp=true path, src/LSQ.jl:42-80, is 256-only, :173-175);
+ *              1..255 takes plain exact kernels with the same arithmetic contract -- the reference's cpp=false path
+ *              iterated_conditional_modes! (src/LSQ.jl:83-149), which works for any h (single device, C is d-by-(m*h))
  */
 int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h,
                        int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,

@@ -173,6 +173,27 @@ void orc_condition(unsigned char* B, float* ub, float* binaries, float* binaries
   }
 }
 
+/* The conditioning loop of iterated_conditional_modes! (src/LSQ.jl:99-142), the pure-Julia twin of `condition` that
+ * the reference runs with cpp=false (e.g. experiment_lsq, src/LSQ.jl:431) and that works for ANY h: same absorb order
+ * (k ascending as listed in to_condition), same first-minimum scan. */
+void orc_condition_h(unsigned char* B, float* ub, float* binaries, float* binaries_t,
+                     int* cbpair2binaryidx, int* to_condition, int j, int n, int m, int h) {
+#pragma omp parallel for schedule(static)
+  for (int l = 0; l < n; l++) {
+    float* u = ub + (size_t)l * h;
+    for (int kidx = 0; kidx < m - 1; kidx++) {
+      int k = to_condition[kidx];
+      int bidx = cbpair2binaryidx[j * m + k];
+      const float* bb = (j < k ? binaries : binaries_t) + (size_t)h * h * bidx;
+      const float* row = bb + (size_t)B[(size_t)l * m + k] * h;
+      for (int ll = 0; ll < h; ll++) u[ll] += row[ll];
+    }
+    float minv = u[0]; int mini = 0;
+    for (int k = 1; k < h; k++) { float v = u[k]; if (v < minv) { minv = v; mini = k; } }
+    B[(size_t)l * m + j] = (unsigned char)mini;
+  }
+}
+
 /* veccost (src/qerrors.jl:36-66): CB = sum_k C_k[:,b_k] accumulated k = 1..m from +0, then
  * cost = sum_t (CB[t]-x[t])^2.  The reference's @simd lets LLVM reassociate; fixed here to the
  * sequential, unfused order of the source text. */
@@ -225,8 +246,9 @@ int orc_encode_icm_fully_ex(const float* X, const float* C, uint8_t* B, int64_t 
                             const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
                             float* cost_out, int* stats,
                             const float* U_pre, const float* bin_pre, const float* bint_pre, double* phases) {
-  if (h != H256) return -1; /* src/LSQ.jl:173-175 */
-  if (!step) step = orc_condition;
+  if (h != H256 && step) return -1; /* the C++ step is 256-only, src/LSQ.jl:173-175; cpp=false takes any h */
+  if (h < 1 || h > 256) return -1;  /* codes are bytes below the boundary */
+  if (!step && h == H256) step = orc_condition;
   int ncbi = m * (m - 1) / 2;
   size_t hh = (size_t)h * h;
   float* U = U_pre ? (float*)U_pre : (float*)malloc(sizeof(float) * (size_t)m * n * h);
@@ -274,7 +296,8 @@ int orc_encode_icm_fully_ex(const float* X, const float* C, uint8_t* B, int64_t 
         int q = 0;
         for (int k = 0; k < m; k++) if (k != j) to_cond[q++] = k;  /* ascending, src/LSQ.jl:211-216 */
         memcpy(ub, U + (size_t)j * n * h, sizeof(float) * (size_t)n * h);  /* src/LSQ.jl:69 */
-        step(newB, ub, bin, bin_t, pair2idx, to_cond, j, (int)n, m);
+        if (step) step(newB, ub, bin, bin_t, pair2idx, to_cond, j, (int)n, m);
+        else orc_condition_h(newB, ub, bin, bin_t, pair2idx, to_cond, j, (int)n, m, h);   /* src/LSQ.jl:83-149 */
       }
     ph[2] += omp_get_wtime() - t0; t0 = omp_get_wtime();
     orc_veccost(X, newB, C, n, d, m, h, newcost);            /* src/LSQ.jl:237 */

@@ -241,6 +241,18 @@ struct Code {
   }
 };
 
+// M <= 8: the codes live in `lo` alone, so the k < 8 selects disappear from the per-step code path
+template <int M>
+__device__ __forceinline__ uint32_t code_get(const Code& c, int k) {
+  if (M <= 8) return (uint32_t)(c.lo >> (8 * k)) & 0xFFu;
+  return c.get(k);
+}
+template <int M>
+__device__ __forceinline__ void code_set(Code& c, int k, uint32_t v) {
+  if (M <= 8) c.lo = (c.lo & ~(0xFFull << (8 * k))) | ((uint64_t)v << (8 * k));
+  else c.set(k, v);
+}
+
 template <int M>
 __device__ __forceinline__ Code load_code(const uint8_t* b) {
   Code c{0, 0};
@@ -321,6 +333,8 @@ struct IcmParams {
   uint8_t* B;           // [nc][m] in/out
   float* cost;          // [nc] or null
   const int* orders;    // [ilsiter][m]
+  const unsigned long long* orders_packed;  // [ilsiter]: the m visiting-order entries of an iteration, 4 bits each
+  uint32_t one;         // == 1, opaque to the compiler (see pf_rows)
   const int* snap_iters;  // [n_snap] (1-based ILS iteration counts)
   uint8_t* B_snap;      // [n_snap][n_total][m], already offset to this chunk's first vector
   int* stats;           // [ilsiter][2] (#equal, #better)
@@ -338,15 +352,19 @@ struct IcmParams {
 // for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
 // The (M-1) quantised rows of one step with the conditioned codebook J as a LITERAL: no per-row predicate, no
 // predicated-off row.  sl = sum lo + (sum hi << 16) (mod 2^32), sh = sum hi.
+// The step is bound by the integer ALU pipe (IADD3 / LEA / LOP3 / SHF / ISETP issue at one warp-instruction per two
+// clocks; ncu: ~137 of a step's ~241 instructions, 76 % pipe utilisation), while the FMA pipe idles.  `one` is a kernel
+// parameter equal to 1 that the compiler cannot fold, so x * one + s is emitted as IMAD (FMA pipe) instead of IADD3.
 template <int M, int J>
-__device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_t (&sl)[4], uint32_t (&sh)[4]) {
+__device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_t (&sl)[4], uint32_t (&sh)[4],
+                                        const uint32_t one) {
 #pragma unroll
   for (int k = 0; k < M; k++) {
     if (k != J) {
       const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
       const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
       const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
-      sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
+      sl[0] = x.x * one + sl[0]; sl[1] = x.y * one + sl[1]; sl[2] = x.z * one + sl[2]; sl[3] = x.w * one + sl[3];
       sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
     }
   }
@@ -371,6 +389,7 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   __syncthreads();
 
   unsigned long long nsteps = 0, nexact = 0;
+  const uint32_t one = p.one;
   const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   // Dynamic schedule: a vector's time depends on how many of its steps the memoisation skips, so a fixed stride
   // leaves the slowest warp ~7 % behind the mean (1M vectors over 4736 warps); every warp draws its next vector
@@ -384,13 +403,14 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
     Code cur = load_code<M>(p.B + (size_t)l * M);
     float curcost = warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
     const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
+    uint32_t vsteps = 0, vexact = 0;                            // this vector's step counters (32 bit in the hot loop)
     float slack = 0.f;                                          // 2.002 * 2^-20 * umax (PF)
     if (PF) slack = __uint_as_float(__ldg(p.umax + l)) * (2.002f * 9.5367431640625e-07f);
 
     for (int it = 0; it < p.ilsiter; it++) {
       Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
       perturb<M>(nb, p.npert, p.seed, it, (uint64_t)(p.g0 + l));  // src/LSQ.jl:225
-      const int* order = p.orders + it * M;
+      const unsigned long long ordp = __ldg(p.orders_packed + it);   // the whole visiting order in a register
       // Memoised conditioning: the step for codebook j is a pure function of (U_j, codes of the others).
       // If none of the other codes changed since j was last evaluated in THIS iteration, its argmin is the
       // code it already holds, so the step is skipped -- bit-identical to running it (all icmiter sweeps
@@ -398,9 +418,9 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
       uint32_t dirty = (1u << M) - 1u;
       for (int sweep = 0; sweep < p.icmiter && dirty; sweep++) {
         for (int s = 0; s < M; s++) {
-          const int j = __ldg(order + s);
+          const int j = (M <= 8) ? (int)(((uint32_t)ordp >> (4 * s)) & 15u) : (int)((ordp >> (4 * s)) & 15ull);
           if (!((dirty >> j) & 1u)) continue;
-          nsteps++;
+          vsteps++;
           float4 a0, a1;
           if (M > 8) {
             a0 = ldg_f4_hint(Ul + j * 64 + lane, pol_keep);
@@ -420,14 +440,14 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
               asm volatile("" : "+l"(tqj));   // keep the base in a register pair: row address = one IMAD.WIDE
               if constexpr (M <= 8 && JSPEC) {                     // one copy of the row loop per j (jump table)
                 switch (j) {
-                  case 0: pf_rows<M, 0>(tqj, nb, sl, sh); break;
-                  case 1: pf_rows<M, 1>(tqj, nb, sl, sh); break;
-                  case 2: pf_rows<M, 2>(tqj, nb, sl, sh); break;
-                  case 3: pf_rows<M, 3>(tqj, nb, sl, sh); break;
-                  case 4: pf_rows<M, 4>(tqj, nb, sl, sh); break;
-                  case 5: pf_rows<M, 5>(tqj, nb, sl, sh); break;
-                  case 6: pf_rows<M, 6>(tqj, nb, sl, sh); break;
-                  default: pf_rows<M, 7>(tqj, nb, sl, sh); break;
+                  case 0: pf_rows<M, 0>(tqj, nb, sl, sh, one); break;
+                  case 1: pf_rows<M, 1>(tqj, nb, sl, sh, one); break;
+                  case 2: pf_rows<M, 2>(tqj, nb, sl, sh, one); break;
+                  case 3: pf_rows<M, 3>(tqj, nb, sl, sh, one); break;
+                  case 4: pf_rows<M, 4>(tqj, nb, sl, sh, one); break;
+                  case 5: pf_rows<M, 5>(tqj, nb, sl, sh, one); break;
+                  case 6: pf_rows<M, 6>(tqj, nb, sl, sh, one); break;
+                  default: pf_rows<M, 7>(tqj, nb, sl, sh, one); break;
                 }
               } else {
 #pragma unroll
@@ -466,12 +486,12 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
             }
           }
           if (bc < 0) {
-            if (PF) nexact++;
+            if (PF) vexact++;
 #pragma unroll
             for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j, encode_icm.cpp:28-45
               const int k = kk + (kk >= j);
               const float4* row =
-                  reinterpret_cast<const float4*>(p.T + (((size_t)j * M + k) * kH + nb.get(k)) * kH);
+                  reinterpret_cast<const float4*>(p.T + (((size_t)j * M + k) * kH + code_get<M>(nb, k)) * kH);
               float4 r0, r1;
               if (PF && M > 8) {
                 r0 = ldg_f4_hint(row + lane, pol_stream);
@@ -506,8 +526,8 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
                                                     // first, like the sequential scan of encode_icm.cpp:47-58)
           }
           dirty &= ~(1u << j);
-          if ((uint32_t)bc != nb.get(j)) {
-            nb.set(j, (uint32_t)bc);
+          if ((uint32_t)bc != code_get<M>(nb, j)) {
+            code_set<M>(nb, j, (uint32_t)bc);
             dirty |= ((1u << M) - 1u) & ~(1u << j);             // everyone conditioned on j must be redone
           }
         }
@@ -527,6 +547,8 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
     }
     if (lane < M) p.B[(size_t)l * M + lane] = (uint8_t)cur.get(lane);
     if (p.cost && lane == 0) p.cost[l] = curcost;
+    nsteps += vsteps;
+    nexact += vexact;
   }
   if (lane == 0 && nsteps) atomicAdd(p.steps, nsteps);
   if (lane == 0 && nexact) atomicAdd(p.steps + 1, nexact);
@@ -754,6 +776,171 @@ __global__ void __launch_bounds__(256) condition_kernel(uint8_t* __restrict__ B,
   }
 }
 
+// ---- any h <= 256: iterated_conditional_modes! (src/LSQ.jl:83-149), the pure-Julia path the reference takes with
+// cpp=false (experiment_lsq, src/LSQ.jl:431).  Same arithmetic contract as the 256-entry kernels (sequential fmaf
+// dots, ascending-k fp32 adds, first-minimum argmin), plain exact rows -- no quantised pre-filter, no tiling tricks:
+// codebooks with h != 256 are a compatibility path, not the benchmarked one.
+__global__ void __launch_bounds__(256) unary_generic_kernel(const float* __restrict__ C, const float* __restrict__ X,
+                                                            const float* __restrict__ nrm, float* __restrict__ U,
+                                                            int64_t n, int d, int mh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* xs = reinterpret_cast<float*>(smem_raw);
+  for (int64_t l = blockIdx.x; l < n; l += gridDim.x) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < d; t += blockDim.x) xs[t] = X[(size_t)l * d + t];
+    __syncthreads();
+    for (int e = threadIdx.x; e < mh; e += blockDim.x) {
+      const float* c = C + (size_t)e * d;
+      float s = 0.f;
+      for (int t = 0; t < d; t++) s = fmaf(c[t], xs[t], s);
+      U[(size_t)l * mh + e] = fmaf(-2.0f, s, nrm[e]);
+    }
+  }
+}
+
+// T[((j*m + k)*h + b)*h + c] = 2 <C_j[:,c], C_k[:,b]>
+__global__ void __launch_bounds__(256) tables_generic_kernel(const float* __restrict__ C, float* __restrict__ T, int d,
+                                                             int m, int h) {
+  const int64_t total = (int64_t)m * m * h * h;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % h), b = (int)((i / h) % h);
+    const int k = (int)((i / ((int64_t)h * h)) % m), j = (int)(i / ((int64_t)h * h * m));
+    if (j == k) continue;
+    const float* cj = C + ((size_t)j * h + c) * d;
+    const float* ck = C + ((size_t)k * h + b) * d;
+    float s = 0.f;
+    for (int t = 0; t < d; t++) s = fmaf(cj[t], ck[t], s);
+    T[i] = 2.0f * s;
+  }
+}
+
+__device__ __forceinline__ float warp_cost_generic(const float* __restrict__ x, const float* __restrict__ C,
+                                                   const Code& code, int d, int m, int h, float* sq, int lane) {
+  for (int t = lane; t < d; t += 32) {
+    float cb = 0.f;
+    for (int k = 0; k < m; k++) cb = __fadd_rn(cb, __ldg(C + ((size_t)k * h + code.get(k)) * d + t));
+    const float df = __fsub_rn(cb, __ldg(x + t));
+    sq[t] = __fmul_rn(df, df);
+  }
+  __syncwarp();
+  float acc = 0.f;
+  for (int t = 0; t < d; t++) acc = __fadd_rn(acc, sq[t]);
+  __syncwarp();
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) veccost_generic_kernel(const float* __restrict__ X, const uint8_t* __restrict__ B,
+                                                              const float* __restrict__ C, int64_t n, int d, int m,
+                                                              int h, float* __restrict__ cost) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((d + 3) & ~3);
+  for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < n; l += (int64_t)gridDim.x * nwarps) {
+    Code c{0, 0};
+    for (int k = 0; k < m; k++) c.set(k, B[(size_t)l * m + k]);
+    const float v = warp_cost_generic(X + (size_t)l * d, C, c, d, m, h, sq, lane);
+    if (lane == 0) cost[l] = v;
+  }
+}
+
+struct IcmGenericParams {
+  IcmParams p;      // U [nc][m][h], T [m][m][h][h]; Tq / pfc / umax unused
+  int m, h;
+};
+
+__global__ void __launch_bounds__(256) icm_generic_kernel(IcmGenericParams gp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const IcmParams& p = gp.p;
+  const int M = gp.m, h = gp.h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int dpad = (p.d + 3) & ~3;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * dpad;
+  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * dpad);
+  for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
+  __syncthreads();
+  const float inf = __int_as_float(0x7f800000);
+  unsigned long long nsteps = 0;
+  for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < p.nc; l += (int64_t)gridDim.x * nwarps) {
+    const float* x = p.X + (size_t)l * p.d;
+    Code cur{0, 0};
+    for (int k = 0; k < M; k++) cur.set(k, p.B[(size_t)l * M + k]);
+    float curcost = warp_cost_generic(x, p.C, cur, p.d, M, h, sq, lane);
+    const float* Ul = p.U + (size_t)l * M * h;
+    for (int it = 0; it < p.ilsiter; it++) {
+      Code nb = cur;
+      for (int jb = 0; jb * 4 < p.npert; jb++) {                          // perturb_codes!, src/LSQ.jl:5-39
+        const uint64_t g = (uint64_t)(p.g0 + l);
+        uint32_t pw[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)it, (uint32_t)jb};
+        uint32_t vw[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)it, 0x80000000u | (uint32_t)jb};
+        philox4x32_10(pw, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        philox4x32_10(vw, (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+          if (jb * 4 + t < p.npert) nb.set((int)mulhi32(pw[t], (uint32_t)M), mulhi32(vw[t], (uint32_t)h));
+      }
+      const int* order = p.orders + it * M;
+      uint32_t dirty = (1u << M) - 1u;
+      for (int sweep = 0; sweep < p.icmiter && dirty; sweep++) {
+        for (int s = 0; s < M; s++) {
+          const int j = __ldg(order + s);
+          if (!((dirty >> j) & 1u)) continue;
+          nsteps++;
+          float a[8];                                                     // lane owns c = lane + 32*i
+#pragma unroll
+          for (int i = 0; i < 8; i++) a[i] = (lane + 32 * i < h) ? __ldg(Ul + (size_t)j * h + lane + 32 * i) : inf;
+          for (int k = 0; k < M; k++) {                                   // ascending k != j, src/LSQ.jl:108-125
+            if (k == j) continue;
+            const float* row = p.T + (((size_t)j * M + k) * h + nb.get(k)) * h;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (lane + 32 * i < h) a[i] = __fadd_rn(a[i], __ldg(row + lane + 32 * i));
+          }
+          float bv = a[0];                                                // first minimum, src/LSQ.jl:128-142
+          int bc = lane;
+#pragma unroll
+          for (int i = 1; i < 8; i++)
+            if (a[i] < bv) { bv = a[i]; bc = lane + 32 * i; }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+            if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+          }
+          bc = __shfl_sync(0xffffffffu, bc, 0);
+          if (bc >= h) bc = 0;                                            // all sums NaN: the reference keeps index 1
+          dirty &= ~(1u << j);
+          if ((uint32_t)bc != nb.get(j)) {
+            nb.set(j, (uint32_t)bc);
+            dirty |= ((1u << M) - 1u) & ~(1u << j);
+          }
+        }
+      }
+      const float newcost = warp_cost_generic(x, p.C, nb, p.d, M, h, sq, lane);
+      if (lane == 0) {
+        if (newcost == curcost) atomicAdd(&stats_s[2 * it], 1);
+        if (newcost < curcost) atomicAdd(&stats_s[2 * it + 1], 1);
+      }
+      if (newcost < curcost) {
+        cur = nb;
+        curcost = newcost;
+      }
+      for (int sidx = 0; sidx < p.n_snap; sidx++)
+        if (__ldg(p.snap_iters + sidx) == it + 1 && lane < M)
+          p.B_snap[((size_t)sidx * p.n_total + l) * M + lane] = (uint8_t)cur.get(lane);
+    }
+    if (lane < M) p.B[(size_t)l * M + lane] = (uint8_t)cur.get(lane);
+    if (p.cost && lane == 0) p.cost[l] = curcost;
+  }
+  if (lane == 0 && nsteps) {
+    atomicAdd(p.steps, nsteps);
+    atomicAdd(p.steps + 1, nsteps);
+  }
+  __syncthreads();
+  if (p.stats)
+    for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x)
+      if (stats_s[i]) atomicAdd(p.stats + i, stats_s[i]);
+}
+
 }  // namespace ryl
 
 // ======================================================================================================
@@ -944,9 +1131,14 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     for (int i = 0; i < m; i++)
       RYL_ARG(ord[(size_t)it * m + i] >= 0 && ord[(size_t)it * m + i] < m, "encode_icm: order entry out of range");
   }
-  DevBuf ord_d, snapit_d, stats_d, nrm_d, T_d;
+  std::vector<unsigned long long> ordp((size_t)std::max(ilsiter, 1), 0ull);
+  for (int it = 0; it < ilsiter; it++)
+    for (int i = 0; i < m; i++) ordp[it] |= (unsigned long long)ord[(size_t)it * m + i] << (4 * i);
+  DevBuf ord_d, ordp_d, snapit_d, stats_d, nrm_d, T_d;
   RYL_TRY(ord_d.alloc(ord.size() * sizeof(int), s));
   RYL_CUDA(cudaMemcpyAsync(ord_d.p, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  RYL_TRY(ordp_d.alloc(ordp.size() * sizeof(unsigned long long), s));
+  RYL_CUDA(cudaMemcpyAsync(ordp_d.p, ordp.data(), ordp.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
   RYL_TRY(snapit_d.alloc((size_t)std::max(n_snap, 1) * sizeof(int), s));
   if (n_snap) RYL_CUDA(cudaMemcpyAsync(snapit_d.p, snap_iters, n_snap * sizeof(int), cudaMemcpyHostToDevice, s));
   RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int) + 16, s));   // + 16: executed / exact-path step counters
@@ -1021,6 +1213,8 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     p.B = b_io.d + (size_t)l0 * m;
     p.cost = cost_o.d ? cost_o.d + l0 : nullptr;
     p.orders = ord_d.as<int>();
+    p.orders_packed = ordp_d.as<unsigned long long>();
+    p.one = 1u;
     p.snap_iters = snapit_d.as<int>();
     p.B_snap = snap_out.d ? snap_out.d + (size_t)l0 * m : nullptr;
     p.stats = stats_d.as<int>();
@@ -1068,6 +1262,126 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     RYL_CUDA(cudaStreamSynchronize(s));
     g_icm_steps_done = done_steps[0];
     g_icm_steps_exact = pf ? done_steps[1] : done_steps[0];
+    g_icm_steps_total = (uint64_t)n * ilsiter * icmiter * m;
+  }
+  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  return RAYUELA_OK;
+}
+
+static int device_veccost_generic(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,
+                                  float* cost, cudaStream_t s) {
+  const int warps = 8;
+  const size_t smem = (size_t)warps * ((d + 3) & ~3) * sizeof(float);
+  RYL_ARG(smem <= 200 * 1024, "veccost: d too large for shared memory");
+  RYL_CUDA(cudaFuncSetAttribute(veccost_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>((n + warps - 1) / warps, (int64_t)sm_count() * 8);
+  RYL_LAUNCH(veccost_generic_kernel, grid, warps * 32, smem, s, X, B, C, n, d, m, h, cost);
+  return RAYUELA_OK;
+}
+
+// h != 256 (1..255): the reference's cpp=false path, iterated_conditional_modes! (src/LSQ.jl:83-149)
+static int encode_icm_generic(const float* X, const float* C, uint8_t* B, int64_t n, int d, int m, int h, int ilsiter,
+                              int icmiter, int npert, int randord, uint64_t seed, int64_t g0, const int* orders,
+                              const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs, float* cost_out,
+                              int* stats, unsigned flags, cudaStream_t s) {
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  const int mh = m * h;
+  InArg<float> x_in, c_in;
+  RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)mh * d, dev, s));
+  OutArg<uint8_t> b_io, snap_out;
+  RYL_TRY(b_io.bind(B, (size_t)n * m, dev, s, /*copy_in=*/true));
+  RYL_TRY(snap_out.bind(n_snap ? B_snap : nullptr, (size_t)n_snap * n * m, dev, s));
+  DevBuf snap_tmp;
+  if (n_snap && !snap_out.d && objs) {
+    RYL_TRY(snap_tmp.alloc((size_t)n_snap * n * m, s));
+    snap_out.d = snap_tmp.as<uint8_t>();
+  }
+  OutArg<float> cost_o;
+  RYL_TRY(cost_o.bind(cost_out, (size_t)n, dev, s));
+  std::vector<int> ord((size_t)std::max(ilsiter, 1) * m);
+  for (int it = 0; it < ilsiter; it++) {
+    if (orders) memcpy(&ord[(size_t)it * m], orders + (size_t)it * m, sizeof(int) * m);
+    else if (randord) philox_randperm(seed, it, m, &ord[(size_t)it * m]);
+    else for (int i = 0; i < m; i++) ord[(size_t)it * m + i] = i;
+    for (int i = 0; i < m; i++)
+      RYL_ARG(ord[(size_t)it * m + i] >= 0 && ord[(size_t)it * m + i] < m, "encode_icm: order entry out of range");
+  }
+  DevBuf ord_d, snapit_d, stats_d, nrm_d, T_d, U_d;
+  RYL_TRY(ord_d.alloc(ord.size() * sizeof(int), s));
+  RYL_CUDA(cudaMemcpyAsync(ord_d.p, ord.data(), ord.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  RYL_TRY(snapit_d.alloc((size_t)std::max(n_snap, 1) * sizeof(int), s));
+  if (n_snap) RYL_CUDA(cudaMemcpyAsync(snapit_d.p, snap_iters, n_snap * sizeof(int), cudaMemcpyHostToDevice, s));
+  RYL_TRY(stats_d.alloc((size_t)std::max(ilsiter, 1) * 2 * sizeof(int) + 16, s));
+  RYL_CUDA(cudaMemsetAsync(stats_d.p, 0, stats_d.bytes, s));
+  unsigned long long* steps_d = reinterpret_cast<unsigned long long*>(stats_d.as<int>() + (size_t)std::max(ilsiter, 1) * 2);
+  RYL_TRY(nrm_d.alloc((size_t)mh * sizeof(float), s));
+  RYL_LAUNCH(sqnorm_kernel, (mh + 255) / 256, 256, 0, s, c_in.d, d, mh, nrm_d.as<float>());
+  RYL_TRY(T_d.alloc((size_t)m * m * h * h * sizeof(float), s));
+  if (m > 1) RYL_LAUNCH(tables_generic_kernel, sm_count() * 8, 256, 0, s, c_in.d, T_d.as<float>(), d, m, h);
+  const int64_t per_vec = (int64_t)mh * sizeof(float);
+  const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(n, (int64_t)(unary_budget_bytes() / per_vec)));
+  RYL_TRY(U_d.alloc((size_t)std::min(chunk, n) * per_vec, s));
+  const int warps = 8;
+  const size_t smem = (size_t)warps * ((d + 3) & ~3) * sizeof(float) + (size_t)2 * ilsiter * sizeof(int);
+  RYL_ARG(smem <= 200 * 1024 && (size_t)d * sizeof(float) <= 200 * 1024, "encode_icm: d too large for shared memory");
+  RYL_CUDA(cudaFuncSetAttribute(icm_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RYL_CUDA(cudaFuncSetAttribute(unary_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d * sizeof(float))));
+  for (int64_t l0 = 0; l0 < n; l0 += chunk) {
+    const int64_t nc = std::min(chunk, n - l0);
+    RYL_LAUNCH(unary_generic_kernel, (int)std::min<int64_t>(nc, (int64_t)sm_count() * 8), 256, d * sizeof(float), s, c_in.d,
+               x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U_d.as<float>(), nc, d, mh);
+    IcmGenericParams gp;
+    IcmParams& p = gp.p;
+    p.U = U_d.as<float>();
+    p.T = T_d.as<float>();
+    p.Tq = nullptr;
+    p.pfc = nullptr;
+    p.umax = nullptr;
+    p.X = x_in.d + (size_t)l0 * d;
+    p.C = c_in.d;
+    p.B = b_io.d + (size_t)l0 * m;
+    p.cost = cost_o.d ? cost_o.d + l0 : nullptr;
+    p.orders = ord_d.as<int>();
+    p.snap_iters = snapit_d.as<int>();
+    p.B_snap = snap_out.d ? snap_out.d + (size_t)l0 * m : nullptr;
+    p.stats = stats_d.as<int>();
+    p.steps = steps_d;
+    p.next = nullptr;
+    p.nc = nc;
+    p.n_total = n;
+    p.g0 = g0 + l0;
+    p.seed = seed;
+    p.d = d;
+    p.ilsiter = ilsiter;
+    p.icmiter = icmiter;
+    p.npert = npert;
+    p.n_snap = snap_out.d ? n_snap : 0;
+    gp.m = m;
+    gp.h = h;
+    const int grid = (int)std::min<int64_t>((nc + warps - 1) / warps, (int64_t)sm_count() * 4);
+    RYL_LAUNCH(icm_generic_kernel, grid, warps * 32, smem, s, gp);
+  }
+  if (n_snap && objs && snap_out.d) {
+    DevBuf tmp;
+    RYL_TRY(tmp.alloc((size_t)n * sizeof(float), s));
+    for (int si = 0; si < n_snap; si++) {
+      RYL_TRY(device_veccost_generic(x_in.d, snap_out.d + (size_t)si * n * m, c_in.d, n, d, m, h, tmp.as<float>(), s));
+      double mean = 0;
+      RYL_TRY(device_mean(tmp.as<float>(), n, &mean, s));
+      objs[si] = (float)mean;
+    }
+  }
+  RYL_TRY(b_io.flush(s));
+  RYL_TRY(snap_out.flush(s));
+  RYL_TRY(cost_o.flush(s));
+  if (stats) {
+    unsigned long long done_steps[2] = {0, 0};
+    RYL_CUDA(cudaMemcpyAsync(stats, stats_d.p, (size_t)ilsiter * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaMemcpyAsync(done_steps, steps_d, sizeof(done_steps), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaStreamSynchronize(s));
+    g_icm_steps_done = done_steps[0];
+    g_icm_steps_exact = done_steps[1];
     g_icm_steps_total = (uint64_t)n * ilsiter * icmiter * m;
   }
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
@@ -1133,13 +1447,16 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
                                   int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
                                   const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap,
                                   float* objs, float* cost_out, int* stats, unsigned flags, void* stream) {
-  RYL_ARG(h == kH, "encode_icm: only codebooks with 256 entries are supported (src/LSQ.jl:173-175)");
+  RYL_ARG(h >= 1 && h <= kH, "encode_icm: h must be in 1..256 (codes are bytes below the boundary)");
   RYL_ARG(m >= 1 && m <= 16, "encode_icm: m must be in 1..16");
   RYL_ARG(n >= 0 && d >= 1, "encode_icm: bad n or d");
   RYL_ARG(ilsiter >= 0 && icmiter >= 0 && npert >= 0, "encode_icm: negative iteration count");
   RYL_ARG(n_snap >= 0 && (n_snap == 0 || snap_iters), "encode_icm: snap_iters missing");
   RYL_ARG(X && C && B, "encode_icm: null array");
   if (n == 0) return RAYUELA_OK;
+  if (h != kH)   // the reference's cpp=false path (src/LSQ.jl:83-149): any h, plain exact kernels, one device
+    return encode_icm_generic(X, C, B, n, d, m, h, ilsiter, icmiter, npert, randord, seed, g0, orders, snap_iters, n_snap,
+                              B_snap, objs, cost_out, stats, flags, (cudaStream_t)stream);
   if (!(flags & RAYUELA_DEVICE_PTRS)) {
     const std::vector<DeviceSlot> slots = device_slots();
     if (slots.size() > 1 && n >= (int64_t)slots.size() * 1024)
@@ -1153,12 +1470,12 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
 extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,
                                float* cost, double* mean_out, unsigned flags, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  RYL_ARG(h == kH && m >= 1 && m <= 16 && n >= 1 && d >= 1, "veccost: bad shape (h must be 256, m in 1..16)");
+  RYL_ARG(h >= 1 && h <= kH && m >= 1 && m <= 16 && n >= 1 && d >= 1, "veccost: bad shape (h in 1..256, m in 1..16)");
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
   InArg<float> x_in, c_in;
   InArg<uint8_t> b_in;
   RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
-  RYL_TRY(c_in.bind(C, (size_t)m * kH * d, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)m * h * d, dev, s));
   RYL_TRY(b_in.bind(B, (size_t)n * m, dev, s));
   OutArg<float> cost_o;
   DevBuf tmp;
@@ -1170,7 +1487,8 @@ extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C,
     RYL_TRY(tmp.alloc((size_t)n * sizeof(float), s));
     cd = tmp.as<float>();
   }
-  RYL_TRY(device_veccost(x_in.d, b_in.d, c_in.d, n, d, m, cd, s));
+  if (h == kH) RYL_TRY(device_veccost(x_in.d, b_in.d, c_in.d, n, d, m, cd, s));
+  else RYL_TRY(device_veccost_generic(x_in.d, b_in.d, c_in.d, n, d, m, h, cd, s));
   if (mean_out) RYL_TRY(device_mean(cd, n, mean_out, s));
   RYL_TRY(cost_o.flush(s));
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));

@@ -60,7 +60,7 @@ function encoding_icm(X::Matrix{Float32}, oldB::Matrix{Int16}, C::Vector{Matrix{
                       ilsiter::Integer, icmiter::Integer, randord::Bool, npert::Integer,
                       cpp::Bool=true, V::Bool=true)
   d, n = size(X); m = length(C); _, h = size(C[1])
-  h == 256 || error("The B200 implementation of ICM encoding only supports codebooks with 256 entries")
+  h <= 256 || error("The B200 implementation of ICM encoding stores codes in one byte: h must be <= 256")
   B     = codes0(oldB)
   stats = zeros(Cint, 2, max(ilsiter, 1))
   check(ccall((:rayuela_encode_icm, librayuela_b200), Cint,

@@ -101,15 +101,16 @@ def _i32(a):
 
 
 def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=None, snap_iters=None,
-               want_cost=False, want_stats=False, inplace=False):
-    """encode_icm_fully! (src/LSQ.jl:152-252) on the GPU.  Returns dict(B, cost, stats, B_snap, objs)."""
+               want_cost=False, want_stats=False, inplace=False, h=H):
+    """encode_icm_fully! (src/LSQ.jl:152-252) on the GPU.  Returns dict(B, cost, stats, B_snap, objs).
+    h = 256: the tuned kernels; h < 256: the reference's any-h path (iterated_conditional_modes!, src/LSQ.jl:83-149)."""
     L = _lib.lib()
     dev = _is_dev(X)
     n, d = X.shape
     m = B.shape[1]
     a = _Args()
     xp = a.inp(X, np.float32, (n, d))
-    cp = a.inp(C, np.float32, (m * H, d))
+    cp = a.inp(C, np.float32, (m * h, d))
     if not inplace:
         B = B.clone() if _is_dev(B) else np.array(B, dtype=np.uint8, order="C", copy=True)
     bp = a.out(B, np.uint8, (n, m))
@@ -129,7 +130,7 @@ def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=N
     if want_cost:
         cost, costp = a.new(dev, np.float32, (n,), device=X.device if dev else None)
     stats = np.zeros((max(ilsiter, 1), 2), dtype=np.int32) if want_stats else None
-    check(L.rayuela_encode_icm(xp, cp, bp, n, d, m, H, ilsiter, icmiter, npert, int(bool(randord)), seed, g0, ordp,
+    check(L.rayuela_encode_icm(xp, cp, bp, n, d, m, h, ilsiter, icmiter, npert, int(bool(randord)), seed, g0, ordp,
                                snaps.ctypes.data if ns else None, ns, Bsp, objs.ctypes.data if ns else None, costp,
                                stats.ctypes.data if want_stats else None, a.flags, a.stream))
     return dict(B=B, cost=cost, stats=stats[:ilsiter] if want_stats else None, B_snap=Bs, objs=objs)
@@ -149,7 +150,7 @@ def last_icm_exact_steps():
     return int(a.value)
 
 
-def veccost(X, B, C, want_mean=False):
+def veccost(X, B, C, want_mean=False, h=H):
     """veccost / qerror (src/qerrors.jl:36-74)."""
     L = _lib.lib()
     n, d = X.shape
@@ -157,16 +158,16 @@ def veccost(X, B, C, want_mean=False):
     a = _Args()
     xp = a.inp(X, np.float32, (n, d))
     bp = a.inp(B, np.uint8, (n, m))
-    cp = a.inp(C, np.float32, (m * H, d))
+    cp = a.inp(C, np.float32, (m * h, d))
     cost, costp = a.new(_is_dev(X), np.float32, (n,), device=X.device if _is_dev(X) else None)
     mean = ct.c_double(0.0)
-    check(L.rayuela_veccost(xp, bp, cp, n, d, m, H, costp, ct.addressof(mean) if want_mean else None, a.flags,
+    check(L.rayuela_veccost(xp, bp, cp, n, d, m, h, costp, ct.addressof(mean) if want_mean else None, a.flags,
                             a.stream))
     return (cost, mean.value) if want_mean else cost
 
 
-def qerror(X, B, C):
-    return veccost(X, B, C, want_mean=True)[1]
+def qerror(X, B, C, h=H):
+    return veccost(X, B, C, want_mean=True, h=h)[1]
 
 
 def quantize_pq(X, Cpq, m):

@@ -58,10 +58,12 @@ def encoding_icm(X, oldB, C, ilsiter, icmiter, randord, npert, cpp=True, V=False
     d, n = np.shape(X)
     m = len(C)
     h = np.shape(C[0])[1]
-    if h != H:
-        raise RayuelaError("The B200 implementation of ICM encoding only supports codebooks with 256 entries")
+    if h > H:
+        raise RayuelaError("The B200 implementation of ICM encoding stores codes in one byte: h must be <= 256")
+    # h == 256 is the reference's cpp=true path (src/LSQ.jl:42-80, 256-only :173-175); other h its cpp=false path
+    # iterated_conditional_modes! (:83-149) -- same results either way, `cpp` only selects the implementation there
     r = core.encode_icm(_img(X), _hcat(C), _codes0(oldB), ilsiter, icmiter, npert, randord, seed=_next_seed(),
-                        want_stats=V, inplace=True)
+                        want_stats=V, inplace=True, h=h)
     if V:
         for it, (neq, nbet) in enumerate(r["stats"]):
             print(" ILS iteration %d/%d done. %5.2f%% new codes are equal. %5.2f%% new codes are better."
@@ -88,12 +90,12 @@ def encode_icm_cuda(RX, B, C, ilsiters, icmiter, npert, randord, nsplits=2, V=Fa
 
 def veccost(X, B, C):
     """veccost(X, B, C) (src/qerrors.jl:36-66)."""
-    return core.veccost(_img(X), _codes0(B), _hcat(C))
+    return core.veccost(_img(X), _codes0(B), _hcat(C), h=np.shape(C[0])[1])
 
 
 def qerror(X, B, C):
     """qerror(X, B, C) = mean(veccost(X, B, C)) (src/qerrors.jl:69-74)."""
-    return np.float32(core.qerror(_img(X), _codes0(B), _hcat(C)))
+    return np.float32(core.qerror(_img(X), _codes0(B), _hcat(C), h=np.shape(C[0])[1]))
 
 
 def _pq_as_full(C, d):

@@ -175,7 +175,36 @@ def test_run_demos_acceptance(rb):
         rec = out[name]["recall"]
         assert rec.shape == (100,) and np.all(np.diff(rec) >= 0)
         assert rec[-1] >= 0.6, (name, rec[-1])          # R@100 over a 10k base; measured 0.78 (LSQ, 7+1 bytes) .. 0.95
-    assert out["opq"]["train_error"] <= out["pq"]["train_error"] * 1.02
-    assert out["lsq"]["train_error"] < out["chainq"]["train_error"]          # training continues to improve the init
-    assert out["lsq"]["train_error"] < out["opq"]["train_error"]             # 7 additive codebooks beat 8 orthogonal
+    errs = {k: float(out[k]["train_error"]) for k in ("pq", "opq", "chainq", "lsq", "sr_d", "sr_c")}
+    print("train errors:", errs)
+    assert errs["opq"] <= errs["pq"] * 1.02, errs
+    assert errs["lsq"] < errs["chainq"], errs            # LSQ training continues to improve its ChainQ initialisation
+    assert errs["sr_d"] < errs["chainq"] and errs["sr_c"] < errs["chainq"], errs
     assert out["sr_d"]["B_base"].shape == (7, 10000)
+
+
+@pytest.mark.parametrize("h,m,d", [(16, 4, 24), (64, 8, 32), (100, 3, 17), (255, 2, 8)])
+def test_encoding_icm_any_h(rb, h, m, d):
+    """h != 256: the reference's cpp=false path iterated_conditional_modes! (src/LSQ.jl:83-149) -- codes, costs, stats,
+    snapshots bit-exact against its oracle restatement; through core and through the Julia-level encoding_icm."""
+    r = np.random.default_rng(h)
+    n = 1500
+    X = r.standard_normal((n, d)).astype(np.float32)
+    C = r.standard_normal((m * h, d)).astype(np.float32)
+    B = r.integers(0, h, (n, m), dtype=np.uint8)
+    want = orc.encode_icm(X, C, B, 3, 2, 3, True, seed=21, g0=5, h=h, snap_iters=[2])
+    got = rb.core.encode_icm(X, C, B, 3, 2, 3, True, seed=21, g0=5, h=h, snap_iters=[2], want_cost=True,
+                             want_stats=True)
+    assert np.array_equal(got["B"], want["B"]) and got["B"].max() < h
+    assert np.array_equal(bits(got["cost"]), bits(want["cost"]))
+    assert np.array_equal(got["stats"], want["stats"])
+    assert np.array_equal(got["B_snap"], want["B_snap"])
+    assert np.allclose(got["objs"], want["objs"], rtol=1e-4)
+    assert np.array_equal(bits(rb.core.veccost(X, B, C, h=h)), bits(orc.veccost(X, B, C, h)))
+    rb.seed_b200(21)
+    Cj = [_julia(C[j * h:(j + 1) * h]) for j in range(m)]
+    oldB = _julia(B).astype(np.int16) + 1
+    Bj = rb.encoding_icm(_julia(X), oldB, Cj, 3, 2, True, 3, False, False)
+    want0 = orc.encode_icm(X, C, B, 3, 2, 3, True, seed=21, g0=0, h=h)
+    assert np.array_equal(Bj.T - 1, want0["B"]) and np.array_equal(oldB, Bj)          # oldB mutated, src/LSQ.jl:248
+    assert abs(float(rb.qerror(_julia(X), Bj, Cj)) - orc.qerror(X, want0["B"], C, h)) < 1e-4 * orc.qerror(X, B, C, h)
