@@ -28,6 +28,12 @@ extern "C" {
 
 /* flags */
 #define RAYUELA_DEVICE_PTRS 1u /* all array arguments are device pointers on the current device */
+#define RAYUELA_FAST_UNARIES 2u /* rayuela_encode_icm / rayuela_get_unaries: OPT-IN tensor-core unaries.  The one dense
+                                 * contraction of the path, -2*C'X (CUBLAS sgemm in the reference, src/LSQ_GPU.jl:74), runs as
+                                 * a tcgen05 bf16x3 GEMM (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) instead of the exact
+                                 * fp32 kernel: unaries within 2^-15 * sum|x_t c_t| of the exact ones, so codes are no longer
+                                 * bit-identical to the oracle (near-ties may flip; qerror agrees to ~1e-5).  Needs d <= 128;
+                                 * otherwise, and by default, the exact kernel runs.  Also: RAYUELA_B200_FAST_UNARIES=1. */
 
 /* Last error message of the calling thread ("" if none). The reference has no error channel at all
  * (void symbols, deps/src/*.cpp extern blocks); Julia-side checks are error() strings. */
@@ -88,6 +94,13 @@ int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total);
  * quantised copy of the tables with a rigorous error window, and only steps with more than one candidate inside the
  * window (near-ties) re-read the fp32 rows -- the result is bit-identical either way. Measurement aid. */
 int rayuela_encode_icm_exact_steps(uint64_t* exact);
+
+/* Replaces get_unaries (src/utils.jl:121-149): U[l][j][c] = -2<C_j[:,c], x_l> + ||C_j[:,c]||^2, written vector-major
+ * as n-by-(m*h) (the reference keeps m separate h-by-n matrices; U[l*m*h + j*h + c] is its unaries[j][c, l]).  The
+ * encoder computes these internally; the entry point exists for callers that want the table (e.g. ChainQ-style
+ * encoders) and for validating the RAYUELA_FAST_UNARIES mode against the exact kernel. */
+int rayuela_get_unaries(const float* X, const float* C, int64_t n, int d, int m, int h, float* U, unsigned flags,
+                        void* stream);
 
 /* Replaces veccost (src/qerrors.jl:36-66).  mean_out (host double, may be NULL) receives qerror
  * (src/qerrors.jl:69-74). cost may be NULL when only the mean is wanted. */

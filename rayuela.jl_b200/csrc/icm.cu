@@ -322,6 +322,12 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4* ptr, uint64_t pol) {
   return v;
 }
 
+// unary_tc.cu: opt-in tcgen05 unaries
+bool unary_tc_supported(int d, int mh);
+int unary_tc_pack_codebooks(const float* C, int d, int mh, DevBuf* Cp, cudaStream_t s);
+int unary_tc_launch(const float* X, const DevBuf& Cp, const float* nrm, float* U, unsigned int* umax, int64_t nc, int d,
+                    int mh, cudaStream_t s);
+
 struct IcmParams {
   const float* U;       // [nc][m][256]  unaries of this chunk
   const float* T;       // [m][m][256][256]
@@ -1166,6 +1172,11 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     RYL_LAUNCH(pf_consts_kernel, 1, 32, 0, s, tmax_d.as<unsigned int>(), m, pfc_d.as<float2>());
   }
 
+  // opt-in tensor-core unaries (RAYUELA_FAST_UNARIES): codebooks are split / packed once per call
+  const char* fast_env = getenv("RAYUELA_B200_FAST_UNARIES");
+  const bool fast = ((flags & RAYUELA_FAST_UNARIES) || (fast_env && atoi(fast_env) != 0)) && unary_tc_supported(d, mh);
+  DevBuf Cp_d;
+  if (fast) RYL_TRY(unary_tc_pack_codebooks(c_in.d, d, mh, &Cp_d, s));
   const int nbuf = piped ? 2 : 1;
   DevBuf U_d[2], umax_d[2], next_d;
   RYL_TRY(next_d.alloc((size_t)nchunks * sizeof(unsigned long long), s));
@@ -1196,7 +1207,9 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     if (piped && !dev) RYL_CUDA(cudaStreamWaitEvent(cs, ev_up[c].e, 0));
     dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
     if (pf) RYL_CUDA(cudaMemsetAsync(umax, 0, (size_t)nc * sizeof(unsigned int), cs));
-    if (d % 4 == 0)
+    if (fast)
+      RYL_TRY(unary_tc_launch(x_in.d + (size_t)l0 * d, Cp_d, nrm_d.as<float>(), U, umax, nc, d, mh, cs));
+    else if (d % 4 == 0)
       RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
                  umax);
     else
@@ -1395,7 +1408,7 @@ static int encode_icm_generic(const float* X, const float* C, uint8_t* B, int64_
 static int encode_icm_multi(const std::vector<DeviceSlot>& slots, const float* X, const float* C, uint8_t* B, int64_t n,
                             int d, int m, int ilsiter, int icmiter, int npert, int randord, uint64_t seed, int64_t g0,
                             const int* orders, const int* snap_iters, int n_snap, uint8_t* B_snap, float* objs,
-                            float* cost_out, int* stats) {
+                            float* cost_out, int* stats, unsigned fast_flag) {
   const int D = (int)slots.size();
   std::vector<std::vector<uint8_t>> snaps(D);
   std::vector<std::vector<double>> sums(D, std::vector<double>((size_t)std::max(n_snap, 1), 0.0));
@@ -1410,7 +1423,7 @@ static int encode_icm_multi(const std::vector<DeviceSlot>& slots, const float* X
     RYL_TRY(encode_icm_single(X + (size_t)a * d, C, B + (size_t)a * m, ni, d, m, ilsiter, icmiter, npert, randord, seed,
                               g0 + a, orders, snap_iters, n_snap, (n_snap && B_snap) ? snaps[i].data() : nullptr, nullptr,
                               (n_snap && objs) ? sums[i].data() : nullptr, cost_out ? cost_out + a : nullptr,
-                              stats ? st[i].data() : nullptr, 0, slots[i].stream));
+                              stats ? st[i].data() : nullptr, fast_flag, slots[i].stream));
     if (stats) {
       done[i] = g_icm_steps_done;        // this worker thread's counters
       exact[i] = g_icm_steps_exact;
@@ -1461,10 +1474,45 @@ extern "C" int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, in
     const std::vector<DeviceSlot> slots = device_slots();
     if (slots.size() > 1 && n >= (int64_t)slots.size() * 1024)
       return encode_icm_multi(slots, X, C, B, n, d, m, ilsiter, icmiter, npert, randord, seed, g0, orders, snap_iters,
-                              n_snap, B_snap, objs, cost_out, stats);
+                              n_snap, B_snap, objs, cost_out, stats, flags & RAYUELA_FAST_UNARIES);
   }
   return encode_icm_single(X, C, B, n, d, m, ilsiter, icmiter, npert, randord, seed, g0, orders, snap_iters, n_snap,
                            B_snap, objs, nullptr, cost_out, stats, flags, (cudaStream_t)stream);
+}
+
+extern "C" int rayuela_get_unaries(const float* X, const float* C, int64_t n, int d, int m, int h, float* U,
+                                   unsigned flags, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  RYL_ARG(h == kH && m >= 1 && m <= 16 && n >= 1 && d >= 1, "get_unaries: bad shape (h must be 256, m in 1..16)");
+  RYL_ARG(X && C && U, "get_unaries: null array");
+  RYL_ARG(n <= (int64_t)65535 * 128, "get_unaries: at most 8388480 vectors per call");
+  const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  const int mh = m * kH;
+  InArg<float> x_in, c_in;
+  RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
+  RYL_TRY(c_in.bind(C, (size_t)mh * d, dev, s));
+  OutArg<float> u_out;
+  RYL_TRY(u_out.bind(U, (size_t)n * mh, dev, s));
+  DevBuf nrm_d, Cp_d;
+  RYL_TRY(nrm_d.alloc((size_t)mh * sizeof(float), s));
+  RYL_LAUNCH(sqnorm_kernel, (mh + 255) / 256, 256, 0, s, c_in.d, d, mh, nrm_d.as<float>());
+  const char* fast_env = getenv("RAYUELA_B200_FAST_UNARIES");
+  const bool fast = ((flags & RAYUELA_FAST_UNARIES) || (fast_env && atoi(fast_env) != 0)) && unary_tc_supported(d, mh);
+  if (fast) {
+    RYL_TRY(unary_tc_pack_codebooks(c_in.d, d, mh, &Cp_d, s));
+    RYL_TRY(unary_tc_launch(x_in.d, Cp_d, nrm_d.as<float>(), u_out.d, nullptr, n, d, mh, s));
+  } else {
+    dim3 ug(mh / 128, (unsigned)((n + 127) / 128));
+    if (d % 4 == 0)
+      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d, nrm_d.as<float>(), u_out.d, n, d, mh,
+                 (unsigned int*)nullptr);
+    else
+      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d, nrm_d.as<float>(), u_out.d, n, d, mh,
+                 (unsigned int*)nullptr);
+  }
+  RYL_TRY(u_out.flush(s));
+  if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
+  return RAYUELA_OK;
 }
 
 extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C, int64_t n, int d, int m, int h,

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "librayuela_b200.so")
 
 DEVICE_PTRS = 1
+FAST_UNARIES = 2
 SCAN_LSQ, SCAN_CQ, SCAN_PQ = 0, 1, 2
 
 _vp = ct.c_void_p
@@ -28,6 +29,7 @@ SIGNATURES = {
                                   _vp, _vp, _int, _vp, _vp, _vp, _vp, ct.c_uint, _vp]),
     "rayuela_encode_icm_steps": (_int, [_vp, _vp]),
     "rayuela_encode_icm_exact_steps": (_int, [_vp]),
+    "rayuela_get_unaries": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, ct.c_uint, _vp]),
     "rayuela_veccost": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, ct.c_uint, _vp]),
     "condition": (None, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int]),
     "linscan_aqd_query": (None, [_vp, _vp, _vp, _vp, _vp, _int, ct.c_uint, _int, _int, _int, _int, _int]),

@@ -11,7 +11,7 @@ import ctypes as ct
 import numpy as np
 
 from . import _lib
-from ._lib import DEVICE_PTRS, SCAN_CQ, SCAN_LSQ, SCAN_PQ, RayuelaError, check
+from ._lib import DEVICE_PTRS, FAST_UNARIES, SCAN_CQ, SCAN_LSQ, SCAN_PQ, RayuelaError, check
 
 H = 256
 
@@ -101,9 +101,10 @@ def _i32(a):
 
 
 def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=None, snap_iters=None,
-               want_cost=False, want_stats=False, inplace=False, h=H):
+               want_cost=False, want_stats=False, inplace=False, h=H, fast=False):
     """encode_icm_fully! (src/LSQ.jl:152-252) on the GPU.  Returns dict(B, cost, stats, B_snap, objs).
-    h = 256: the tuned kernels; h < 256: the reference's any-h path (iterated_conditional_modes!, src/LSQ.jl:83-149)."""
+    h = 256: the tuned kernels; h < 256: the reference's any-h path (iterated_conditional_modes!, src/LSQ.jl:83-149).
+    fast=True: opt-in tensor-core (tcgen05 bf16x3) unaries -- no longer bit-identical to the oracle."""
     L = _lib.lib()
     dev = _is_dev(X)
     n, d = X.shape
@@ -132,8 +133,21 @@ def encode_icm(X, C, B, ilsiter, icmiter, npert, randord, seed=0, g0=0, orders=N
     stats = np.zeros((max(ilsiter, 1), 2), dtype=np.int32) if want_stats else None
     check(L.rayuela_encode_icm(xp, cp, bp, n, d, m, h, ilsiter, icmiter, npert, int(bool(randord)), seed, g0, ordp,
                                snaps.ctypes.data if ns else None, ns, Bsp, objs.ctypes.data if ns else None, costp,
-                               stats.ctypes.data if want_stats else None, a.flags, a.stream))
+                               stats.ctypes.data if want_stats else None, a.flags | (FAST_UNARIES if fast else 0),
+                               a.stream))
     return dict(B=B, cost=cost, stats=stats[:ilsiter] if want_stats else None, B_snap=Bs, objs=objs)
+
+
+def get_unaries(X, C, m, fast=False):
+    """get_unaries (src/utils.jl:121-149) on the GPU: U (n, m*256) with U[l, j*256 + c] = unaries[j][c, l]."""
+    L = _lib.lib()
+    n, d = X.shape
+    a = _Args()
+    xp = a.inp(X, np.float32, (n, d))
+    cp = a.inp(C, np.float32, (m * H, d))
+    U, up = a.new(_is_dev(X), np.float32, (n, m * H), device=X.device if _is_dev(X) else None)
+    check(L.rayuela_get_unaries(xp, cp, n, d, m, H, up, a.flags | (FAST_UNARIES if fast else 0), a.stream))
+    return U
 
 
 def last_icm_steps():

@@ -1,0 +1,56 @@
+"""The OPT-IN tensor-core mode (RAYUELA_FAST_UNARIES: tcgen05 bf16x3 GEMM for the unaries).  It is validated by
+tolerance and by encode-quality statistics, never by bit identity; the default (exact) kernel is checked bit-for-bit
+against the oracle in the same test so the two are never confused."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rb():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import rayuela_b200
+    return rayuela_b200
+
+
+def _data(n, d, m, seed):
+    r = np.random.default_rng(seed)
+    centres = r.standard_normal((64, d)).astype(np.float32) * 3
+    X = (centres[r.integers(0, 64, n)] + r.standard_normal((n, d))).astype(np.float32)
+    C = (r.standard_normal((m * 256, d)) * 1.5).astype(np.float32)
+    return X, C, r.integers(0, 256, (n, m), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("n,d,m", [(1000, 128, 8), (333, 64, 7), (129, 100, 16), (128, 8, 1), (5000, 128, 2)])
+def test_unaries_exact_and_fast(rb, n, d, m):
+    X, C, _ = _data(n, d, m, seed=n + d)
+    want = orc.get_unaries(X, C, m)                                     # (m, n, 256)
+    want = np.ascontiguousarray(want.transpose(1, 0, 2)).reshape(n, m * 256)
+    exact = rb.core.get_unaries(X, C, m)
+    assert np.array_equal(exact.view(np.uint32), want.view(np.uint32))  # exact kernel: bit-identical to the oracle
+    fast = rb.core.get_unaries(X, C, m, fast=True)
+    # bf16x3: every product within 2^-16 relative (the dropped lo*lo term and the rounding of lo), fp32 accumulation
+    bound = 2.0 ** -15 * (np.abs(X) @ np.abs(C).T) * 2 + 1e-6 * np.abs(want)
+    err = np.abs(fast.astype(np.float64) - want.astype(np.float64))
+    assert np.all(err <= bound), float((err / np.maximum(bound, 1e-30)).max())
+    assert not np.array_equal(fast, want) or d <= 8                     # it really is a different arithmetic
+
+
+def test_fast_mode_encode_quality(rb):
+    n, d, m = 20000, 128, 8
+    X, C, B = _data(n, d, m, seed=7)
+    want = orc.encode_icm(X, C, B, 4, 4, 4, True, seed=3, use_ref_step=orc.have_ref())
+    exact = rb.core.encode_icm(X, C, B, 4, 4, 4, True, seed=3, want_cost=True)
+    fast = rb.core.encode_icm(X, C, B, 4, 4, 4, True, seed=3, want_cost=True, fast=True)
+    assert np.array_equal(exact["B"], want["B"])                        # the default is untouched by the fast mode
+    mismatch = float((fast["B"] != want["B"]).any(axis=1).mean())
+    qe, qf = float(exact["cost"].mean()), float(fast["cost"].mean())
+    print("fast unaries: vector mismatch rate %.3e, qerror %.6f vs %.6f" % (mismatch, qf, qe))
+    assert mismatch < 2e-2
+    assert abs(qf - qe) <= 1e-4 * qe                                    # north_star tolerance on qerror
+    # costs are still exact veccosts of the codes it returns
+    assert np.array_equal(rb.core.veccost(X, fast["B"], C).view(np.uint32), fast["cost"].view(np.uint32))
