@@ -538,7 +538,10 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
           }
         }
       }
-      const float newcost = warp_cost<M>(x, p.C, nb, p.d, sq, lane);  // src/LSQ.jl:237
+      // newcost, src/LSQ.jl:237.  When ICM led back to the codes the iteration started from (the perturbation was
+      // undone -- the common case late in the search) the cost is the same arithmetic on the same inputs: reuse it.
+      const bool same = nb.lo == cur.lo && nb.hi == cur.hi;
+      const float newcost = same ? curcost : warp_cost<M>(x, p.C, nb, p.d, sq, lane);
       if (lane == 0) {
         if (newcost == curcost) atomicAdd(&stats_s[2 * it], 1);
         if (newcost < curcost) atomicAdd(&stats_s[2 * it + 1], 1);
