@@ -76,7 +76,7 @@ def make_data(n, nq, d, seed, device, rank=0):
     """SIFT-like synthetic base: 1024 Gaussian clusters with a power-law spectrum (sigma_i ~ i^-0.75) plus
     unit within-cluster noise on the same spectrum, then a fixed random rotation; queries come from the same
     distribution.  Isotropic noise would make Recall@1 degenerate (~1%); this gives R@1 ~ 0.3 at 64-bit codes,
-    the regime of the reference's SIFT1M demo (probe: scratch/recall_probe.py)."""
+    the regime of the reference's SIFT1M demo (probe: tools/recall_probe.py)."""
     import torch
     g = torch.Generator(device=device).manual_seed(1234)
     s = torch.arange(1, d + 1, device=device, dtype=torch.float32) ** -0.75
@@ -371,7 +371,27 @@ def run_ours(args, cfg):
     n, d, m, nq, k = cfg["n"], cfg["d"], cfg["m"], cfg["nq"], cfg["k"]
 
     # ---- workload -----------------------------------------------------------------------------------------
-    X, Q = make_data(n, nq, d, seed=1000, device=device, rank=rank)
+    real = None
+    if args.data_dir:
+        # real SIFT1M (src/read_datasets.jl:63-85; demos/experiment_utils.jl:63-86) when the files are there: base,
+        # queries and -- for the full base on one GPU -- the dataset's own ground truth, so Recall@1 is the true one
+        from rayuela_b200 import demos
+        if demos.have_sift1m(args.data_dir):
+            a0 = rank * n
+            Xb = demos.read_dataset("SIFT1M_base", (a0 + 1, a0 + n), False, args.data_dir)
+            Xq = demos.read_dataset("SIFT1M_query", nq, False, args.data_dir)
+            gtf = demos.read_dataset("SIFT1M_groundtruth", nq, False, args.data_dir)
+            X = torch.from_numpy(np.ascontiguousarray(Xb.T)).to(device)
+            Q = torch.from_numpy(np.ascontiguousarray(Xq.T)).to(device)
+            real = {"dataset": "SIFT1M", "dir": args.data_dir,
+                    "gt": torch.from_numpy(gtf[0, :nq].astype(np.int64)).to(device) if world == 1 and n == 1_000_000
+                    else None}
+            d = X.shape[1]
+        else:
+            print("bench: no SIFT1M files under %s (sift/sift_{learn,base,query}.fvecs, sift_groundtruth.ivecs); "
+                  "using the synthetic base" % args.data_dir, file=sys.stderr)
+    if real is None:
+        X, Q = make_data(n, nq, d, seed=1000, device=device, rank=rank)
     C = train_codebooks(X[:50000], m, device)
     gB = torch.Generator(device=device).manual_seed(5 + rank)
     B0 = torch.randint(0, H, (n, m), generator=gB, device=device, dtype=torch.uint8)   # src/LSQ_GPU.jl:351
@@ -465,8 +485,8 @@ def run_ours(args, cfg):
     scan_launches = rb.launch_count() - l1
     scan_per = scan_ms / args.steps
     scan_value = nq / (scan_per * 1e-3)
-    # Recall@1 against exact fp32 brute force over the GLOBAL base
-    gt = exact_nn(X, Q)
+    # Recall@1 against exact fp32 brute force over the GLOBAL base (or the dataset's own ground truth)
+    gt = real["gt"] if real is not None and real["gt"] is not None else exact_nn(X, Q)
     if dist is not None:
         # per-rank best -> global best: compare distances
         dbest = ((X[gt] - Q) ** 2).sum(1)
@@ -587,7 +607,8 @@ def run_ours(args, cfg):
         "unit": "vectors/s" if primary_icm else "queries/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": icm_per if primary_icm else scan_per,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "SIFT1M (%s)" % args.data_dir if real is not None else "synthetic",
         "config": workload_config(cfg, args),
         "clocks": clocks,
         "e2e": ({"value": world * n / (icm_e2e_ms * 1e-3), "unit": "vectors/s",
@@ -804,6 +825,9 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="skip the config4 / config5 / k=1000 objects")
+    ap.add_argument("--data-dir", default=os.environ.get("RAYUELA_DATA_DIR", ""),
+                    help="directory holding sift/sift_{learn,base,query}.fvecs + sift_groundtruth.ivecs: bench on the "
+                         "real SIFT1M base (true Recall@1) instead of the synthetic one")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference" or os.environ.get("BENCH_ALLOW_SHORT"), "warmup must be >= 3"
     cfg = dict(n=args.n, nq=args.nq, m=args.m, d=args.d, k=args.k, ilsiter=args.ilsiter, icmiter=4, npert=4)

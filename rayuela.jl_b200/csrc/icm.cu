@@ -382,7 +382,7 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 //                              + 2^-20 * (umax + (M-1)*tmax_j)       fp32 roundings of the exact chain
 // =: delta.  Every candidate that can be the exact first-minimum has S <= min(S) + 2*delta/scale_j.  If exactly ONE
 // candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~1-3 % of
-// the steps, scratch/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
+// the steps, tools/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
 // construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
 template <int M, bool PF, bool JSPEC = false>
 __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {

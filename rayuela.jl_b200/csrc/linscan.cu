@@ -234,7 +234,7 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
 // K5: bank-conflict-free scan, period P = 8 (m <= 8) or 16 (m = 9..16) codebooks.
 //
 // A 4-byte LUT lookup per byte of code makes the scan shared-memory-gather bound (one LDS.64 warp-instruction per
-// 2 clk per SM, measured: scratch/ubench/lds_ffma2.cu), and 32 lanes looking up random entries of the same
+// 2 clk per SM, measured: tools/ubench/lds_ffma2.cu), and 32 lanes looking up random entries of the same
 // 256-entry row collide ~3.6x (measured on the round-1 v1 kernel, profiles/r1_v1).  Here every lane of a half-warp
 // is at a DIFFERENT bank-pair at any instant:
 //   P = 8 : tile[tt][c][bp = g*8 + k][e]  (float; 4 queries per 32 KB tile: q = tt*4 + g*2 + e); lane = hw*16 + g*8 + j
@@ -1040,7 +1040,7 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       const size_t smem = (size_t)kScanSortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
       // DB slices.  A launch of qtiles x S blocks takes ceil(qtiles*S / SMs) waves of (1/S + c) base passes each,
       // c = per-block fixed cost (LUT staging, threshold warm-up, final selection) ~ 0.065 + 0.0005 k of a pass
-      // (fit to scratch/slices_probe.py): whole waves of tiles stay unsliced, a partial wave is cut so that it fills
+      // (fit to tools/slices_probe.py): whole waves of tiles stay unsliced, a partial wave is cut so that it fills
       // the machine once (33 tiles -> 4 slices, 100 tiles -> 4 slices = 2.7 waves of quarter passes, 1 tile -> 61)
       const int64_t unit = (int64_t)kChunkCodes * kScanWarps;   // codes per block round
       const int smax = (int)std::min<int64_t>(std::min<int64_t>(std::max<int64_t>(1, ix->n / unit), 4 * sms),

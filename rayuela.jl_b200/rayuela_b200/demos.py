@@ -35,7 +35,8 @@ def read_dataset(dname, nvectors, V=False, data_dir="./data"):
     fname = os.path.join(data_dir, _SIFT_FILES[dname])
     if V:
         print("Loading %s from %s" % (dname, fname))
-    return (ivecs_read if fname.endswith(".ivecs") else fvecs_read)(int(nvectors), fname)
+    bounds = tuple(int(v) for v in nvectors) if isinstance(nvectors, (tuple, list)) else int(nvectors)
+    return (ivecs_read if fname.endswith(".ivecs") else fvecs_read)(bounds, fname)
 
 
 def have_sift1m(data_dir="./data"):

@@ -75,3 +75,28 @@ def test_quantize_norms_oracle_against_numpy():
     codes, norms = orc.quantize_norms(B, C, cb)
     assert np.allclose(norms, (rec ** 2).sum(1), rtol=1e-5)
     assert (codes == np.abs(norms[:, None] - cb[None]).argmin(1)).mean() > 0.995
+
+
+def test_sift1m_loader_round_trip(tmp_path):
+    """read_dataset / load_experiment_data (src/read_datasets.jl:63-85, demos/experiment_utils.jl:63-86) on a tiny
+    directory laid out like ./data/sift/: shapes, the +1 on the zero-based ground truth, range reads."""
+    import numpy as np
+    from rayuela_b200 import demos, xvecs
+    r = np.random.default_rng(0)
+    d, nt, nb, nq = 16, 50, 200, 7
+    (tmp_path / "sift").mkdir()
+    Xt = np.asfortranarray(r.random((d, nt)).astype(np.float32))
+    Xb = np.asfortranarray(r.random((d, nb)).astype(np.float32))
+    Xq = np.asfortranarray(r.random((d, nq)).astype(np.float32))
+    gt0 = ((Xb.T[None, :, :] - Xq.T[:, None, :]) ** 2).sum(-1).argsort(1)[:, :5].T.astype(np.int32)   # 5-by-nq, 0-based
+    xvecs.fvecs_write(Xt, str(tmp_path / "sift" / "sift_learn.fvecs"))
+    xvecs.fvecs_write(Xb, str(tmp_path / "sift" / "sift_base.fvecs"))
+    xvecs.fvecs_write(Xq, str(tmp_path / "sift" / "sift_query.fvecs"))
+    xvecs.ivecs_write(gt0, str(tmp_path / "sift" / "sift_groundtruth.ivecs"))
+    assert demos.have_sift1m(str(tmp_path)) and not demos.have_sift1m(str(tmp_path / "nope"))
+    a, b, q, gt = demos.load_experiment_data("SIFT1M", 40, nb, nq, False, str(tmp_path))
+    assert a.shape == (d, 40) and b.shape == (d, nb) and q.shape == (d, nq)
+    assert np.array_equal(a, Xt[:, :40]) and np.array_equal(b, Xb)
+    assert np.array_equal(gt, gt0[0] + 1)                       # a truncated base recomputes it: same answer here
+    part = demos.read_dataset("SIFT1M_base", (11, 20), False, str(tmp_path))
+    assert np.array_equal(part, Xb[:, 10:20])
