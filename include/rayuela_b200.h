@@ -35,6 +35,12 @@ extern "C" {
                                  * bit-identical to the oracle (near-ties may flip; qerror agrees to ~1e-5).  Needs d <= 128;
                                  * otherwise, and by default, the exact kernel runs.  Also: RAYUELA_B200_FAST_UNARIES=1. */
 
+#define RAYUELA_FAST_LUT 4u     /* rayuela_index_search, LSQ scan: OPT-IN tensor-core lookup tables.  The per-query m*256 table
+                                 * -2<q,c> (the dense Q x C' contraction, pairwise_byte.cpp:42-49) is built by the same tcgen05
+                                 * bf16x3 GEMM; the byte-code scan, the norm add and the top-k stay exact given that table.
+                                 * Distances within ~1e-5 relative of the exact ones; ids may differ on near-ties.  Needs
+                                 * d <= 128.  Also: RAYUELA_B200_FAST_LUT=1.  Off by default. */
+
 /* Last error message of the calling thread ("" if none). The reference has no error channel at all
  * (void symbols, deps/src/*.cpp extern blocks); Julia-side checks are error() strings. */
 const char* rayuela_last_error(void);

@@ -166,6 +166,13 @@ inline void split_range(int64_t n, int nparts, int part, int64_t* a, int64_t* b)
 // the first non-OK status, with that thread's error message copied to the caller's error channel.
 int for_each_slot(const std::vector<DeviceSlot>& slots, const std::function<int(int)>& fn);
 
+// ---- unary_tc.cu: opt-in tcgen05 GEMM  out[l][e] = -2 <C[e], X[l]> + nrm[e]  (bf16x3, fp32 accumulation in TMEM) ----
+struct DevBuf;
+bool unary_tc_supported(int d, int mh);
+int unary_tc_pack_codebooks(const float* C, int d, int mh, DevBuf* Cp, cudaStream_t s);
+int unary_tc_launch(const float* X, const DevBuf& Cp, const float* nrm, float* U, unsigned int* umax, int64_t nc, int d,
+                    int mh, cudaStream_t s);
+
 // ---- Philox4x32-10 (host + device): the RNG contract shared with the oracle (DESIGN.md "RNG") --------
 __host__ __device__ inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
 #pragma unroll

@@ -322,12 +322,6 @@ __device__ __forceinline__ float4 ldg_f4_hint(const float4* ptr, uint64_t pol) {
   return v;
 }
 
-// unary_tc.cu: opt-in tcgen05 unaries
-bool unary_tc_supported(int d, int mh);
-int unary_tc_pack_codebooks(const float* C, int d, int mh, DevBuf* Cp, cudaStream_t s);
-int unary_tc_launch(const float* X, const DevBuf& Cp, const float* nrm, float* U, unsigned int* umax, int64_t nc, int d,
-                    int mh, cudaStream_t s);
-
 struct IcmParams {
   const float* U;       // [nc][m][256]  unaries of this chunk
   const float* T;       // [m][m][256][256]

@@ -87,6 +87,22 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
   }
 }
 
+// OPT-IN fast LUT (RAYUELA_FAST_LUT, LSQ only): the LUT is the dense contraction -2 * Q C^T, computed row-major by the
+// tcgen05 GEMM of unary_tc.cu (bf16x3) and re-laid-out here into the scan's tiled layout (same index maps as lut_kernel).
+__global__ void __launch_bounds__(256) lut_relayout_kernel(const float* __restrict__ rowmajor, float* __restrict__ lut,
+                                                           int nq, int mh, int tiled, int* __restrict__ bad) {
+  const int64_t total = (int64_t)nq * mh;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i / mh), ent = (int)(i % mh), k = ent >> 8, c = ent & 255;
+    const float v = rowmajor[i];
+    if (!(fabsf(v) <= 1e37f)) *bad = 1;
+    if (tiled == 1)
+      lut[(size_t)(q >> 4) * 32768 + ((q & 15) >> 2) * 8192 + c * 32 + ((((q & 3) >> 1) * 8 + k) << 1) + (q & 1)] = v;
+    else
+      lut[(size_t)(q >> 3) * 32768 + ((q & 7) >> 1) * 8192 + c * 32 + (k << 1) + (q & 1)] = v;
+  }
+}
+
 // Block-wide barrier (named barrier 1 with an explicit thread count; same semantics as __syncthreads()).  In
 // scanx_kernel every block barrier between the prologue and the final phase lives inside service(), which is ONE
 // non-inlined function, so the warps that call it from the period loop and the finished warps that call it from
@@ -987,8 +1003,16 @@ static int merge_lists(const uint64_t* keys, const float* din, const int32_t* ii
 
 // all arrays on the current device; bad: device int, set when a LUT entry is unusable (see lut_kernel)
 static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* cb_dev, int nq, int d, int k,
-                            float* d_dev, int32_t* i_dev, int* bad, cudaStream_t s) {
+                            float* d_dev, int32_t* i_dev, int* bad, cudaStream_t s, bool fast_lut = false) {
   const int m = ix->m, mh = m * kH;
+  // opt-in: tensor-core LUT for the LSQ scan (codebooks split / packed once per search)
+  fast_lut = fast_lut && ix->kind == RAYUELA_SCAN_LSQ && unary_tc_supported(d, mh);
+  DevBuf Cp_d, zero_d;
+  if (fast_lut) {
+    RYL_TRY(unary_tc_pack_codebooks(cb_dev, d, mh, &Cp_d, s));
+    RYL_TRY(zero_d.alloc((size_t)mh * sizeof(float), s));
+    RYL_CUDA(cudaMemsetAsync(zero_d.p, 0, zero_d.bytes, s));
+  }
   const bool pq = ix->kind == RAYUELA_SCAN_PQ;
   const int len = pq ? d / m : d;
   const int period = ix->period;
@@ -1017,7 +1041,12 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
     dim3 lg(mh / 32, (nqc + 31) / 32);
     const float* qptr = q_dev + (size_t)qb * d;
     const int tiled = period == 16 ? 2 : 1;
-    if (ix->kind == RAYUELA_SCAN_LSQ)
+    if (fast_lut) {
+      DevBuf rowmajor;
+      RYL_TRY(rowmajor.alloc((size_t)nqc * mh * sizeof(float), s));
+      RYL_TRY(unary_tc_launch(qptr, Cp_d, zero_d.as<float>(), rowmajor.as<float>(), nullptr, nqc, d, mh, s));
+      RYL_LAUNCH(lut_relayout_kernel, sm_count() * 8, 256, 0, s, rowmajor.as<float>(), lut.as<float>(), nqc, mh, tiled, bad);
+    } else if (ix->kind == RAYUELA_SCAN_LSQ)
       RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
     else if (ix->kind == RAYUELA_SCAN_CQ)
       RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
@@ -1127,7 +1156,7 @@ static const char* kBadLutMsg =
 // copied peer-to-peer to the first slot's device and merged there by the (dist, id) total order -- the single exchange
 // step of SURVEY 8e, done with peer copies inside one process instead of an NCCL all-gather between processes.
 static int index_search_multi(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d, int k,
-                              float* dists, int32_t* idx) {
+                              float* dists, int32_t* idx, bool fast_lut) {
   const int D = (int)ix->shards.size();
   const int len = ix->kind == RAYUELA_SCAN_PQ ? d / ix->m : d;
   const size_t per = (size_t)nq * k;
@@ -1153,7 +1182,8 @@ static int index_search_multi(rayuela_index* ix, const float* queries, const flo
       RYL_TRY(il.alloc(per * sizeof(int32_t), s));
       RYL_TRY(bd.alloc(sizeof(int), s));
       RYL_CUDA(cudaMemsetAsync(bd.p, 0, sizeof(int), s));
-      RYL_TRY(index_search_dev(ix->shards[i], q_in.d, cb_in.d, nq, d, k, dl.as<float>(), il.as<int32_t>(), bd.as<int>(), s));
+      RYL_TRY(index_search_dev(ix->shards[i], q_in.d, cb_in.d, nq, d, k, dl.as<float>(), il.as<int32_t>(), bd.as<int>(), s,
+                               fast_lut));
       RYL_CUDA(cudaMemcpyPeerAsync(gd.as<float>() + (size_t)i * per, root.device, dl.p, ix->slots[i].device,
                                    per * sizeof(float), s));
       RYL_CUDA(cudaMemcpyPeerAsync(gi.as<int32_t>() + (size_t)i * per, root.device, il.p, ix->slots[i].device,
@@ -1190,9 +1220,11 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   RYL_ARG(!pq || d % m == 0, "index_search: PQ scan needs d divisible by m");
   const int len = pq ? d / m : d;
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  const char* fast_env = getenv("RAYUELA_B200_FAST_LUT");
+  const bool fast_lut = (flags & RAYUELA_FAST_LUT) || (fast_env && atoi(fast_env) != 0);
   if (!ix->shards.empty()) {
     RYL_ARG(!dev, "index_search: a multi-device index takes host arrays");
-    return index_search_multi(ix, queries, codebooks, nq, d, k, dists, idx);
+    return index_search_multi(ix, queries, codebooks, nq, d, k, dists, idx, fast_lut);
   }
 
   InArg<float> q_in, cb_in;
@@ -1205,7 +1237,7 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   DevBuf bad;
   RYL_TRY(bad.alloc(sizeof(int), s));
   RYL_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), s));
-  RYL_TRY(index_search_dev(ix, q_in.d, cb_in.d, nq, d, k, d_out.d, i_out.d, bad.as<int>(), s));
+  RYL_TRY(index_search_dev(ix, q_in.d, cb_in.d, nq, d, k, d_out.d, i_out.d, bad.as<int>(), s, fast_lut));
   RYL_TRY(d_out.flush(s));
   RYL_TRY(i_out.flush(s));
   if (!dev) {

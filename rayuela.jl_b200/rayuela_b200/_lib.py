@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "librayuela_b200.so")
 
 DEVICE_PTRS = 1
 FAST_UNARIES = 2
+FAST_LUT = 4
 SCAN_LSQ, SCAN_CQ, SCAN_PQ = 0, 1, 2
 
 _vp = ct.c_void_p

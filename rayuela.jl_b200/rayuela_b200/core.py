@@ -11,7 +11,7 @@ import ctypes as ct
 import numpy as np
 
 from . import _lib
-from ._lib import DEVICE_PTRS, FAST_UNARIES, SCAN_CQ, SCAN_LSQ, SCAN_PQ, RayuelaError, check
+from ._lib import DEVICE_PTRS, FAST_LUT, FAST_UNARIES, SCAN_CQ, SCAN_LSQ, SCAN_PQ, RayuelaError, check
 
 H = 256
 
@@ -209,8 +209,8 @@ class Index:
         check(L.rayuela_index_create(ct.byref(h), kind, cp, np_, n, m, H, id_offset, a.flags, a.stream))
         self._h, self.kind, self.n, self.m, self.id_offset = h, kind, n, m, id_offset
 
-    def search(self, queries, codebooks, k, out=None):
-        """Top-k of every query.  out=(dists, idx): preallocated (nq, k) float32 / int32 result arrays on the same
+    def search(self, queries, codebooks, k, out=None, fast=False):
+        """Top-k of every query.  fast=True (LSQ only): opt-in tensor-core LUT build, not bit-identical.  out=(dists, idx): preallocated (nq, k) float32 / int32 result arrays on the same
         side as the queries (e.g. pinned host memory), like the caller-allocated outputs of src/Linscan.jl:132-133."""
         L = _lib.lib()
         if self._h is None:
@@ -227,7 +227,7 @@ class Index:
         else:
             dists, dp = a.new(dev, np.float32, (nq, k), device=queries.device if dev else None)
             idx, ip = a.new(dev, np.int32, (nq, k), device=queries.device if dev else None)
-        check(L.rayuela_index_search(self._h, qp, cp, nq, d, k, dp, ip, a.flags, a.stream))
+        check(L.rayuela_index_search(self._h, qp, cp, nq, d, k, dp, ip, a.flags | (FAST_LUT if fast else 0), a.stream))
         return dists, idx
 
     def free(self):

@@ -54,3 +54,28 @@ def test_fast_mode_encode_quality(rb):
     assert abs(qf - qe) <= 1e-4 * qe                                    # north_star tolerance on qerror
     # costs are still exact veccosts of the codes it returns
     assert np.array_equal(rb.core.veccost(X, fast["B"], C).view(np.uint32), fast["cost"].view(np.uint32))
+
+
+@pytest.mark.parametrize("m,k", [(8, 1), (8, 100), (16, 10)])
+def test_fast_lut_scan(rb, m, k):
+    """RAYUELA_FAST_LUT: the LSQ lookup tables by the tcgen05 GEMM; scan / norm add / top-k unchanged.  Distances within
+    1e-4 relative (north_star), neighbour lists agree except on near-ties, Recall@1 against the exact search >= 0.995;
+    the default search stays bit-identical to the reference."""
+    r = np.random.default_rng(m * 100 + k)
+    n, nq, d = 60_000, 200, 128
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    C = (r.standard_normal((m * 256, d)) / np.sqrt(m)).astype(np.float32)
+    Xq = r.standard_normal((nq, d)).astype(np.float32)
+    rec = sum(C.reshape(m, 256, d)[j][B[:, j]] for j in range(m))
+    nrm = (rec * rec).sum(1).astype(np.float32)
+    d0, i0 = (orc.ref_linscan if orc.have_ref() else orc.linscan)(orc.LSQ, B, Xq, C, k, nrm)
+    ix = rb.core.Index(rb.core.SCAN_LSQ, B, nrm)
+    de, ie = ix.search(Xq, C, k)
+    assert np.array_equal(ie, i0) and np.array_equal(de.view(np.uint32), d0.view(np.uint32))
+    df, jf = ix.search(Xq, C, k, fast=True)
+    scale = np.abs(d0).max()
+    assert np.abs(np.sort(df, 1) - np.sort(d0, 1)).max() <= 1e-4 * scale
+    assert (jf[:, 0] == i0[:, 0]).mean() >= 0.995
+    agree = np.mean([len(set(a) & set(b)) / k for a, b in zip(jf, i0)])
+    print("fast LUT: top-%d list overlap %.5f, top-1 agreement %.4f" % (k, agree, (jf[:, 0] == i0[:, 0]).mean()))
+    assert agree >= 0.99

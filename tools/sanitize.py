@@ -29,4 +29,24 @@ Bp = core.quantize_pq(X, Cpq, m); core.Index(core.SCAN_PQ, Bp).search(Q, Cpq, 20
 core.fast_bin_matmul(X, B); core.quantize_chainq(X[:500], C, m)
 dd = np.sort(r.standard_normal((3, 5, 16)).astype(np.float32), axis=2); ii = r.permutation(240).reshape(3, 5, 16).astype(np.int32)
 core.topk_merge(dd, ii)
+# ---- round 2: chunk pipeline (two streams + copy stream), dynamic schedule, any-h kernels, tcgen05 unaries, merge tree,
+# multi-device (two shards on device 0), ragged query tile, get_unaries
+import os
+import rayuela_b200 as rb
+os.environ["RAYUELA_B200_UNARY_BYTES"] = str(8 * 1024 * 1024)             # 1024 vectors per chunk -> 3 chunks
+core.encode_icm(X, C, B, 2, 2, 4, True, seed=1, want_cost=True, snap_iters=[2])
+del os.environ["RAYUELA_B200_UNARY_BYTES"]
+for h in (16, 100):
+    Ch = r.standard_normal((4 * h, d)).astype(np.float32); Bh = r.integers(0, h, (700, 4), dtype=np.uint8)
+    core.encode_icm(X[:700], Ch, Bh, 2, 2, 3, True, seed=2, h=h, want_cost=True, snap_iters=[1])
+    core.veccost(X[:700], Bh, Ch, h=h)
+core.get_unaries(X[:300], C, m); core.get_unaries(X[:300], C, m, fast=True)
+core.encode_icm(X[:1000], C, B[:1000], 1, 2, 4, True, seed=1, fast=True)
+dd = np.sort(r.standard_normal((3, 4, 6000)).astype(np.float32), axis=2); ii = r.permutation(3 * 4 * 6000).reshape(3, 4, 6000).astype(np.int32)
+core.topk_merge(dd, ii)                                                      # 18000 keys per query: the rank-merge tree
+rb.init([0, 0])
+core.encode_icm(X, C, B, 1, 2, 4, True, seed=1, snap_iters=[1])
+ix = core.Index(core.SCAN_LSQ, out['B'], nrm); ix.search(Q, C, 10); ix.free()
+rb.init(None)
+core.Index(core.SCAN_PQ, Bp).search(Q[:17], Cpq, 3)                          # ragged last query tile (dummy queries)
 print("sanitize run done")
