@@ -425,6 +425,7 @@ def run_ours(args, cfg):
                     inplace=True, want_stats=True)          # untimed: executed-step count of the same workload
     steps_done, steps_total = core.last_icm_steps()
     steps_exact = core.last_icm_exact_steps()
+    lib_ms = core.last_icm_timings()                        # the library's own CUDA-event phase timers (cross-check)
     # bytes the kernel actually gathers: a 512 B quantised row per (step, other codebook) + the step's 1 KB unary row,
     # and the 1 KB fp32 rows again for the steps the pre-filter left undecided; memoised steps read nothing
     gather_bytes = float(steps_done) * ((m - 1) * H * 2 + H * 4) + float(steps_exact) * (m - 1) * H * 4
@@ -591,6 +592,7 @@ def run_ours(args, cfg):
                 "peak_source": "148 SM x 128 B/clk x sampled SM clock (SURVEY 8d: the path is not HBM-bound)",
                 "hbm_peak": pk["hbm_gbs"], "hbm_peak_source": pk_src, "hbm_frac_of_algorithmic": achieved / pk["hbm_gbs"],
                 "kernel": "icm_warp_kernel<%d,true,%s>" % (m, "true" if m <= 8 else "false"), "kernel_ms": k3_ms,
+                "kernel_ms_library_events": lib_ms,
                 "steps_executed": steps_done, "steps_reference": steps_total, "steps_exact_rows": steps_exact,
                 "gathered_actual": gather_bytes / (k3_ms * 1e-3) / 1e9,
                 "note": "achieved = SURVEY 8d algorithmic (work-equivalent) bytes n*ilsiter*icmiter*m*(m-1)*256*4 -- what "

@@ -101,6 +101,12 @@ int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total);
  * window (near-ties) re-read the fp32 rows -- the result is bit-identical either way. Measurement aid. */
 int rayuela_encode_icm_exact_steps(uint64_t* exact);
 
+/* CUDA-event timings (ms) of the last rayuela_encode_icm call of this thread that requested `stats`:
+ * {tables + setup, unaries (K1), ICM / ILS kernel (K3), whole call on the device}.  The reference times the same
+ * phases with time_ns() around host calls (src/LSQ_GPU.jl:50-55,58,213).  With several chunks on alternating streams the
+ * phases overlap, so unaries + ICM may exceed the whole-call figure.  Single-device calls only. */
+int rayuela_encode_icm_timings(float* ms4);
+
 /* Replaces get_unaries (src/utils.jl:121-149): U[l][j][c] = -2<C_j[:,c], x_l> + ||C_j[:,c]||^2, written vector-major
  * as n-by-(m*h) (the reference keeps m separate h-by-n matrices; U[l*m*h + j*h + c] is its unaries[j][c, l]).  The
  * encoder computes these internally; the entry point exists for callers that want the table (e.g. ChainQ-style

@@ -952,6 +952,12 @@ __global__ void __launch_bounds__(256) icm_generic_kernel(IcmGenericParams gp) {
 using namespace ryl;
 
 static thread_local uint64_t g_icm_steps_done = 0, g_icm_steps_total = 0, g_icm_steps_exact = 0;
+static thread_local float g_icm_ms[4] = {0, 0, 0, 0};   // setup (tables), unaries, ICM kernel, whole call -- CUDA events
+
+extern "C" int rayuela_encode_icm_timings(float* ms4) {
+  if (ms4) memcpy(ms4, g_icm_ms, sizeof g_icm_ms);
+  return RAYUELA_OK;
+}
 
 extern "C" int rayuela_encode_icm_exact_steps(uint64_t* exact) {
   if (exact) *exact = g_icm_steps_exact;
@@ -1106,6 +1112,25 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     }
   }
 
+  // CUDA-event timers of the phases, kept when `stats` is requested (rayuela_encode_icm_timings)
+  EventBox t_begin, t_setup, t_end;
+  std::vector<EventBox> t_u0(stats ? nchunks : 0), t_u1(stats ? nchunks : 0), t_k(stats ? nchunks : 0);
+  auto timed_event = [](EventBox& e) -> int {
+    RYL_CUDA(cudaEventCreate(&e.e));
+    return RAYUELA_OK;
+  };
+  if (stats) {
+    RYL_TRY(timed_event(t_begin));
+    RYL_TRY(timed_event(t_setup));
+    RYL_TRY(timed_event(t_end));
+    for (int c = 0; c < nchunks; c++) {
+      RYL_TRY(timed_event(t_u0[c]));
+      RYL_TRY(timed_event(t_u1[c]));
+      RYL_TRY(timed_event(t_k[c]));
+    }
+    RYL_CUDA(cudaEventRecord(t_begin.e, s));
+  }
+
   InArg<float> x_in, c_in;
   if (dev || !piped) {
     RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
@@ -1182,6 +1207,7 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     RYL_TRY(U_d[i].alloc((size_t)std::min(chunk, n) * per_vec, s));
     if (pf) RYL_TRY(umax_d[i].alloc((size_t)std::min(chunk, n) * sizeof(unsigned int), s));
   }
+  if (stats) RYL_CUDA(cudaEventRecord(t_setup.e, s));
   if (piped) {
     RYL_CUDA(cudaEventRecord(ev_setup.e, s));               // allocations + tables are ordered before the other streams
     RYL_CUDA(cudaStreamWaitEvent(s_alt, ev_setup.e, 0));
@@ -1204,6 +1230,7 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     if (piped && !dev) RYL_CUDA(cudaStreamWaitEvent(cs, ev_up[c].e, 0));
     dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
     if (pf) RYL_CUDA(cudaMemsetAsync(umax, 0, (size_t)nc * sizeof(unsigned int), cs));
+    if (stats) RYL_CUDA(cudaEventRecord(t_u0[c].e, cs));
     if (fast)
       RYL_TRY(unary_tc_launch(x_in.d + (size_t)l0 * d, Cp_d, nrm_d.as<float>(), U, umax, nc, d, mh, cs));
     else if (d % 4 == 0)
@@ -1212,6 +1239,7 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     else
       RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
                  umax);
+    if (stats) RYL_CUDA(cudaEventRecord(t_u1[c].e, cs));
     IcmParams p;
     p.U = U;
     p.T = T_d.as<float>();
@@ -1244,6 +1272,7 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     RYL_M_SWITCH(m, CALL)
 #undef CALL
     RYL_TRY(rc);
+    if (stats) RYL_CUDA(cudaEventRecord(t_k[c].e, cs));
   }
   if (piped) {                                              // join: everything below is ordered after both streams
     RYL_CUDA(cudaEventRecord(ev_alt_done.e, s_alt));

@@ -96,6 +96,13 @@ function encode_icm_cuda(RX::Matrix{Float32}, B::Matrix{Int16}, C::Vector{Matrix
   return Bs, objs
 end
 
+"Phase times (ms) of the last verbose encode: (setup, unaries, icm, total) -- the reference prints time_ns() deltas, src/LSQ_GPU.jl:50-58,213"
+function encode_icm_timings()
+  t = zeros(Cfloat, 4)
+  check(ccall((:rayuela_encode_icm_timings, librayuela_b200), Cint, (Ptr{Cfloat},), t))
+  return (setup=t[1], unaries=t[2], icm=t[3], total=t[4])
+end
+
 "veccost(X, B, C)   (src/qerrors.jl:36-66)"
 function veccost(X::Matrix{Float32}, B::Matrix{<:Integer}, C::Vector{Matrix{Float32}})
   d, n = size(X); m = length(C)

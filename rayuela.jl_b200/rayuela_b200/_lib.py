@@ -30,6 +30,7 @@ SIGNATURES = {
                                   _vp, _vp, _int, _vp, _vp, _vp, _vp, ct.c_uint, _vp]),
     "rayuela_encode_icm_steps": (_int, [_vp, _vp]),
     "rayuela_encode_icm_exact_steps": (_int, [_vp]),
+    "rayuela_encode_icm_timings": (_int, [_vp]),
     "rayuela_get_unaries": (_int, [_vp, _vp, _i64, _int, _int, _int, _vp, ct.c_uint, _vp]),
     "rayuela_veccost": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, ct.c_uint, _vp]),
     "condition": (None, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int]),

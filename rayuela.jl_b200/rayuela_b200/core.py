@@ -157,6 +157,13 @@ def last_icm_steps():
     return int(a.value), int(b.value)
 
 
+def last_icm_timings():
+    """CUDA-event times (ms) of the last encode_icm(..., want_stats=True): dict(setup, unaries, icm, total)."""
+    t = (ct.c_float * 4)()
+    check(_lib.lib().rayuela_encode_icm_timings(ct.addressof(t)))
+    return dict(setup=float(t[0]), unaries=float(t[1]), icm=float(t[2]), total=float(t[3]))
+
+
 def last_icm_exact_steps():
     """Executed steps of that call that re-read the exact fp32 rows (the quantised pre-filter left a near-tie)."""
     a = ct.c_uint64(0)
