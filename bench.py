@@ -550,7 +550,9 @@ def run_ours(args, cfg):
     # ---- strong-scaling objects (every rank takes part; rank 0 keeps the result) ---------------------------------
     index.free()
     strong = {}
-    if not args.no_strong:
+    if not args.no_strong and 8 % world != 0:
+        strong["config4"] = strong["config5"] = {"skipped": "the strong-scaling bases are cut in 8 fixed blocks: N must divide 8"}
+    elif not args.no_strong:
         del X, Bwork, B0, Bscratch
         torch.cuda.empty_cache()
         strong["config4"] = run_config4(dist, device, world, rank)

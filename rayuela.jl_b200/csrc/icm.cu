@@ -1298,10 +1298,20 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     unsigned long long done_steps[2] = {0, 0};
     RYL_CUDA(cudaMemcpyAsync(stats, stats_d.p, (size_t)ilsiter * 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     RYL_CUDA(cudaMemcpyAsync(done_steps, steps_d, sizeof(done_steps), cudaMemcpyDeviceToHost, s));
+    RYL_CUDA(cudaEventRecord(t_end.e, s));
     RYL_CUDA(cudaStreamSynchronize(s));
     g_icm_steps_done = done_steps[0];
     g_icm_steps_exact = pf ? done_steps[1] : done_steps[0];
     g_icm_steps_total = (uint64_t)n * ilsiter * icmiter * m;
+    // phase times: chunks on alternating streams overlap, so unaries + ICM can exceed the whole-call figure
+    float t = 0;
+    g_icm_ms[1] = g_icm_ms[2] = 0;
+    cudaEventElapsedTime(&g_icm_ms[0], t_begin.e, t_setup.e);
+    for (int c = 0; c < nchunks; c++) {
+      if (cudaEventElapsedTime(&t, t_u0[c].e, t_u1[c].e) == cudaSuccess) g_icm_ms[1] += t;
+      if (cudaEventElapsedTime(&t, t_u1[c].e, t_k[c].e) == cudaSuccess) g_icm_ms[2] += t;
+    }
+    cudaEventElapsedTime(&g_icm_ms[3], t_begin.e, t_end.e);
   }
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
   return RAYUELA_OK;

@@ -12,8 +12,8 @@
 // Data movement: a pre-pass (split_pack_kernel) writes both operands as ready-made shared-memory images -- one 128-byte
 // row per 64 bf16 of K, 16-byte chunks XOR-swizzled by (row & 7), i.e. exactly the canonical K-major SWIZZLE_128B layout
 // tcgen05.mma reads -- so a tile is fetched with plain 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx), no
-// tensor maps.  Kernel: one persistent CTA per SM, 6 warps: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA
-// issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32x32b -> fma(-2, acc, ||c||^2) -> global, per-vector
+// tensor maps.  Kernel: one persistent CTA per SM, 10 warps: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA
+// issuer (one elected lane), warps 2..9 = epilogue (tcgen05.ld 32x32b -> fma(-2, acc, ||c||^2) -> global, per-vector
 // max |U| for K3's pre-filter slack).  Tile = 128 vectors x 256 entries (one codebook) x K = d <= 128; the A images of an
 // M-tile stay in shared memory for all m codebooks; two 256-column TMEM accumulators let the epilogue of codebook j
 // overlap the MMAs of codebook j+1.
@@ -108,6 +108,18 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 32 lanes x 32 consecutive 32-bit columns of TMEM -> 32 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t (&r)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor: start address >> 4, LBO (ignored for swizzled K-major) = 1,
 // SBO = 1024 bytes (8 rows x 128 B) >> 4, descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t tc_desc(uint32_t smem_addr) {
@@ -128,7 +140,7 @@ struct UnaryTcParams {
   int ntiles;
 };
 
-__global__ void __launch_bounds__(192, 1) unary_tc_kernel(UnaryTcParams p) {
+__global__ void __launch_bounds__(320, 1) unary_tc_kernel(UnaryTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // [A: KB x 2 x 16 KB][B: KB x 2 x 32 KB] (1024-byte aligned images), then barriers
   const uint32_t smem0 = (tc_smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(192, 1) unary_tc_kernel(UnaryTcParams p) {
     }
     for (int b = 0; b < 2; b++) {
       mbar_init(bar_t_full(b), 1);
-      mbar_init(bar_t_empty(b), 4);                                  // one arrival per epilogue warp
+      mbar_init(bar_t_empty(b), 8);                                  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,8 +238,10 @@ __global__ void __launch_bounds__(192, 1) unary_tc_kernel(UnaryTcParams p) {
       }
     }
   } else {
-    // ===== epilogue: warp w reads TMEM lanes 32*(w%4).. = rows of the tile =====
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps; warp w may only read TMEM lanes 32*(w%4).. (= 32 rows of the tile), so two warps share a
+    // lane quarter and split the 256 columns.  The tcgen05.ld of the next 32-column chunk is in flight while the current
+    // one is scaled, biased and stored =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
     uint32_t t_phase[2] = {0, 0};
     uint32_t tile = 0;
     for (int64_t mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
@@ -239,32 +253,25 @@ __global__ void __launch_bounds__(192, 1) unary_tc_kernel(UnaryTcParams p) {
         mbar_wait(bar_t_full(buf), t_phase[buf]);
         t_phase[buf] ^= 1;
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * kTcN;
-        float* dst = p.U + (size_t)l * p.mh + (size_t)nt * kTcN;
-        const float* nr = p.nrm + (size_t)nt * kTcN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < kTcN; c0 += 32) {
-          uint32_t r[32];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-              : "r"(taddr + c0));
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * kTcN + half * (kTcN / 2);
+        float* dst = p.U + (size_t)l * p.mh + (size_t)nt * kTcN + half * (kTcN / 2);
+        const float* nr = p.nrm + (size_t)nt * kTcN + half * (kTcN / 2);
+        uint32_t r[2][32];
+        tmem_ld32(r[0], taddr);
+#pragma unroll
+        for (int ch = 0; ch < kTcN / 2 / 32; ch++) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ch + 1 < kTcN / 2 / 32) tmem_ld32(r[(ch + 1) & 1], taddr + (ch + 1) * 32);
           if (l < p.n) {
 #pragma unroll
             for (int e = 0; e < 32; e += 4) {
-              const float4 nv = __ldg(reinterpret_cast<const float4*>(nr + c0 + e));
+              const float4 nv = __ldg(reinterpret_cast<const float4*>(nr + ch * 32 + e));
               float4 o;
-              o.x = fmaf(-2.0f, __uint_as_float(r[e]), nv.x);
-              o.y = fmaf(-2.0f, __uint_as_float(r[e + 1]), nv.y);
-              o.z = fmaf(-2.0f, __uint_as_float(r[e + 2]), nv.z);
-              o.w = fmaf(-2.0f, __uint_as_float(r[e + 3]), nv.w);
-              *reinterpret_cast<float4*>(dst + c0 + e) = o;
+              o.x = fmaf(-2.0f, __uint_as_float(r[ch & 1][e]), nv.x);
+              o.y = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 1]), nv.y);
+              o.z = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 2]), nv.z);
+              o.w = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 3]), nv.w);
+              *reinterpret_cast<float4*>(dst + ch * 32 + e) = o;
               mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
               bad |= (o.x != o.x) | (o.y != o.y) | (o.z != o.z) | (o.w != o.w);
             }
@@ -274,7 +281,8 @@ __global__ void __launch_bounds__(192, 1) unary_tc_kernel(UnaryTcParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_t_empty(buf));
       }
-      if (p.umax && l < p.n) p.umax[l] = __float_as_uint(bad ? __int_as_float(0x7f800000) : mx);
+      // two warps hold parts of a row: combine with atomicMax on the float bits (non-negative floats order like integers)
+      if (p.umax && l < p.n) atomicMax(p.umax + l, __float_as_uint(bad ? __int_as_float(0x7f800000) : mx));
     }
   }
   tc_fence_before();
@@ -326,7 +334,7 @@ int unary_tc_launch(const float* X, const DevBuf& Cp, const float* nrm, float* U
   const size_t smem = (size_t)KB * 2 * (kTcM * 128 + kTcN * 128) + 1024;
   RYL_CUDA(cudaFuncSetAttribute(unary_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(mtiles, sm_count());
-  RYL_LAUNCH(unary_tc_kernel, grid, 192, smem, s, p);
+  RYL_LAUNCH(unary_tc_kernel, grid, 320, smem, s, p);
   return RAYUELA_OK;
 }
 }  // namespace ryl

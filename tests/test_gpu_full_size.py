@@ -68,6 +68,30 @@ def test_icm_1M_subranges_match_oracle_and_shards_agree(env, base, monkeypatch):
     assert torch.equal(rb.core.encode_icm(X, C, B0, 0, icm, npert, True, seed=77)["B"], B0)
 
 
+def test_icm_1M_timed_configuration_ilsiter32(env, base):
+    """The TIMED configuration (configs[2]: 1M x 128, m = 8, ilsiter = 32 as src/LSQ_GPU.jl:352 uses for the base set):
+    sub-ranges against the oracle, and the three ways of running it -- device arrays (one chunk), host arrays (chunk
+    pipeline on alternating streams with overlapped uploads), two shards inside one process -- give the same bits."""
+    rb, torch = env
+    X, C, B0 = base
+    n, m = B0.shape
+    ils, icm, npert = 32, 4, 4
+    dev_run = rb.core.encode_icm(X, C, B0, ils, icm, npert, True, seed=2024)["B"].cpu().numpy()
+    Xh, Ch, B0h = X.cpu().numpy(), C.cpu().numpy(), B0.cpu().numpy()
+    for s in (123_456, n - 1024):
+        want = orc.encode_icm(Xh[s:s + 1024], Ch, B0h[s:s + 1024], ils, icm, npert, True, seed=2024, g0=s,
+                              use_ref_step=orc.have_ref())
+        assert np.array_equal(dev_run[s:s + 1024], want["B"]), s
+    host_run = rb.core.encode_icm(Xh, Ch, B0h, ils, icm, npert, True, seed=2024)["B"]
+    assert np.array_equal(host_run, dev_run)
+    rb.init([0, 0])
+    try:
+        two = rb.core.encode_icm(Xh, Ch, B0h, ils, icm, npert, True, seed=2024)["B"]
+    finally:
+        rb.init(None)
+    assert np.array_equal(two, dev_run)
+
+
 @pytest.mark.parametrize("m", [8, 16])
 def test_scan_10k_by_1M_properties(env, m):
     rb, torch = env
