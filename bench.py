@@ -659,7 +659,7 @@ def parity_subrange(cfg, parity_in, g0, count=1536):
     """Untimed: the oracle (fixed-order restatement + the reference's compiled `condition`) encodes `count` vectors
     of the TIMED workload at the timed ilsiter, and the GPU's codes for the same global indices must be identical."""
     from oracle import oracle as orc
-    orc.build()
+    force_host_threads()                       # also under torchrun (OMP_NUM_THREADS=1): the oracle is OpenMP-parallel
     Xs, Cs, B0s, got, off = parity_in
     want = orc.encode_icm(Xs, Cs, B0s, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0 + off,
                           use_ref_step=orc.have_ref())
