@@ -168,36 +168,39 @@ __device__ __forceinline__ uint64_t lds64(uint32_t addr) {
 }
 
 // Block-wide radix select over c distinct 64-bit keys in shared memory: returns the k-th smallest key
-// (1 <= k <= c).  Eight 8-bit passes from the most significant byte; per pass a 256-bin histogram of the keys
-// that match the prefix decided so far (lanes with equal digits are aggregated with match.any so the all-equal
-// leading bytes of similar distances cost one shared atomic per warp), then warp 0 picks the bin holding rank k.
-__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int c, int k, int* hist, int* sel) {
-  const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x;
-  // Leading bytes shared by all keys (same exponent / high mantissa for similar distances) need no pass:
-  // OR of (key ^ buf[0]) over the block tells the first byte where any two keys differ.
+// (1 <= k <= c <= 8192).  Eight 8-bit passes from the most significant byte, skipping the leading bytes all keys share;
+// per pass a 256-bin histogram of the keys that match the prefix decided so far, then EVERY warp finds the bin holding
+// rank k by itself (same histogram, same answer) -- so a pass costs ONE block barrier: the histograms rotate through
+// three buffers (pass p adds into buffer p % 3 and zeroes buffer (p+1) % 3, whose last readers finished before the
+// previous barrier).  Bins are 16-bit counters, two per word (c <= 8192 cannot carry into the neighbour).
+// hist: 3 x 128 words.  Replaces a 3-barrier-per-pass version whose serial bin search by warp 0 made the other 15 warps
+// wait (ncu r1, k = 1000: 22 % of the samples of the scan kernel sat in this function).
+__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int c, int k, uint32_t* hist) {
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nt = blockDim.x;
+  // first byte where any two keys differ: per-warp OR of (key ^ buf[0]) parked in buffer 2, combined by everyone
   uint64_t diff = 0;
   const uint64_t k0 = buf[0];
   for (int t = tid; t < c; t += nt) diff |= buf[t] ^ k0;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) diff |= __shfl_xor_sync(0xffffffffu, diff, off);
-  if (tid == 0) {
-    sel[2] = 0;
-    sel[3] = 0;
+  const uint32_t dlo = __reduce_or_sync(0xffffffffu, (uint32_t)diff), dhi = __reduce_or_sync(0xffffffffu, (uint32_t)(diff >> 32));
+  if (lane == 0) {
+    hist[256 + 2 * w] = dlo;
+    hist[256 + 2 * w + 1] = dhi;
   }
+  if (tid < 128) hist[tid] = 0;                                  // buffer 0 for the first pass
   block_sync();
-  if (lane == 0 && diff) {
-    atomicOr(&sel[2], (int)(uint32_t)diff);
-    atomicOr(&sel[3], (int)(uint32_t)(diff >> 32));
+  {
+    const uint32_t v = hist[256 + lane];                          // 16 warps x 2 words
+    const uint32_t lo = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : v), hi = __reduce_or_sync(0xffffffffu, (lane & 1) ? v : 0u);
+    diff = ((uint64_t)hi << 32) | lo;
   }
-  block_sync();
-  diff = ((uint64_t)(uint32_t)sel[3] << 32) | (uint32_t)sel[2];
-  const int first = diff ? (__clzll((long long)diff) >> 3) : 8;       // first pass that can discriminate
+  const int first = diff ? (__clzll((long long)diff) >> 3) : 8;
   uint64_t prefix = first ? (k0 >> (64 - 8 * first)) : 0;
   int krem = k;
   for (int pass = first; pass < 8; pass++) {
     const int shift = 56 - 8 * pass;
-    if (tid < 256) hist[tid] = 0;
-    block_sync();
+    uint32_t* h = hist + ((pass - first) % 3) * 128;
+    uint32_t* hz = hist + ((pass - first + 1) % 3) * 128;
+    if (tid < 128) hz[tid] = 0;
     if (pass == first) {
       // the first discriminating byte usually takes few distinct values: aggregate equal digits per warp
       for (int t0 = 0; t0 < c; t0 += nt) {        // uniform trip count: match.any needs converged warps
@@ -205,43 +208,48 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* buf, int 
         const bool act = t < c;
         const uint32_t digit = act ? (uint32_t)(buf[t] >> shift) & 255u : 256u + lane;
         const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-        if (act && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], __popc(peers));
+        if (act && lane == __ffs(peers) - 1) atomicAdd(&h[digit >> 1], (uint32_t)__popc(peers) << (16 * (digit & 1)));
       }
     } else {
       for (int t = tid; t < c; t += nt) {
         const uint64_t key = buf[t];
-        if ((key >> (shift + 8)) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1);
-      }
-    }
-    block_sync();
-    if (tid < 32) {
-      int loc[8], sum = 0;
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        loc[i] = hist[lane * 8 + i];
-        sum += loc[i];
-      }
-      int inc = sum;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        int v = __shfl_up_sync(0xffffffffu, inc, off);
-        if (lane >= off) inc += v;
-      }
-      int run = inc - sum;
-      if (run < krem && krem <= inc) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          if (run < krem && krem <= run + loc[i]) {
-            sel[0] = lane * 8 + i;
-            sel[1] = krem - run;
-          }
-          run += loc[i];
+        if ((key >> (shift + 8)) == prefix) {
+          const uint32_t digit = (uint32_t)(key >> shift) & 255u;
+          atomicAdd(&h[digit >> 1], 1u << (16 * (digit & 1)));
         }
       }
     }
     block_sync();
-    prefix = (prefix << 8) | (uint32_t)sel[0];
-    krem = sel[1];
+    int loc[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t v = h[lane * 4 + i];
+      loc[2 * i] = (int)(v & 0xFFFFu);
+      loc[2 * i + 1] = (int)(v >> 16);
+      sum += loc[2 * i] + loc[2 * i + 1];
+    }
+    int inc = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += v;
+    }
+    int run = inc - sum, bin = 0, newk = 0;
+    const bool mine = run < krem && krem <= inc;
+    if (mine) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (run < krem && krem <= run + loc[i]) {
+          bin = lane * 8 + i;
+          newk = krem - run;
+        }
+        run += loc[i];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    krem = __shfl_sync(0xffffffffu, newk, src);
+    prefix = (prefix << 8) | (uint32_t)bin;
   }
   return prefix;
 }
@@ -332,9 +340,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int cnt_s[16];
   __shared__ float tau_s[16];
+  __shared__ uint64_t taukey_s[16];  // the threshold as a (dist, id) key: every key seen so far that is <= it is in the buffer
   __shared__ uint64_t lb_s[16];
   __shared__ __align__(8) uint64_t mbar;
-  __shared__ int hist_s[256];
+  __shared__ uint32_t hist_s[3 * 128];   // three rotating histograms of 256 16-bit bins (block_radix_select)
   __shared__ int sel_s[4];
   __shared__ int flag_s;     // some query's buffer needs compacting (set by the appending thread)
   __shared__ int nfin_s;     // warps that have finished their chunks
@@ -367,6 +376,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     cnt_s[tid] = 0;
     // padded dummy queries of the last tile (all-zero LUT) must never append: their threshold is -inf for good
     tau_s[tid] = (q0 + tid < p.nq) ? p.tau0 : -__int_as_float(0x7f800000);
+    taukey_s[tid] = make_key(p.tau0, 0xFFFFFFFFu);
     lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
   }
   if (SPEC && p.pass == 1 && p.redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // redo launch: nothing to redo
@@ -459,6 +469,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       }
     }
   };
+  // Compaction keeps the r = spec_rank() <= k smallest keys and makes the r-th the new threshold (tau_s as a distance for
+  // the filter, taukey_s as a full key for the invariant: every key seen so far that is <= taukey_s is in the buffer --
+  // later arrivals with key <= taukey_s pass the float filter, compactions keep everything <= the new, smaller key).
+  // Without speculation r = k and this is the plain "keep the k best".  ONE selection per compaction.
   auto warp_sort_keep = [=](int q) -> int {
     const int c = cnt_s[q];
     uint64_t* cq = cand + (size_t)q * p.cap;
@@ -466,14 +480,15 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     for (int t = lane; t < np2; t += 32) wslice[t] = t < c ? cq[t] : ~0ull;
     __syncwarp();
     warp_bitonic(wslice, np2);
-    const int keep = min(c, p.k);
-    if (c > p.k)
+    const int r = spec_rank();
+    const int keep = c >= p.k ? r : c;
+    if (c > keep)
       for (int t = lane; t < keep; t += 32) cq[t] = wslice[t];
     if (lane == 0) {
       cnt_s[q] = keep;
       if (c >= p.k) {
-        const int r = spec_rank();
         tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(wslice[r - 1] >> 32)));
+        taukey_s[q] = min(taukey_s[q], wslice[r - 1]);
         if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
       }
     }
@@ -483,11 +498,11 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     const int c = cnt_s[q];
     return c > (SPEC ? min(p.piggy, softq_s[q]) : p.piggy) || (c >= p.k && tau_s[q] == __int_as_float(0x7f800000));
   };
-  // exactness check of a finished query (see spec_rank): kth = k-th smallest key of the final buffer, c its size
+  // exactness check of a finished query (see spec_rank): kth = k-th smallest key of the final buffer, c its size.
+  // kth <= taukey_s  =>  every key <= kth ever seen is in the buffer  =>  the buffer's k smallest are the true top-k.
   auto verify = [=](int q, int c, uint64_t kth) {
     if (!SPEC) return;
-    const float t = tau_s[q];
-    if (c >= p.k ? ordered_to_f32((uint32_t)(kth >> 32)) > t : t < __int_as_float(0x7f800000)) fail_s = 1;
+    if (c >= p.k ? kth > taukey_s[q] : tau_s[q] < __int_as_float(0x7f800000)) fail_s = 1;
   };
 
   auto compact = [=](int q) {
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         if (tid == 0) {
           for (int i = 1; i < kScanWarps; i++) mx = max(mx, sortbuf[i]);
           tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(mx >> 32)));
+          taukey_s[q] = min(taukey_s[q], mx);
         }
         block_sync();
       }
@@ -515,10 +531,11 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       for (int t = tid; t < np2; t += NT) sortbuf[t] = t < c ? cq[t] : ~0ull;
       block_sync();
       block_bitonic_sort(sortbuf, np2);
-      for (int t = tid; t < p.k; t += NT) cq[t] = sortbuf[t];
+      for (int t = tid; t < r; t += NT) cq[t] = sortbuf[t];
       if (tid == 0) {
-        cnt_s[q] = p.k;
+        cnt_s[q] = r;
         tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(sortbuf[r - 1] >> 32)));
+        taukey_s[q] = min(taukey_s[q], sortbuf[r - 1]);
         if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
       }
       block_sync();
@@ -526,22 +543,18 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     }
     for (int t = tid; t < c; t += NT) sortbuf[t] = cq[t];
     block_sync();
-    const uint64_t pivot = block_radix_select(sortbuf, c, p.k, hist_s, sel_s);
-    uint64_t pivot_r = pivot;
-    if (SPEC && r < p.k) {
-      block_sync();
-      pivot_r = block_radix_select(sortbuf, c, r, hist_s, sel_s);
-    }
+    const uint64_t pivot = block_radix_select(sortbuf, c, r, hist_s);
     block_sync();
     if (tid == 0) sel_s[2] = 0;
     block_sync();
     for (int t = tid; t < c; t += NT) {
       const uint64_t key = sortbuf[t];
-      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly k keys (keys are distinct)
+      if (key <= pivot) cq[atomicAdd(&sel_s[2], 1)] = key;     // exactly r keys (keys are distinct)
     }
     if (tid == 0) {
-      cnt_s[q] = p.k;
-      tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(pivot_r >> 32)));
+      cnt_s[q] = r;
+      tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(pivot >> 32)));
+      taukey_s[q] = min(taukey_s[q], pivot);
       if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
     }
     block_sync();

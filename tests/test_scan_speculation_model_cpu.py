@@ -1,7 +1,8 @@
 """CPU model of scanx_kernel's verified speculative threshold (csrc/linscan.cu): keys stream by in periods, keys <= tau
-are appended, a compaction keeps the k smallest and lowers tau to the key of rank r = x + 5.5 sqrt(x) + 15, x = k*f.
-Invariant under test: thresholds only decrease and every key <= the final threshold stays in the buffer unless k smaller
-ones are, so  k-th smallest of the final buffer <= final tau  ==>  the buffer's k smallest ARE the true top-k;
+are appended, a compaction keeps the r smallest -- r = x + 5.5 sqrt(x) + 15, x = k*f, or k without speculation -- and
+makes the r-th the new threshold (ONE selection per compaction).
+Invariant under test: thresholds only decrease and every key <= the current threshold that has been seen is in the
+buffer, so  k-th smallest of the final buffer <= final tau  ==>  the buffer's k smallest ARE the true top-k;
 and when the stream is ordered best-first the check must fail (the kernel then redoes the block exactly)."""
 import numpy as np
 import pytest
@@ -22,7 +23,7 @@ def stream_topk(keys, k, soft, period=256, spec=True):
                 r = int(x + 5.5 * np.sqrt(x) + 15.125) + 1
                 r = r if (spec and r * 4 < k * 3) else k
                 tau = min(tau, buf[r - 1])
-                buf = buf[:k]
+                buf = buf[:r]
             elif len(buf) == k:
                 tau = min(tau, buf[-1])
     buf.sort()
