@@ -326,6 +326,7 @@ struct ScanXParams {
   int64_t n, nchunks, chunks_per_slice;
   int nq, k, cap, soft;
   int piggy;             // a service() also compacts every buffer already past this many keys
+  int spec_soft;         // soft limit while a speculative threshold (r < k) is in force
   float tau0;            // initial threshold (+inf; a finite value is a measurement aid, RAYUELA_B200_SCAN_TAU0)
   int spec;              // speculative thresholds on (verified at the end; a failed block is redone in pass 1)
   int pass;              // 0: main launch; 1: redo launch -- only blocks whose redo flag is set run, without speculation
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       if (c >= p.k) {
         tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(wslice[r - 1] >> 32)));
         taukey_s[q] = min(taukey_s[q], wslice[r - 1]);
-        if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
+        if (SPEC) softq_s[q] = r < p.k ? min(p.soft, p.spec_soft) : p.soft;
       }
     }
     return keep;
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         cnt_s[q] = r;
         tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(sortbuf[r - 1] >> 32)));
         taukey_s[q] = min(taukey_s[q], sortbuf[r - 1]);
-        if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
+        if (SPEC) softq_s[q] = r < p.k ? min(p.soft, p.spec_soft) : p.soft;
       }
       block_sync();
       return;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       cnt_s[q] = r;
       tau_s[q] = fminf(tau_s[q], ordered_to_f32((uint32_t)(pivot >> 32)));
       taukey_s[q] = min(taukey_s[q], pivot);
-      if (SPEC) softq_s[q] = r < p.k ? min(p.soft, 2 * p.k + X::ADDS) : p.soft;
+      if (SPEC) softq_s[q] = r < p.k ? min(p.soft, p.spec_soft) : p.soft;
     }
     block_sync();
   };
@@ -1123,7 +1124,11 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       p.k = kp;
       p.cap = cap;
       p.soft = soft;
-      p.piggy = kp + (soft - kp) / 2;   // a service() also compacts buffers already half-way to the soft limit
+      p.piggy = kp + (soft - kp) / 6;   // a service() also compacts every buffer already a sixth of the way to the soft limit
+                                        // (sweep at k = 16 / 100 / 1000 / 4000, profiles/r2_scan_knob_sweeps.txt: +2..5 % over 1/2)
+      p.spec_soft = 2 * kp + adds;
+      if (const char* e = getenv("RAYUELA_B200_SCAN_SPECSOFT")) p.spec_soft = std::max(kp, std::min(atoi(e), soft));   // tuning knob
+      if (const char* e = getenv("RAYUELA_B200_SCAN_PIGGY")) p.piggy = std::max(kp, std::min(atoi(e), soft));          // tuning knob
       p.tau0 = std::numeric_limits<float>::infinity();
       if (const char* e = getenv("RAYUELA_B200_SCAN_TAU0")) p.tau0 = (float)atof(e);   // measurement aid only
       // speculative thresholds (verified; see scanx_kernel): worth it once a compaction is more than a warp's work
