@@ -7,7 +7,7 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "librayuela_b200.so")
+LIB_PATH = os.environ.get("RAYUELA_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "librayuela_b200.so")
 
 DEVICE_PTRS = 1
 FAST_UNARIES = 2
