@@ -461,7 +461,13 @@ def run_ours(args, cfg):
     e2e_steps = max(1, min(args.steps, 3))
     icm_e2e_ms = wall_steps(icm_e2e, e2e_steps, 1, dist, device) / e2e_steps
     same = bool(np.array_equal(Bh, Bwork.cpu().numpy()))
-    del Xh
+    # the same call from PAGEABLE host arrays -- what a Julia caller passes (Julia arrays are not pinned)
+    Xp, Cp_, Bp = np.array(Xh), np.array(Ch), np.array(B0h)
+
+    def icm_e2e_pageable():
+        core.encode_icm(Xp, Cp_, Bp, cfg["ilsiter"], cfg["icmiter"], cfg["npert"], True, seed=2024, g0=g0)
+    icm_e2e_pageable_ms = wall_steps(icm_e2e_pageable, 2, 1, dist, device) / 2
+    del Xh, Xp
 
     # ---- path (2): linscan_lsq over the encoded base -----------------------------------------------------------
     Cm = C.reshape(m, H, d)
@@ -640,7 +646,9 @@ def run_ours(args, cfg):
         "parity_checked": parity,
         "icm": {"vectors_per_sec": icm_value, "vector_ils_iters_per_sec": icm_value * cfg["ilsiter"],
                 "ms_per_step": icm_per, "setup_ms(K0+K1+K2+cost)": setup_ms, "qerror_before": qerr0,
-                "qerror_after": qerr, "e2e_vectors_per_sec": world * n / (icm_e2e_ms * 1e-3), "roofline": icm_roof,
+                "qerror_after": qerr, "e2e_vectors_per_sec": world * n / (icm_e2e_ms * 1e-3),
+                "e2e_pageable_host_arrays_vectors_per_sec": world * n / (icm_e2e_pageable_ms * 1e-3),
+                "e2e_pageable_ms_per_step": icm_e2e_pageable_ms, "roofline": icm_roof,
                 "cpu_baseline": cpu, "gpu_launches": icm_launches, "fast_mode": fast_obj},
         "linscan": {"metric": "linscan_lsq_queries_per_sec", "queries_per_sec": scan_value, "recall_at_1": recall1,
                     "k": k, "nq": nq, "n_base_total": world * n, "ms_per_step": scan_per,

@@ -1211,16 +1211,19 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
   if (piped) {
     RYL_CUDA(cudaEventRecord(ev_setup.e, s));               // allocations + tables are ordered before the other streams
     RYL_CUDA(cudaStreamWaitEvent(s_alt, ev_setup.e, 0));
-    if (!dev) {
-      RYL_CUDA(cudaStreamWaitEvent(s_copy, ev_setup.e, 0));
-      for (int c = 0; c < nchunks; c++) {
-        const int64_t l0 = (int64_t)c * chunk, nc = std::min(chunk, n - l0);
-        RYL_CUDA(cudaMemcpyAsync(const_cast<float*>(x_in.d) + (size_t)l0 * d, X + (size_t)l0 * d,
-                                 (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, s_copy));
-        RYL_CUDA(cudaEventRecord(ev_up[c].e, s_copy));
-      }
-    }
+    if (!dev) RYL_CUDA(cudaStreamWaitEvent(s_copy, ev_setup.e, 0));
   }
+  // upload of chunk c on the copy stream.  Chunk c+1 is enqueued right AFTER chunk c's kernels: with pinned host memory
+  // the order would not matter, but Julia arrays are pageable and a pageable cudaMemcpyAsync blocks the host while it
+  // stages -- this way that staging overlaps the kernels already launched
+  auto upload_chunk = [&](int c) -> int {
+    const int64_t l0 = (int64_t)c * chunk, nc = std::min(chunk, n - l0);
+    RYL_CUDA(cudaMemcpyAsync(const_cast<float*>(x_in.d) + (size_t)l0 * d, X + (size_t)l0 * d,
+                             (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, s_copy));
+    RYL_CUDA(cudaEventRecord(ev_up[c].e, s_copy));
+    return RAYUELA_OK;
+  };
+  if (piped && !dev) RYL_TRY(upload_chunk(0));
   for (int c = 0; c < nchunks; c++) {
     const int64_t l0 = (int64_t)c * chunk;
     const int64_t nc = std::min(chunk, n - l0);
@@ -1273,6 +1276,7 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
 #undef CALL
     RYL_TRY(rc);
     if (stats) RYL_CUDA(cudaEventRecord(t_k[c].e, cs));
+    if (piped && !dev && c + 1 < nchunks) RYL_TRY(upload_chunk(c + 1));
   }
   if (piped) {                                              // join: everything below is ordered after both streams
     RYL_CUDA(cudaEventRecord(ev_alt_done.e, s_alt));

@@ -79,3 +79,23 @@ def test_fast_lut_scan(rb, m, k):
     agree = np.mean([len(set(a) & set(b)) / k for a, b in zip(jf, i0)])
     print("fast LUT: top-%d list overlap %.5f, top-1 agreement %.4f" % (k, agree, (jf[:, 0] == i0[:, 0]).mean()))
     assert agree >= 0.99
+
+
+def test_fast_mode_falls_back_to_exact_when_unsupported(rb):
+    """d > 128 is outside the tensor-core kernel's tile: the flag is ignored and the exact kernels run (same bits)."""
+    X, C, B = _data(700, 160, 4, seed=1)
+    a = rb.core.get_unaries(X, C, 4)
+    b = rb.core.get_unaries(X, C, 4, fast=True)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    ea = rb.core.encode_icm(X, C, B, 2, 2, 4, True, seed=5)["B"]
+    eb = rb.core.encode_icm(X, C, B, 2, 2, 4, True, seed=5, fast=True)["B"]
+    assert np.array_equal(ea, eb)
+
+
+def test_phase_timers_through_the_abi(rb):
+    """rayuela_encode_icm_timings: CUDA-event phase times of the last call that asked for stats."""
+    X, C, B = _data(20000, 64, 8, seed=2)
+    rb.core.encode_icm(X, C, B, 4, 4, 4, True, seed=1, want_stats=True)
+    t = rb.core.last_icm_timings()
+    assert t["total"] > 0 and t["icm"] > 0 and t["unaries"] > 0 and t["setup"] >= 0
+    assert t["icm"] <= t["total"] * 1.01 and t["unaries"] + t["setup"] <= t["total"] * 1.01      # one chunk: no overlap
