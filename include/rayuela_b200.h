@@ -145,7 +145,8 @@ void linscan_aqd_cq_query_extra_byte(float* dists, int* idx, unsigned char* code
 #define RAYUELA_SCAN_PQ 2  /* lut = per-subspace ||c-q||^2, ids 0-based (linscan_aqd.cpp:37-102) */
 typedef struct rayuela_index rayuela_index;
 
-/* id_offset is added to every returned id (global ids for a base shard of a multi-GPU index). */
+/* id_offset is added to every returned id (global ids for a base shard of a multi-GPU index).
+ * h: entries per codebook, 1..256 like the reference's scans (pairwise_byte.cpp takes h; codes are bytes). */
 int rayuela_index_create(rayuela_index** out, int kind, const uint8_t* codes, const float* dbnorms, int64_t n,
                          int m, int h, int64_t id_offset, unsigned flags, void* stream);
 /* codebooks: d-by-(m*h) (LSQ/CQ) or sub-by-h-by-m (PQ, d = m*sub).  dists/idx: k-by-nq.

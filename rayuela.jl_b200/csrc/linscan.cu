@@ -26,20 +26,23 @@ static constexpr int kH = 256;
 template <int KIND>
 __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ queries, const float* __restrict__ cb,
                                                   float* __restrict__ lut, int nq, int d, int len, int mh,
-                                                  int tiled, int* __restrict__ bad) {
+                                                  int tiled, int* __restrict__ bad, int h) {
   constexpr int CH = 64;
   __shared__ float cs[32][CH + 1];
   __shared__ float qs[32][CH];
-  const int e0 = blockIdx.x * 32, q0 = blockIdx.y * 32;
+  // blockIdx.x = (codebook kk, 32-entry group inside it): a block never straddles two codebooks, for any h <= 256
+  const int gph = (h + 31) >> 5, kk = blockIdx.x / gph, c0 = (blockIdx.x % gph) * 32;
+  const int e0 = kk * h + c0, q0 = blockIdx.y * 32;
+  const int nvalid = min(32, h - c0);                    // entries of this block that exist
   const int e = threadIdx.x & 31, qg = threadIdx.x >> 5;
-  const int qoff = (KIND == RAYUELA_SCAN_PQ) ? (e0 / kH) * len : 0;
+  const int qoff = (KIND == RAYUELA_SCAN_PQ) ? kk * len : 0;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int base = 0; base < len; base += CH) {
     const int chunk = min(CH, len - base);
     for (int i = threadIdx.x; i < 32 * CH; i += 256) {
       int r = i / CH, t = i % CH;
       if (t < chunk) {
-        cs[r][t] = cb[(size_t)(e0 + r) * len + base + t];
+        cs[r][t] = r < nvalid ? cb[(size_t)(e0 + r) * len + base + t] : 0.f;
         int q = min(q0 + r, nq - 1);
         qs[r][t] = queries[(size_t)q * d + qoff + base + t];
       }
@@ -66,19 +69,19 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     int q = q0 + qg + 8 * i;
-    if (q < nq) {
+    if (q < nq && e < nvalid) {
       // The scan restarts a lane's accumulator by multiplying it by zero, so one non-finite partial sum would turn
       // every later code of that lane into NaN.  Entries are therefore required to be finite and small enough that a
       // sum of 16 cannot overflow; a violation fails the whole search instead of silently dropping neighbours.
       if (!(fabsf(acc[i]) <= 1e37f)) *bad = 1;
       if (tiled == 1) {
         // layout of scanx_kernel<8>'s shared-memory tile (see there): [q/16][(q%16)/4][c][((q%4)/2)*8 + k][q%2]
-        const int ent = e0 + e, k = ent >> 8, c = ent & 255;
+        const int k = kk, c = c0 + e;
         lut[(size_t)(q >> 4) * 32768 + ((q & 15) >> 2) * 8192 + c * 32 + ((((q & 3) >> 1) * 8 + k) << 1) + (q & 1)] =
             acc[i];
       } else if (tiled == 2) {
         // scanx_kernel<16>: [q/8][(q%8)/2][c][k][q%2]
-        const int ent = e0 + e, k = ent >> 8, c = ent & 255;
+        const int k = kk, c = c0 + e;
         lut[(size_t)(q >> 3) * 32768 + ((q & 7) >> 1) * 8192 + c * 32 + (k << 1) + (q & 1)] = acc[i];
       } else {
         lut[(size_t)q * mh + e0 + e] = acc[i];
@@ -941,7 +944,7 @@ extern "C" int rayuela_index_create(rayuela_index** out, int kind, const uint8_t
                                     int64_t n, int m, int h, int64_t id_offset, unsigned flags, void* stream) {
   RYL_ARG(out != nullptr, "index_create: out is null");
   RYL_ARG(kind >= 0 && kind <= 2, "index_create: unknown kind");
-  RYL_ARG(h == kH, "index_create: only h = 256 is supported (one byte per codebook)");
+  RYL_ARG(h >= 1 && h <= kH, "index_create: h must be in 1..256 (one byte per codebook)");
   RYL_ARG(m >= 1 && m <= 16, "index_create: m must be in 1..16");
   RYL_ARG(n >= 1, "index_create: n must be positive");
   RYL_ARG(codes != nullptr, "index_create: codes is null");
@@ -1018,9 +1021,9 @@ static int merge_lists(const uint64_t* keys, const float* din, const int32_t* ii
 // all arrays on the current device; bad: device int, set when a LUT entry is unusable (see lut_kernel)
 static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* cb_dev, int nq, int d, int k,
                             float* d_dev, int32_t* i_dev, int* bad, cudaStream_t s, bool fast_lut = false) {
-  const int m = ix->m, mh = m * kH;
+  const int m = ix->m, h = ix->h, mh = m * h;
   // opt-in: tensor-core LUT for the LSQ scan (codebooks split / packed once per search)
-  fast_lut = fast_lut && ix->kind == RAYUELA_SCAN_LSQ && unary_tc_supported(d, mh);
+  fast_lut = fast_lut && ix->kind == RAYUELA_SCAN_LSQ && h == kH && unary_tc_supported(d, mh);
   DevBuf Cp_d, zero_d;
   if (fast_lut) {
     RYL_TRY(unary_tc_pack_codebooks(cb_dev, d, mh, &Cp_d, s));
@@ -1051,8 +1054,8 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
     const int qtiles = (nqc + QT - 1) / QT;
     DevBuf lut, lb;
     RYL_TRY(lut.alloc((size_t)qtiles * kLutTileBytes, s));
-    if (m < period || nqc % QT) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m
-    dim3 lg(mh / 32, (nqc + 31) / 32);
+    if (m < period || nqc % QT || h < kH) RYL_CUDA(cudaMemsetAsync(lut.p, 0, lut.bytes, s));   // zero rows for k >= m, c >= h
+    dim3 lg(m * ((h + 31) / 32), (nqc + 31) / 32);
     const float* qptr = q_dev + (size_t)qb * d;
     const int tiled = period == 16 ? 2 : 1;
     if (fast_lut) {
@@ -1061,11 +1064,11 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       RYL_TRY(unary_tc_launch(qptr, Cp_d, zero_d.as<float>(), rowmajor.as<float>(), nullptr, nqc, d, mh, s));
       RYL_LAUNCH(lut_relayout_kernel, sm_count() * 8, 256, 0, s, rowmajor.as<float>(), lut.as<float>(), nqc, mh, tiled, bad);
     } else if (ix->kind == RAYUELA_SCAN_LSQ)
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_LSQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad, h);
     else if (ix->kind == RAYUELA_SCAN_CQ)
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_CQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad, h);
     else
-      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad);
+      RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad, h);
     if (k > kmax) RYL_TRY(lb.alloc((size_t)nqc * sizeof(uint64_t), s));
 
     for (int koff = 0; koff < k; koff += kmax) {
@@ -1194,7 +1197,7 @@ static int index_search_multi(rayuela_index* ix, const float* queries, const flo
       cudaStream_t s = ix->slots[i].stream;
       InArg<float> q_in, cb_in;
       RYL_TRY(q_in.bind(queries, (size_t)nq * d, false, s));
-      RYL_TRY(cb_in.bind(codebooks, (size_t)ix->m * kH * len, false, s));
+      RYL_TRY(cb_in.bind(codebooks, (size_t)ix->m * ix->h * len, false, s));
       DevBuf dl, il, bd;
       RYL_TRY(dl.alloc(per * sizeof(float), s));
       RYL_TRY(il.alloc(per * sizeof(int32_t), s));
@@ -1233,7 +1236,7 @@ extern "C" int rayuela_index_search(rayuela_index* ix, const float* queries, con
   RYL_ARG(ix != nullptr, "index_search: null index");
   RYL_ARG(nq >= 1 && d >= 1, "index_search: nq and d must be positive");
   RYL_ARG(k >= 1 && (int64_t)k <= ix->n, "index_search: k must be in 1..n");
-  const int m = ix->m, mh = m * kH;
+  const int m = ix->m, mh = m * ix->h;
   const bool pq = ix->kind == RAYUELA_SCAN_PQ;
   RYL_ARG(!pq || d % m == 0, "index_search: PQ scan needs d divisible by m");
   const int len = pq ? d / m : d;

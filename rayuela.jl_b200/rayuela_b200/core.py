@@ -206,15 +206,16 @@ def quantize_pq(X, Cpq, m):
 class Index:
     """Encoded base set resident on the GPU (rayuela_index_*): upload / re-layout once, scan many times."""
 
-    def __init__(self, kind, codes, dbnorms=None, id_offset=0):
+    def __init__(self, kind, codes, dbnorms=None, id_offset=0, h=H):
+        """h: entries per codebook (1..256; the codes are bytes either way)."""
         L = _lib.lib()
         n, m = codes.shape
         a = _Args()
         cp = a.inp(codes, np.uint8, (n, m))
         np_ = a.inp(dbnorms, np.float32, (n,)) if dbnorms is not None else None
-        h = ct.c_void_p()
-        check(L.rayuela_index_create(ct.byref(h), kind, cp, np_, n, m, H, id_offset, a.flags, a.stream))
-        self._h, self.kind, self.n, self.m, self.id_offset = h, kind, n, m, id_offset
+        hd = ct.c_void_p()
+        check(L.rayuela_index_create(ct.byref(hd), kind, cp, np_, n, m, h, id_offset, a.flags, a.stream))
+        self._h, self.kind, self.n, self.m, self.id_offset, self.h = hd, kind, n, m, id_offset, h
 
     def search(self, queries, codebooks, k, out=None, fast=False):
         """Top-k of every query.  fast=True (LSQ only): opt-in tensor-core LUT build, not bit-identical.  out=(dists, idx): preallocated (nq, k) float32 / int32 result arrays on the same
@@ -226,7 +227,7 @@ class Index:
         a = _Args()
         qp = a.inp(queries, np.float32, (nq, d))
         cols = d // self.m if self.kind == SCAN_PQ else d
-        cp = a.inp(codebooks, np.float32, (self.m * H, cols))
+        cp = a.inp(codebooks, np.float32, (self.m * self.h, cols))
         dev = _is_dev(queries)
         if out is not None:
             dists, idx = out
@@ -280,7 +281,7 @@ def c_linscan_aqd_query(B, Xq, centers, k):
     return dists, res
 
 
-def c_linscan_aqd_query_extra_byte(B, Xq, codebooks, dbnorms, k):
+def c_linscan_aqd_query_extra_byte(B, Xq, codebooks, dbnorms, k, h=H):
     """linscan_aqd_query_extra_byte as src/Linscan.jl:135-141 calls it (1-based ids)."""
     B, Xq, codebooks, dbnorms = _np(B, np.uint8), _np(Xq, np.float32), _np(codebooks, np.float32), \
         _np(dbnorms, np.float32)
@@ -289,7 +290,7 @@ def c_linscan_aqd_query_extra_byte(B, Xq, codebooks, dbnorms, k):
     dists = np.zeros((nq, k), dtype=np.float32)
     idx = np.zeros((nq, k), dtype=np.int32)
     _lib.lib().linscan_aqd_query_extra_byte(dists.ctypes.data, idx.ctypes.data, B.ctypes.data, Xq.ctypes.data,
-                                            codebooks.ctypes.data, dbnorms.ctypes.data, nq, n, m, H, d, k)
+                                            codebooks.ctypes.data, dbnorms.ctypes.data, nq, n, m, h, d, k)
     return dists, idx
 
 

@@ -178,7 +178,7 @@ def linscan_opq(B, X, C, b, R, k=10000):
 def linscan_lsq(B, X, C, dbnorms, R, k=10000):
     """linscan_lsq(B, X, C, dbnorms, R, k) -> dists, res (one-based)   (src/Linscan.jl:118-157)."""
     RX = np.asarray(R, dtype=np.float32).T @ np.asarray(X, dtype=np.float32)
-    ix = core.Index(SCAN_LSQ, _scan_codes(B), np.asarray(dbnorms, dtype=np.float32).reshape(-1))
+    ix = core.Index(SCAN_LSQ, _scan_codes(B), np.asarray(dbnorms, dtype=np.float32).reshape(-1), h=np.shape(C[0])[1])
     dists, idx = ix.search(_img(RX), _hcat(C), k)
     ix.free()
     return _out(dists, idx)
@@ -186,7 +186,7 @@ def linscan_lsq(B, X, C, dbnorms, R, k=10000):
 
 def linscan_cq(B, X, C, k=10000):
     """linscan_cq(B, X, C, k) -> dists, res (one-based)   (src/Linscan.jl:160-193)."""
-    ix = core.Index(SCAN_CQ, _scan_codes(B))
+    ix = core.Index(SCAN_CQ, _scan_codes(B), h=np.shape(C[0])[1])
     dists, idx = ix.search(_img(X), _hcat(C), k)
     ix.free()
     return _out(dists, idx)

@@ -208,3 +208,27 @@ def test_encoding_icm_any_h(rb, h, m, d):
     want0 = orc.encode_icm(X, C, B, 3, 2, 3, True, seed=21, g0=0, h=h)
     assert np.array_equal(Bj.T - 1, want0["B"]) and np.array_equal(oldB, Bj)          # oldB mutated, src/LSQ.jl:248
     assert abs(float(rb.qerror(_julia(X), Bj, Cj)) - orc.qerror(X, want0["B"], C, h)) < 1e-4 * orc.qerror(X, B, C, h)
+
+
+@pytest.mark.parametrize("kind,h,m,k", [(orc.LSQ, 64, 8, 10), (orc.CQ, 100, 4, 3), (orc.LSQ, 16, 16, 100), (orc.CQ, 255, 8, 1)])
+def test_linscan_any_h(rb, kind, h, m, k):
+    """The reference's extra_byte scans take h as an argument (deps/src/linscan_aqd_pairwise_byte.cpp:14-24,97-106):
+    codebooks with fewer than 256 entries scan bit-identically too (index, compat symbol and Julia-level API)."""
+    r = np.random.default_rng(h + m)
+    n, nq, d = 30_000, 21, 48
+    B = r.integers(0, h, (n, m), dtype=np.uint8)
+    Xq = r.standard_normal((nq, d)).astype(np.float32)
+    cb = r.standard_normal((m * h, d)).astype(np.float32)
+    nrm = r.standard_normal(n).astype(np.float32) if kind == orc.LSQ else None
+    d0, i0 = (orc.ref_linscan if orc.have_ref() else orc.linscan)(kind, B, Xq, cb, k, nrm, h=h)
+    ix = rb.core.Index(rb.core.SCAN_LSQ if kind == orc.LSQ else rb.core.SCAN_CQ, B, nrm, h=h)
+    dg, ig = ix.search(Xq, cb, k)
+    assert np.array_equal(ig, i0) and np.array_equal(bits(dg), bits(d0))
+    Cj = [_julia(cb[j * h:(j + 1) * h]) for j in range(m)]
+    if kind == orc.LSQ:
+        dj, ij = rb.linscan_lsq(_julia(B), _julia(Xq), Cj, nrm, np.eye(d, dtype=np.float32), k)
+        d2, i2 = rb.core.c_linscan_aqd_query_extra_byte(B, Xq, cb, nrm, k, h=h)
+        assert np.array_equal(i2, i0) and np.array_equal(bits(d2), bits(d0))
+    else:
+        dj, ij = rb.linscan_cq(_julia(B), _julia(Xq), Cj, k)
+    assert np.array_equal(ij.T.astype(np.int32), i0) and np.array_equal(bits(dj.T), bits(d0))
