@@ -50,8 +50,7 @@ def main():
     orc.build()
     dev = torch.device("cuda")
     n, d, m = args.n, 128, 8
-    cores = bench.host_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores, _ = bench.force_host_threads()          # OpenMP / BLAS pools at the host core count, verified
     X, _ = bench.make_data(n, 16, d, 1000, dev)
     C = bench.train_codebooks(X[:50000], m, dev)
     B = torch.randint(0, 256, (n, m), device=dev, dtype=torch.uint8)

@@ -18,12 +18,18 @@ module RayuelaB200
 export encoding_icm, encode_icm_cuda, veccost, qerror, quantize_pq, quantize_opq,
        linscan_pq, linscan_opq, linscan_lsq, linscan_cq, seed_b200!,
        quantize_norms, quantize_chainq, fast_bin_matmul, update_codebooks_fast_bin,
-       install!, init_devices!, shutdown_devices!
+       install!, init_devices!, shutdown_devices!, fast_unaries!, encode_icm_timings
 
 using Printf, Statistics, LinearAlgebra
 
 const librayuela_b200 = get(ENV, "RAYUELA_B200_LIB",
                             joinpath(@__DIR__, "..", "lib", "librayuela_b200.so"))
+
+# flags passed to rayuela_encode_icm: 0 = exact (bit-identical to the CPU path), 2 = RAYUELA_FAST_UNARIES (opt-in tcgen05
+# bf16x3 unaries; codes may differ on near-ties).  For the scans set ENV["RAYUELA_B200_FAST_LUT"] = "1" instead (their
+# exact-signature symbols have no flags argument).
+const ENCODE_FLAGS = Ref{Cuint}(0)
+fast_unaries!(on::Bool) = (ENCODE_FLAGS[] = on ? Cuint(2) : Cuint(0); nothing)
 
 const SEED = Ref{UInt64}(0)
 "Reproducible stream for the ILS perturbations / visiting orders (each encode call consumes one seed)."
@@ -67,7 +73,7 @@ function encoding_icm(X::Matrix{Float32}, oldB::Matrix{Int16}, C::Vector{Matrix{
     (Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cuchar}, Int64, Cint, Cint, Cint, Cint, Cint, Cint, Cint, UInt64, Int64,
      Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cint}, Cuint, Ptr{Cvoid}),
     X, hcat(C...), B, n, d, m, h, ilsiter, icmiter, npert, randord, next_seed(), 0,
-    C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, stats, 0, C_NULL))
+    C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, stats, ENCODE_FLAGS[], C_NULL))
   if V
     for i = 1:ilsiter                                                         # src/LSQ.jl:243-245
       @printf(" ILS iteration %d/%d done. %5.2f%% new codes are equal. %5.2f%% new codes are better.\n",
@@ -91,7 +97,7 @@ function encode_icm_cuda(RX::Matrix{Float32}, B::Matrix{Int16}, C::Vector{Matrix
     (Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cuchar}, Int64, Cint, Cint, Cint, Cint, Cint, Cint, Cint, UInt64, Int64,
      Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Cuchar}, Ptr{Cfloat}, Ptr{Cfloat}, Ptr{Cint}, Cuint, Ptr{Cvoid}),
     RX, hcat(C...), B0, n, d, m, h, maximum(ilsiters), icmiter, npert, randord, next_seed(), 0,
-    C_NULL, convert(Vector{Cint}, ilsiters), nr, snaps, objs, C_NULL, C_NULL, 0, C_NULL))
+    C_NULL, convert(Vector{Cint}, ilsiters), nr, snaps, objs, C_NULL, C_NULL, ENCODE_FLAGS[], C_NULL))
   Bs = [codes1(snaps[:, :, i]) for i = 1:nr]
   return Bs, objs
 end
