@@ -435,14 +435,14 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
   const float nslice = (float)(min(p.n, c1 * kChunkCodes) - c0 * kChunkCodes);     // codes in this block's slice
 
-  // Speculative threshold.  After a compaction the exact k-th smallest key seen so far is known; with a fraction
-  // f = seen/nslice of the slice scanned, the final k-th distance is close to the (k*f)-th smallest seen.  The
-  // filter threshold is therefore tightened to the key of rank r = x + z*sqrt(x) + z*z/2, x = k*f, z = 5.5 (the
-  // count of keys below it in the whole slice is >= k except with probability ~1e-7 on exchangeable data), which
-  // cuts the appends and compactions of large-k searches several-fold.  It is VERIFIED, not trusted: thresholds
-  // only ever decrease, every key <= the final threshold is in the buffer unless k smaller ones are, so the result
-  // is exact iff the k-th smallest key of the final buffer is <= the final threshold; otherwise the block raises
-  // its redo flag and is rerun without speculation by the second launch.
+  // Speculative threshold.  With a fraction f = seen/nslice of the slice scanned, the final k-th distance is close to
+  // the (k*f)-th smallest seen.  A compaction therefore keeps only the r = x + z*sqrt(x) + z*z/2 smallest keys
+  // (x = k*f, z = 5.5: the count of keys below the r-th in the whole slice is >= k except with probability ~1e-7 on
+  // exchangeable data) and makes the r-th the threshold, which cuts the appends and compactions of large-k searches
+  // several-fold.  It is VERIFIED, not trusted: thresholds only ever decrease and every key seen so far that is <= the
+  // current threshold KEY (taukey_s) is in the buffer, so the result is exact iff the k-th smallest key of the final
+  // buffer is <= the final threshold key; otherwise the block raises its redo flag and is rerun without speculation
+  // (r = k: plain "keep the k best") by the second launch.
   bool final_phase = false;                                    // no tightening once the scan is over
   auto spec_rank = [=, &final_phase]() -> int {
     if (!SPEC || !spec || final_phase) return p.k;
