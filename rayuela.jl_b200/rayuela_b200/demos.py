@@ -254,3 +254,28 @@ def run_demos(dataset_name="SIFT1M", ntrain=int(1e5), m=8, h=256, niter=25, nque
             nsplits_base, sr_method, 1, 0.5, verbose)
         out[sr_method.lower()] = dict(train_error=float(train_error[-1]), recall=recall, B_base=B_base)
     return out
+
+
+def high_recall_experiments(C, B, Xb, Xq, gt, m, h=256, ilsiters=(1, 2, 4, 8, 16, 32, 64, 128, 256), icmiter=4,
+                            npert=4, randord=True, knn=1000, nsplits_base=2, V=True):
+    """The per-trial body of high_recall_experiments (demos/demos_train_query_base.jl:107-158): given trained codebooks
+    C and training codes B (the demo loads them from its HDF5 results, :127), encode the base ONCE with
+    encode_icm_cuda's `ilsiters` snapshots (:134), then for every snapshot: qerror, quantize_norms, linscan_lsq,
+    eval_recall (:136-152).  Returns {ilsiter: dict(base_error, recall)}."""
+    Xb = np.asarray(Xb, dtype=np.float32)
+    Xq = np.asarray(Xq, dtype=np.float32)
+    d = Xb.shape[0]
+    norms_B, norms_C = J.get_norms_codebook(B, C)                                                  # :128
+    B_base = J._rand_codes(h, m, Xb.shape[1])                                                      # :131
+    Bs_base, _ = J.encode_icm_cuda(Xb, B_base, C, list(ilsiters), icmiter, npert, randord, nsplits_base, V)
+    out = {}
+    for idx, ilsiter in enumerate(ilsiters):
+        B_base = Bs_base[idx]
+        base_error = float(J.qerror(Xb, B_base, C))
+        if V:
+            print("Error in base is %e" % base_error)
+        B_base_norms, _ = J.quantize_norms(B_base, C, norms_C)
+        db_norms = np.asarray(norms_C, dtype=np.float32)[np.asarray(B_base_norms, dtype=np.int64) - 1]
+        dists, ids = J.linscan_lsq(B_base, Xq, C, db_norms, np.eye(d, dtype=np.float32), knn)
+        out[int(ilsiter)] = dict(base_error=base_error, recall=J.eval_recall(gt, ids, knn, V))
+    return out

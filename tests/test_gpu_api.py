@@ -232,3 +232,20 @@ def test_linscan_any_h(rb, kind, h, m, k):
     else:
         dj, ij = rb.linscan_cq(_julia(B), _julia(Xq), Cj, k)
     assert np.array_equal(ij.T.astype(np.int32), i0) and np.array_equal(bits(dj.T), bits(d0))
+
+
+def test_high_recall_experiments_snapshots(rb):
+    """demos/demos_train_query_base.jl:107-158: one encode with `ilsiters` snapshots; the error of the snapshots can only
+    go down with more ILS iterations (strict-< accept, src/LSQ.jl:242), and each snapshot equals a separate encode with
+    that many iterations (same seed => same perturbations)."""
+    Xt, Xb, Xq, gt = rb.demos.synthetic_sift(2000, 6000, 40, d=32, seed=9)
+    m = 4
+    r = np.random.default_rng(1)
+    B = np.asfortranarray(r.integers(1, H + 1, (m, Xt.shape[1])).astype(np.int16))
+    rb.seed_b200(5)
+    C, B, _ = rb.train_lsq(Xt, m, H, np.eye(32, dtype=np.float32), B, None, 2, 2, 2, True, 4, True, False)
+    rb.seed_b200(77)
+    out = rb.demos.high_recall_experiments(C, B, Xb, Xq, gt, m, H, ilsiters=(1, 2, 4, 8), knn=20, V=False)
+    errs = [out[i]["base_error"] for i in (1, 2, 4, 8)]
+    assert all(a >= b for a, b in zip(errs, errs[1:])) and errs[-1] < errs[0]
+    assert all(out[i]["recall"].shape == (20,) for i in out)
