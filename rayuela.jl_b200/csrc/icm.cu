@@ -261,17 +261,28 @@ __device__ __forceinline__ Code load_code(const uint8_t* b) {
   return c;
 }
 
-// perturb_codes! (src/LSQ.jl:5-39, with replacement); identical draws to the oracle (DESIGN.md "RNG").
-template <int M>
-__device__ __forceinline__ void perturb(Code& c, int npert, uint64_t seed, int it, uint64_t g) {
-  for (int jb = 0; jb * 4 < npert; jb++) {
+// perturb_codes! (src/LSQ.jl:5-39, with replacement); identical draws to the oracle (DESIGN.md "RNG"): Philox4x32-10
+// keyed by the seed, counter (g_lo, g_hi, it, block) for the positions (mulhi(w, m)) and block | 0x80000000 for the
+// values (mulhi(w, 256)), applied in draw order so a later draw on the same position wins.
+// Precomputed: one thread per (vector, ILS iteration, Philox block of 4 draws), packed as 4 positions
+// (4 bits each, bits 0..15) + 4 values (8 bits each, bits 16..47).  K3 used to run both Philox blocks redundantly in all
+// 32 lanes of the warp at the top of every ILS iteration (~240 instructions, 4 % of the kernel); now it loads 8 bytes.
+__global__ void __launch_bounds__(256) perturb_draws_kernel(unsigned long long* __restrict__ P, int64_t nc, int64_t g0,
+                                                            int ilsiter, int nblk, int m, uint64_t seed) {
+  const int64_t total = nc * ilsiter * nblk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int jb = (int)(i % nblk), it = (int)((i / nblk) % ilsiter);
+    const uint64_t g = (uint64_t)(g0 + i / ((int64_t)nblk * ilsiter));
     uint32_t pw[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)it, (uint32_t)jb};
     uint32_t vw[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)it, 0x80000000u | (uint32_t)jb};
     philox4x32_10(pw, (uint32_t)seed, (uint32_t)(seed >> 32));
     philox4x32_10(vw, (uint32_t)seed, (uint32_t)(seed >> 32));
+    unsigned long long pk = 0;
 #pragma unroll
     for (int t = 0; t < 4; t++)
-      if (jb * 4 + t < npert) c.set((int)mulhi32(pw[t], (uint32_t)M), mulhi32(vw[t], (uint32_t)kH));
+      pk |= (unsigned long long)mulhi32(pw[t], (uint32_t)m) << (4 * t) |
+            (unsigned long long)mulhi32(vw[t], (uint32_t)kH) << (16 + 8 * t);
+    P[i] = pk;
   }
 }
 
@@ -335,6 +346,7 @@ struct IcmParams {
   const int* orders;    // [ilsiter][m]
   const unsigned long long* orders_packed;  // [ilsiter]: the m visiting-order entries of an iteration, 4 bits each
   uint32_t one;         // == 1, opaque to the compiler (see pf_rows)
+  const unsigned long long* draws;  // [nc][ilsiter][ceil(npert/4)] packed perturbation draws (perturb_draws_kernel)
   const int* snap_iters;  // [n_snap] (1-based ILS iteration counts)
   uint8_t* B_snap;      // [n_snap][n_total][m], already offset to this chunk's first vector
   int* stats;           // [ilsiter][2] (#equal, #better)
@@ -409,7 +421,16 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
 
     for (int it = 0; it < p.ilsiter; it++) {
       Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
-      perturb<M>(nb, p.npert, p.seed, it, (uint64_t)(p.g0 + l));  // src/LSQ.jl:225
+      {                                                         // perturb_codes!, src/LSQ.jl:225 (draws precomputed)
+        const int nblk = (p.npert + 3) >> 2;
+        for (int jb = 0; jb < nblk; jb++) {
+          const unsigned long long pk = __ldg(p.draws + ((size_t)l * p.ilsiter + it) * nblk + jb);
+#pragma unroll
+          for (int t = 0; t < 4; t++)
+            if (jb * 4 + t < p.npert)
+              code_set<M>(nb, (int)(pk >> (4 * t)) & 15, (uint32_t)(pk >> (16 + 8 * t)) & 255u);
+        }
+      }
       const unsigned long long ordp = __ldg(p.orders_packed + it);   // the whole visiting order in a register
       // Memoised conditioning: the step for codebook j is a pure function of (U_j, codes of the others).
       // If none of the other codes changed since j was last evaluated in THIS iteration, its argmin is the
@@ -1200,12 +1221,15 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
   DevBuf Cp_d;
   if (fast) RYL_TRY(unary_tc_pack_codebooks(c_in.d, d, mh, &Cp_d, s));
   const int nbuf = piped ? 2 : 1;
-  DevBuf U_d[2], umax_d[2], next_d;
+  DevBuf U_d[2], umax_d[2], next_d, draws_d[2];
+  const int nblk = (npert + 3) / 4;
+  const bool predraw = ilsiter > 0 && npert > 0;
   RYL_TRY(next_d.alloc((size_t)nchunks * sizeof(unsigned long long), s));
   RYL_CUDA(cudaMemsetAsync(next_d.p, 0, next_d.bytes, s));
   for (int i = 0; i < nbuf; i++) {
     RYL_TRY(U_d[i].alloc((size_t)std::min(chunk, n) * per_vec, s));
     if (pf) RYL_TRY(umax_d[i].alloc((size_t)std::min(chunk, n) * sizeof(unsigned int), s));
+    if (predraw) RYL_TRY(draws_d[i].alloc((size_t)std::min(chunk, n) * ilsiter * nblk * sizeof(unsigned long long), s));
   }
   if (stats) RYL_CUDA(cudaEventRecord(t_setup.e, s));
   if (piped) {
@@ -1243,6 +1267,10 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
       RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
                  umax);
     if (stats) RYL_CUDA(cudaEventRecord(t_u1[c].e, cs));
+    unsigned long long* draws = draws_d[c & (nbuf - 1)].as<unsigned long long>();
+    if (predraw)
+      RYL_LAUNCH(perturb_draws_kernel, (int)std::min<int64_t>((nc * ilsiter * nblk + 255) / 256, (int64_t)sm_count() * 16), 256,
+                 0, cs, draws, nc, g0 + l0, ilsiter, nblk, m, seed);
     IcmParams p;
     p.U = U;
     p.T = T_d.as<float>();
@@ -1256,6 +1284,7 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     p.orders = ord_d.as<int>();
     p.orders_packed = ordp_d.as<unsigned long long>();
     p.one = 1u;
+    p.draws = predraw ? draws : nullptr;
     p.snap_iters = snapit_d.as<int>();
     p.B_snap = snap_out.d ? snap_out.d + (size_t)l0 * m : nullptr;
     p.stats = stats_d.as<int>();
@@ -1401,6 +1430,7 @@ static int encode_icm_generic(const float* X, const float* C, uint8_t* B, int64_
     p.stats = stats_d.as<int>();
     p.steps = steps_d;
     p.next = nullptr;
+    p.draws = nullptr;
     p.nc = nc;
     p.n_total = n;
     p.g0 = g0 + l0;
