@@ -13,8 +13,8 @@
 // row per 64 bf16 of K, 16-byte chunks XOR-swizzled by (row & 7), i.e. exactly the canonical K-major SWIZZLE_128B layout
 // tcgen05.mma reads -- so a tile is fetched with plain 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx), no
 // tensor maps.  Kernel: one persistent CTA per SM, 10 warps: warp 0 = bulk-copy producer, warp 1 = TMEM allocator + MMA
-// issuer (one elected lane), warps 2..9 = epilogue (tcgen05.ld 32x32b -> fma(-2, acc, ||c||^2) -> global, per-vector
-// max |U| for K3's pre-filter slack).  Tile = 128 vectors x 256 entries (one codebook) x K = d <= 128; the A images of an
+// issuer (one elected lane), warps 2..9 = epilogue (tcgen05.ld 32x32b -> fma(-2, acc, ||c||^2) -> XOR-swizzled 4 KB staging
+// tile per warp -> transposed read-back -> full 128-byte-line global stores; per-vector max |U| for K3's pre-filter slack).  Tile = 128 vectors x 256 entries (one codebook) x K = d <= 128; the A images of an
 // M-tile stay in shared memory for all m codebooks; two 256-column TMEM accumulators let the epilogue of codebook j
 // overlap the MMAs of codebook j+1.
 #include <cuda_bf16.h>
@@ -242,6 +242,8 @@ __global__ void __launch_bounds__(320, 1) unary_tc_kernel(UnaryTcParams p) {
     // lane quarter and split the 256 columns.  The tcgen05.ld of the next 32-column chunk is in flight while the current
     // one is scaled, biased and stored =====
     const int q = warp & 3, half = (warp - 2) >> 2;
+    float4* stage = reinterpret_cast<float4*>(smem_raw + (smem0 - tc_smem_u32(smem_raw)) + (size_t)p.KB * 2 * (a_img + b_img)) +
+                    (warp - 2) * 256;                       // 32 rows x 8 quads of 16 bytes = 4 KB per epilogue warp
     uint32_t t_phase[2] = {0, 0};
     uint32_t tile = 0;
     for (int64_t mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
@@ -254,7 +256,6 @@ __global__ void __launch_bounds__(320, 1) unary_tc_kernel(UnaryTcParams p) {
         t_phase[buf] ^= 1;
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + buf * kTcN + half * (kTcN / 2);
-        float* dst = p.U + (size_t)l * p.mh + (size_t)nt * kTcN + half * (kTcN / 2);
         const float* nr = p.nrm + (size_t)nt * kTcN + half * (kTcN / 2);
         uint32_t r[2][32];
         tmem_ld32(r[0], taddr);
@@ -262,19 +263,32 @@ __global__ void __launch_bounds__(320, 1) unary_tc_kernel(UnaryTcParams p) {
         for (int ch = 0; ch < kTcN / 2 / 32; ch++) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (ch + 1 < kTcN / 2 / 32) tmem_ld32(r[(ch + 1) & 1], taddr + (ch + 1) * 32);
-          if (l < p.n) {
+          // thread = row: scale, bias, track max |U|, and park the 32 x 32 chunk in this warp's 4 KB staging tile with
+          // the 16-byte column quads XOR-swizzled by the row, so that both the row-wise writes and the transposed reads
+          // below are bank-conflict free
+          __syncwarp();                                    // the previous chunk's reads of the staging tile are done
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              const float4 nv = __ldg(reinterpret_cast<const float4*>(nr + ch * 32 + e));
-              float4 o;
-              o.x = fmaf(-2.0f, __uint_as_float(r[ch & 1][e]), nv.x);
-              o.y = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 1]), nv.y);
-              o.z = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 2]), nv.z);
-              o.w = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 3]), nv.w);
-              *reinterpret_cast<float4*>(dst + ch * 32 + e) = o;
-              mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-              bad |= (o.x != o.x) | (o.y != o.y) | (o.z != o.z) | (o.w != o.w);
-            }
+          for (int e = 0; e < 32; e += 4) {
+            const float4 nv = __ldg(reinterpret_cast<const float4*>(nr + ch * 32 + e));
+            float4 o;
+            o.x = fmaf(-2.0f, __uint_as_float(r[ch & 1][e]), nv.x);
+            o.y = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 1]), nv.y);
+            o.z = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 2]), nv.z);
+            o.w = fmaf(-2.0f, __uint_as_float(r[ch & 1][e + 3]), nv.w);
+            stage[lane * 8 + ((e >> 2) ^ (lane & 7))] = o;
+            mx = fmaxf(fmaxf(mx, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+            bad |= (o.x != o.x) | (o.y != o.y) | (o.z != o.z) | (o.w != o.w);
+          }
+          __syncwarp();
+          // transposed read-back: one instruction stores 4 rows x 128 contiguous bytes (full lines) instead of 16 bytes
+          // into each of 32 different lines
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int row = 4 * i + (lane >> 3), quad = lane & 7;
+            const float4 o = stage[row * 8 + (quad ^ (row & 7))];
+            const int64_t lr = mt * kTcM + q * 32 + row;
+            if (lr < p.n)
+              *reinterpret_cast<float4*>(p.U + (size_t)lr * p.mh + (size_t)nt * kTcN + half * (kTcN / 2) + ch * 32 + quad * 4) = o;
           }
         }
         tc_fence_before();
@@ -331,7 +345,7 @@ int unary_tc_launch(const float* X, const DevBuf& Cp, const float* nrm, float* U
   p.KB = KB;
   p.mtiles = mtiles;
   p.ntiles = ntiles;
-  const size_t smem = (size_t)KB * 2 * (kTcM * 128 + kTcN * 128) + 1024;
+  const size_t smem = (size_t)KB * 2 * (kTcM * 128 + kTcN * 128) + 8 * 4096 + 1024;   // images + staging tiles + alignment
   RYL_CUDA(cudaFuncSetAttribute(unary_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = (int)std::min<int64_t>(mtiles, sm_count());
   RYL_LAUNCH(unary_tc_kernel, grid, 320, smem, s, p);
