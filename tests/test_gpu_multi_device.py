@@ -107,9 +107,12 @@ def test_devices_from_environment_variable():
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("S,nq,k", [(2, 7, 10000), (8, 5, 2500), (3, 4, 6000), (5, 3, 3277), (2, 3, 8192)])
+@pytest.mark.parametrize("S,nq,k", [(2, 7, 10000), (8, 5, 2500), (3, 4, 6000), (5, 3, 3277), (2, 3, 8192),
+                                    (8, 6, 1000), (3, 5, 700), (7, 4, 333), (2, 9, 4000), (16, 3, 512)])
 def test_topk_merge_beyond_one_block(rb, S, nq, k):
-    """S*k > 16384 keys per query: the tree of pairwise rank merges; heavy ties in the distances."""
+    """Merges of sorted lists beyond the small bitonic case: the rank-merge tree in shared memory (more than 1024 keys per
+    query, e.g. 8 GPUs at k = 1000) and in global memory (more than ~16k keys per query, ADVICE r1: 2 shards at the
+    reference's default k = 10000); heavy ties in the distances."""
     r = np.random.default_rng(S * k)
     d = np.round(r.standard_normal((S, nq, k)) * 20).astype(np.float32) + np.float32(0)   # no -0.0: keys canonicalise it
     i = r.permutation(S * nq * k).astype(np.int32).reshape(S, nq, k)        # distinct ids
