@@ -39,17 +39,33 @@ static int set_slots_locked(const int* devices, int n) {
     RYL_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
     g_slots.push_back(sl);
   }
-  // direct NVLink peer copies for the gather of per-shard results (falls back to staged copies when unavailable)
-  for (int i = 0; i < n; i++)
+  // peer access (NVLink): a shard's search kernels store their results straight into slot 0's gather buffer; without
+  // it (or on a failure) the results are staged locally and copied with cudaMemcpyPeerAsync
+  for (int i = 0; i < n; i++) {
+    g_slots[i].direct_to_first = devices[i] == devices[0];
     for (int j = 0; j < n; j++)
       if (devices[i] != devices[j]) {
         int can = 0;
         if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
           cudaSetDevice(devices[i]);
           cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
-          if (e != cudaSuccess) cudaGetLastError();   // already enabled: fine
+          if (e != cudaSuccess) cudaGetLastError();   // cudaErrorPeerAccessAlreadyEnabled: fine
+          if (j == 0 && (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled)) {
+            // the gather buffer comes from slot 0's stream-ordered pool, which is mapped on peers only on request
+            cudaMemPool_t pool;
+            cudaMemAccessDesc acc = {};
+            acc.location.type = cudaMemLocationTypeDevice;
+            acc.location.id = devices[i];
+            acc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (cudaDeviceGetDefaultMemPool(&pool, devices[0]) == cudaSuccess &&
+                cudaMemPoolSetAccess(pool, &acc, 1) == cudaSuccess)
+              g_slots[i].direct_to_first = true;
+            else
+              cudaGetLastError();
+          }
         }
       }
+  }
   RYL_CUDA(cudaSetDevice(cur));
   g_slots_ready = true;
   return RAYUELA_OK;

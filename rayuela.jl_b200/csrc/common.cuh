@@ -152,6 +152,8 @@ inline int sm_count() {
 struct DeviceSlot {
   int device = 0;
   cudaStream_t stream = nullptr;   // non-blocking stream owned by the library, one per slot
+  bool direct_to_first = false;    // kernels on this device may store straight into slot 0's memory (same device, or peer
+                                   // access over NVLink enabled): the sharded search writes its results there, no copy
 };
 const std::vector<DeviceSlot>& device_slots();   // lazily initialised from RAYUELA_B200_DEVICES when rayuela_init was not called
 

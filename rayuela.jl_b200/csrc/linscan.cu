@@ -1240,9 +1240,10 @@ static const char* kBadLutMsg =
     "index_search: a lookup-table entry is not finite (or exceeds 1e37): queries / codebooks contain inf or NaN, or "
     "their products overflow";
 
-// multi-device parent: every slot scans its shard for ALL queries (LUTs replicated), the per-shard top-k lists are
-// copied peer-to-peer to the first slot's device and merged there by the (dist, id) total order -- the single exchange
-// step of SURVEY 8e, done with peer copies inside one process instead of an NCCL all-gather between processes.
+// multi-device parent: every slot scans its shard for ALL queries (LUTs replicated); the per-shard top-k lists land in the
+// first slot's gather buffer -- stored there directly by the shard's last kernel over NVLink peer access (or copied
+// peer-to-peer when that is unavailable) -- and are merged there by the (dist, id) total order: the single exchange
+// step of SURVEY 8e, fused into the search inside one process instead of an NCCL all-gather between processes.
 static int index_search_multi(rayuela_index* ix, const float* queries, const float* codebooks, int nq, int d, int k,
                               float* dists, int32_t* idx, bool fast_lut) {
   const int D = (int)ix->shards.size();
@@ -1266,16 +1267,22 @@ static int index_search_multi(rayuela_index* ix, const float* queries, const flo
       RYL_TRY(q_in.bind(queries, (size_t)nq * d, false, s));
       RYL_TRY(cb_in.bind(codebooks, (size_t)ix->m * ix->h * len, false, s));
       DevBuf dl, il, bd;
-      RYL_TRY(dl.alloc(per * sizeof(float), s));
-      RYL_TRY(il.alloc(per * sizeof(int32_t), s));
       RYL_TRY(bd.alloc(sizeof(int), s));
       RYL_CUDA(cudaMemsetAsync(bd.p, 0, sizeof(int), s));
-      RYL_TRY(index_search_dev(ix->shards[i], q_in.d, cb_in.d, nq, d, k, dl.as<float>(), il.as<int32_t>(), bd.as<int>(), s,
-                               fast_lut));
-      RYL_CUDA(cudaMemcpyPeerAsync(gd.as<float>() + (size_t)i * per, root.device, dl.p, ix->slots[i].device,
-                                   per * sizeof(float), s));
-      RYL_CUDA(cudaMemcpyPeerAsync(gi.as<int32_t>() + (size_t)i * per, root.device, il.p, ix->slots[i].device,
-                                   per * sizeof(int32_t), s));
+      float* dst_d = gd.as<float>() + (size_t)i * per;
+      int32_t* dst_i = gi.as<int32_t>() + (size_t)i * per;
+      if (ix->slots[i].direct_to_first) {
+        // the shard's final merge kernel stores its (dist, id) lists over NVLink straight into slot 0's gather buffer:
+        // search and exchange are one step, there is no separate copy
+        RYL_TRY(index_search_dev(ix->shards[i], q_in.d, cb_in.d, nq, d, k, dst_d, dst_i, bd.as<int>(), s, fast_lut));
+      } else {
+        RYL_TRY(dl.alloc(per * sizeof(float), s));
+        RYL_TRY(il.alloc(per * sizeof(int32_t), s));
+        RYL_TRY(index_search_dev(ix->shards[i], q_in.d, cb_in.d, nq, d, k, dl.as<float>(), il.as<int32_t>(), bd.as<int>(), s,
+                                 fast_lut));
+        RYL_CUDA(cudaMemcpyPeerAsync(dst_d, root.device, dl.p, ix->slots[i].device, per * sizeof(float), s));
+        RYL_CUDA(cudaMemcpyPeerAsync(dst_i, root.device, il.p, ix->slots[i].device, per * sizeof(int32_t), s));
+      }
       RYL_CUDA(cudaMemcpyAsync(&bad[i], bd.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       RYL_CUDA(cudaStreamSynchronize(s));
       return RAYUELA_OK;
