@@ -5,6 +5,7 @@
 //   K6 merge_kernel   k-way merge of sorted (dist,id) lists (DB slices of one GPU, or per-GPU shards)
 // Replaces deps/src/linscan_aqd.cpp:37-102 and deps/src/linscan_aqd_pairwise_byte.cpp:14-176.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <limits>
 
@@ -103,6 +104,126 @@ __global__ void __launch_bounds__(256) lut_relayout_kernel(const float* __restri
       lut[(size_t)(q >> 4) * 32768 + ((q & 15) >> 2) * 8192 + c * 32 + ((((q & 3) >> 1) * 8 + k) << 1) + (q & 1)] = v;
     else
       lut[(size_t)(q >> 3) * 32768 + ((q & 7) >> 1) * 8192 + c * 32 + (k << 1) + (q & 1)] = v;
+  }
+}
+
+// K4q: quantised twin of one fp32 LUT tile for the pre-filter scan (QPF, see scanx_kernel).  One block per query tile:
+//   lo[q][k], hi[q][k] = min / max over the valid entries c < h of codebook k < m
+//   s      = max_q (sum_k (hi - lo) + norm range) / 2000              one scale per tile (1 if that is 0)
+//   v      = rint((LUT - lo[q][k]) / s)  (+ 1 for k = 0)              two queries per fp32 word as v_hi * 4096 + v_lo, laid
+//            out like the fp32 tile with 4 queries per 8-byte entry:
+//            P = 8: [tt2][c][g*8 + k][e2], queries tt2*8 + g*4 + 2*e2 (+1);   P = 16: [tt2][c][k][e2], queries tt2*4 + 2*e2 (+1)
+//   off_q  = sum_k lo[q][k] + min norm;   mu_q = ceil(0.5 m + 2.6) + 1 + ceil((m+1) 2^-23 (sum_k max|LUT| + max|norm|) / s)
+// so that A = sum_k v + rint((norm - min norm)/s) <= 2000 + m/2 + 3 < 2^11 and every code with exact fp32 distance
+// E <= tau has A <= floor((tau - off_q)/s) + mu_q: m roundings of 0.5 (+ the division's), 1.5 for the norm (its rint, the
+// rounded constant of the magic-number conversion), 1 for the offset of codebook 0, and the fp32 roundings of the exact chain.
+template <int P>
+__global__ void __launch_bounds__(512) lut_quant_kernel(const float* __restrict__ lut, float* __restrict__ lutq,
+                                                        float4* __restrict__ tilep, double* __restrict__ qoff,
+                                                        int* __restrict__ qmu, int m, int h, float nmin, float nmax,
+                                                        int has_norms) {
+  constexpr int QB = P == 8 ? 16 : 8;
+  extern __shared__ __align__(16) float tile_s[];          // 32768 floats
+  __shared__ unsigned int mn_s[16 * 16], mx_s[16 * 16];    // ordered-uint images, [q][k]
+  __shared__ double rng_s[16], off_s[16], bmax_s[16];
+  __shared__ float s_s;
+  const int tid = threadIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(lut + (size_t)blockIdx.x * 32768);
+  for (int i = tid; i < 8192; i += 512) reinterpret_cast<float4*>(tile_s)[i] = __ldg(src + i);
+  if (tid < 256) {
+    mn_s[tid] = 0xFFFFFFFFu;
+    mx_s[tid] = 0u;
+  }
+  __syncthreads();
+  auto fidx = [](int q, int k, int c) -> int {
+    return P == 8 ? (q >> 2) * 8192 + c * 32 + (((((q & 3) >> 1) << 3) + k) << 1) + (q & 1)
+                  : (q >> 1) * 8192 + c * 32 + (k << 1) + (q & 1);
+  };
+  {
+    // thread <-> (column of the 32-float row, tile quarter tt, quarter of the c range): conflict-free column walks
+    const int col = tid & 31, tt = (tid >> 5) & 3, part = tid >> 7;
+    const int bp = col >> 1, e = col & 1;
+    const int k = P == 8 ? (bp & 7) : bp;
+    const int q = P == 8 ? tt * 4 + (bp >> 3) * 2 + e : tt * 2 + e;
+    if (k < m) {
+      float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+      for (int c = part * 64; c < min(h, part * 64 + 64); c++) {
+        const float v = tile_s[tt * 8192 + c * 32 + col];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+      }
+      if (lo <= hi) {
+        atomicMin(&mn_s[q * 16 + k], f32_to_ordered(lo));
+        atomicMax(&mx_s[q * 16 + k], f32_to_ordered(hi));
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < QB) {
+    double rng = 0, off = 0, bm = 0;
+    for (int k = 0; k < m; k++) {
+      const float lo = ordered_to_f32(mn_s[tid * 16 + k]), hi = ordered_to_f32(mx_s[tid * 16 + k]);
+      rng += (double)hi - (double)lo;
+      off += (double)lo;
+      bm += fmax(fabs((double)lo), fabs((double)hi));
+    }
+    rng_s[tid] = rng;
+    off_s[tid] = off;
+    bmax_s[tid] = bm;
+  }
+  __syncthreads();
+  const double nrange = has_norms ? (double)nmax - (double)nmin : 0.0;
+  if (tid == 0) {
+    double r = 0;
+    for (int q = 0; q < QB; q++) r = fmax(r, rng_s[q]);
+    float sc = (float)((r + nrange) / 2000.0);
+    if (!(sc > 0.f) || !(sc < __int_as_float(0x7f800000))) sc = 1.0f;
+    s_s = sc;
+    const float inv = __fdiv_rn(1.0f, sc);
+    tilep[blockIdx.x] = make_float4(sc, inv, has_norms ? (float)(12582912.0 - (double)nmin * (double)inv) : 12582912.0f, 0.f);
+  }
+  __syncthreads();
+  const float sc = s_s;
+  if (tid < QB) {
+    const double nb = has_norms ? fmax(fabs((double)nmin), fabs((double)nmax)) : 0.0;
+    const double fp = ceil((double)(m + 1) * 1.1920928955078125e-07 * (bmax_s[tid] + nb) / (double)sc);
+    qoff[(size_t)blockIdx.x * QB + tid] = off_s[tid] + (has_norms ? (double)nmin : 0.0);
+    qmu[(size_t)blockIdx.x * QB + tid] = (int)ceil(0.5 * m + 2.6) + 1 + (int)fmin(fp, 40000.0);
+  }
+  for (int o = tid; o < 16384; o += 512) {
+    const int tt2 = o >> 13, c = (o >> 5) & 255, bp = (o >> 1) & 15, e2 = o & 1;
+    const int k = P == 8 ? (bp & 7) : bp;
+    const int q = P == 8 ? tt2 * 8 + (bp >> 3) * 4 + 2 * e2 : tt2 * 4 + 2 * e2;      // low digit; q + 1 is the high one
+    float w = 0.f;
+    if (k < m && c < h) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float f = tile_s[fidx(q + e, k, c)], lo = ordered_to_f32(mn_s[(q + e) * 16 + k]);
+        v[e] = fminf(fmaxf(rintf(__fdiv_rn(__fsub_rn(f, lo), sc)), 0.f), 2010.f) + (k == 0 ? 1.f : 0.f);
+      }
+      w = v[1] * 4096.f + v[0];
+    }
+    lutq[(size_t)blockIdx.x * 16384 + o] = w;
+  }
+}
+
+// min / max of the database norms (ordered-uint images; NaN norms are skipped -- such codes can never be returned)
+__global__ void __launch_bounds__(256) norm_range_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ out) {
+  float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float x = v[i];
+    lo = fminf(lo, x);
+    hi = fmaxf(hi, x);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if ((threadIdx.x & 31) == 0 && lo <= hi) {
+    atomicMin(out, f32_to_ordered(lo));
+    atomicMax(out + 1, f32_to_ordered(hi));
   }
 }
 
@@ -334,9 +455,33 @@ struct ScanXParams {
   int spec;              // speculative thresholds on (verified at the end; a failed block is redone in pass 1)
   int pass;              // 0: main launch; 1: redo launch -- only blocks whose redo flag is set run, without speculation
   int* redo;             // [slices][qtiles] flags
+  // QPF (quantised pre-filter scan, see scanx_kernel): quantised tiles + their parameters, the raw codes for the exact
+  // re-evaluation of the survivors, and the per-query lists of survivors awaiting it
+  const float* lutq;     // tiled [qtiles][16384]: two queries per word (lut_quant_kernel)
+  const float4* tilep;   // [qtiles] {s, 1/s, norm rounding constant, -}
+  const double* qoff;    // [qtiles*QB] sum_k min_c LUT + min norm: the distance that quantises to 0
+  const int* qmu;        // [qtiles*QB] threshold margin in units of s
+  const uint8_t* codes;  // [n][m] raw codes
+  uint32_t* pend;        // [slices][qtiles*QB][pcap] ids that passed the 16-bit filter
+  int m, pcap, psoft;
 };
 
-template <int P, bool NORMS, bool SPEC>
+// QPF = true: the same scan with a quantised INTEGER pre-filter in front of the exact arithmetic -- results bit-identical.
+// The scan is bound by shared-memory bandwidth (4 bytes looked up per byte of code and query), so the tile is stored a
+// second time as small integers in units of a per-tile scale s:  v[q][k][c] = rint((LUT[q][k][c] - min_c LUT[q][k][.]) / s)
+// (+1 for k = 0), TWO queries per fp32 word as the exact integer v_hi * 4096 + v_lo, i.e. four queries per LDS.64 and per
+// FFMA2 (integers below 2^24 add exactly in fp32, so the packed accumulate / restart / capture of the fp32 loop carries
+// over unchanged at half the loads and half the math per query).  s is chosen so that the m terms plus the quantised
+// norm stay below 2^11 per query: no carry between the two digits.  For every code
+//     A = sum_k v + rint((norm - min norm)/s)   satisfies   A <= 1 + (E - off_q)/s + 0.5 m + 1.5 + fp32 slack
+// where E is the exact fp32 distance of the reference chain and off_q = sum_k min_c LUT + min norm.  A code is a
+// SURVIVOR of query q when A <= T_q = floor((tau_q - off_q)/s) + mu_q (mu_q = that margin, lut_quant_kernel), which every
+// code with E <= tau_q is.  The test is one exact subtraction per pair, (T + 2048) - A per base-4096 digit: a digit keeps
+// its 2048 bit iff A <= T and never borrows from its neighbour.  Survivors are only noted (id appended to the query's
+// pending list); service() re-evaluates them with the exact fp32 chain from the fp32 tile in L2 (ascending k from 0,
+// + norm last -- the arithmetic of the fp32 hot loop) and hands those with E <= tau_q to the unchanged candidate
+// buffers / compaction / speculation.  The window is ~4e-3 of the tile's distance range.
+template <int P, bool NORMS, bool SPEC, bool QPF = false>
 __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p) {
   using X = ScanX<P>;
   constexpr int NT = kScanWarps * 32;
@@ -356,6 +501,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   __shared__ int seen_s;     // codes of this block's slice scanned so far (all warps)
   __shared__ int softq_s[16];// per-query soft limit (lower while a speculative threshold waits for confirmation)
   __shared__ int fail_s;     // a speculative threshold turned out too tight for some query: redo the block
+  __shared__ int pcnt_s[16]; // QPF: survivors pending exact evaluation, per query
+  __shared__ int thr_s[16];  // QPF: integer thresholds T_q (0: nothing passes, 2047: everything does)
 
   // dynamic shared memory: [sort buffer 64 KB][pad][LUT tile 128 KB, 32 KB-aligned] -- the alignment makes the
   // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
@@ -370,6 +517,19 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   const int q0 = blockIdx.x * QB;
   const int slice = blockIdx.y;
   uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * QB + (size_t)blockIdx.x * QB) * p.cap;
+  uint32_t* pend = QPF ? p.pend + ((size_t)slice * gridDim.x * QB + (size_t)blockIdx.x * QB) * p.pcap : nullptr;
+  const float inf = __int_as_float(0x7f800000);
+  // QPF: T_q from the current exact threshold (double arithmetic: once per query per service())
+  auto thr_of = [=](int q) -> int {
+    const float tau = tau_s[q];
+    if (tau == inf) return 2047;
+    if (!(tau > -inf)) return 0;
+    const float4 tp = __ldg(p.tilep + blockIdx.x);
+    const double x = floor(((double)tau - __ldg(p.qoff + (size_t)blockIdx.x * QB + q)) / (double)tp.x) +
+                     (double)__ldg(p.qmu + (size_t)blockIdx.x * QB + q);
+    if (!(x >= 1.0)) return 0;                     // A >= 1 for every code (the +1 of codebook 0)
+    return (int)fmin(x, 2046.0);
+  };
 
   const uint32_t mbar_addr = smem_u32(&mbar);
   if (tid == 0) {
@@ -382,6 +542,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     tau_s[tid] = (q0 + tid < p.nq) ? p.tau0 : -__int_as_float(0x7f800000);
     taukey_s[tid] = make_key(p.tau0, 0xFFFFFFFFu);
     lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
+    if (QPF) {
+      pcnt_s[tid] = 0;
+      thr_s[tid] = tid < QB ? thr_of(tid) : 0;
+    }
   }
   if (SPEC && p.pass == 1 && p.redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // redo launch: nothing to redo
   const bool spec = SPEC && p.pass == 0;           // SPEC = false instantiations carry none of the speculation code
@@ -395,11 +559,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   }
   block_sync();
   if (tid == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(kLutTileBytes)
+    constexpr int kTileBytes = QPF ? kLutTileBytes / 2 : kLutTileBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_addr), "r"(kTileBytes)
                  : "memory");
-    const char* src = reinterpret_cast<const char*>(p.lut) + (size_t)blockIdx.x * kLutTileBytes;
+    const char* src = QPF ? reinterpret_cast<const char*>(p.lutq) + (size_t)blockIdx.x * kTileBytes
+                          : reinterpret_cast<const char*>(p.lut) + (size_t)blockIdx.x * kTileBytes;
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < kTileBytes / 32768; i++)
       asm volatile(
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
               lut_addr + i * 32768),
@@ -430,6 +596,21 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   for (int i = 0; i < 8; i++)
     tau[i] = (q0 + (i >> 1) * (2 * X::G) + g * 2 + (i & 1) < p.nq) ? p.tau0 : -__int_as_float(0x7f800000);
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
+  // QPF: the lane's 8 queries are i = 0..7 <-> block query (i >> 2) * 4G + 4g + (i & 3): LDS.64 number i >> 2 of a step,
+  // fp32 word (i >> 1) & 1 of it, base-4096 digit i & 1 of that word.  thr2: per word (T_hi + 2048) * 4096 + (T_lo + 2048).
+  uint64_t thr2[2] = {0, 0};
+  auto lane_query = [=](int i) -> int { return (i >> 2) * (4 * X::G) + g * 4 + (i & 3); };
+  auto thr_word = [=](int i) -> float {      // word holding queries i (low digit) and i + 1
+    return (float)((thr_s[lane_query(i + 1)] + 2048) * 4096 + thr_s[lane_query(i)] + 2048);
+  };
+  float q_invs = 0.f, q_c0 = 0.f;
+  if (QPF) {
+    const float4 tp = __ldg(p.tilep + blockIdx.x);
+    q_invs = tp.y;
+    q_c0 = tp.z;
+    thr2[0] = pack2(thr_word(0), thr_word(2));
+    thr2[1] = pack2(thr_word(4), thr_word(6));
+  }
   int warm = 1;
   const int64_t c0 = (int64_t)slice * p.chunks_per_slice;
   const int64_t c1 = min(p.nchunks, c0 + p.chunks_per_slice);
@@ -585,9 +766,62 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   // instructions; it hands the refreshed thresholds back through tau_x / warm_x (address-taken locals) so that the
   // hot loop's own copies stay in registers; everything else is captured BY VALUE (also by the helpers it calls) so
   // that taking the closure's address does not push the kernel's locals into local memory.
+  // QPF: exact re-evaluation of the pending survivors, all threads of the block over the flattened (query, slot) pairs;
+  // callers hold every warp at a barrier.  ((0 + t_0) + t_1) + ... in ascending k, + dbnorms[i] last
+  // (pairwise_byte.cpp:70-74): the fp32 hot loop's arithmetic.
+  auto drain = [=]() {
+    const float* lt = p.lut + (size_t)blockIdx.x * (kLutTileBytes / 4);
+    int total = 0;
+#pragma unroll
+    for (int q = 0; q < QB; q++) total += pcnt_s[q];
+    for (int f = tid; f < total; f += NT) {
+      int q = 0, t = f;
+      while (t >= pcnt_s[q]) t -= pcnt_s[q++];
+      const uint32_t id = pend[(size_t)q * p.pcap + t];
+      const float* lq = (P == 8) ? lt + (q >> 2) * 8192 + (((q & 3) >> 1) << 4) + (q & 1) : lt + (q >> 1) * 8192 + (q & 1);
+      const uint8_t* cb = p.codes + (size_t)id * p.m;
+      float nrm = 0.f;
+      if (NORMS) nrm = __ldg(p.norms + id);
+      // all code bytes first, then all table entries: two load levels per survivor instead of 2 m dependent ones
+      uint32_t cw[P / 4];
+      if (P == 8 && p.m == 8) {
+        const uint2 c8 = __ldg(reinterpret_cast<const uint2*>(cb));
+        cw[0] = c8.x;
+        cw[1] = c8.y;
+      } else if (P == 16 && p.m == 16) {
+        const uint4 c16 = __ldg(reinterpret_cast<const uint4*>(cb));
+        cw[0] = c16.x; cw[1] = c16.y; cw[2] = c16.z; cw[3] = c16.w;
+      } else {
+#pragma unroll
+        for (int w4 = 0; w4 < P / 4; w4++) {
+          uint32_t x = 0;
+#pragma unroll
+          for (int b = 0; b < 4; b++)
+            if (w4 * 4 + b < p.m) x |= (uint32_t)__ldg(cb + w4 * 4 + b) << (8 * b);
+          cw[w4] = x;
+        }
+      }
+      float tv[P];
+#pragma unroll
+      for (int k = 0; k < P; k++) tv[k] = k < p.m ? __ldg(lq + (int)((cw[k >> 2] >> (8 * (k & 3))) & 255u) * 32 + (k << 1)) : 0.f;
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < P; k++)
+        if (k < p.m) d = __fadd_rn(d, tv[k]);
+      if (NORMS) d = __fadd_rn(d, nrm);
+      if (d <= tau_s[q]) {
+        const uint64_t key = make_key(d, id);
+        if (!p.lb || key > lb_s[q]) cand[(size_t)q * p.cap + atomicAdd(&cnt_s[q], 1)] = key;
+      }
+    }
+    block_sync();
+    if (tid < 16) pcnt_s[tid] = 0;
+  };
+
   float tau_x[8];
+  uint64_t thr_x[2];
   int warm_x = 1;
-  auto service = [=, &tau_x, &warm_x](int progress) __attribute__((noinline)) -> bool {   // progress: codes this warp has completed
+  auto service = [=, &tau_x, &thr_x, &warm_x](int progress) __attribute__((noinline)) -> bool {   // progress: codes this warp has completed
     block_sync();                                   // nobody is appending past this point
     const int nf = nfin_s;
     const int fl = *(volatile int*)&flag_s;
@@ -596,6 +830,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       block_sync();
     }
     if (fl) {
+      if (QPF) {
+        drain();
+        block_sync();
+      }
       if (w < QB && cnt_s[w] <= kWarpKeys && needs_compaction(w)) warp_sort_keep(w);   // warp w <-> query w
       block_sync();
       for (int q = 0; q < QB; q++)
@@ -607,19 +845,24 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         for (int q = 0; q < QB; q++) warm |= tau_s[q] == __int_as_float(0x7f800000);
         warm_s = warm;
       }
+      if (QPF && tid < QB) thr_s[tid] = thr_of(tid);
     }
     block_sync();
     warm_x = warm_s;
+    if (QPF) {
+      thr_x[0] = pack2(thr_word(0), thr_word(2));
+      thr_x[1] = pack2(thr_word(4), thr_word(6));
+    } else {
 #pragma unroll
-    for (int tt = 0; tt < 4; tt++) {
-      tau_x[2 * tt] = tau_s[tt * 2 * X::G + g * 2];
-      tau_x[2 * tt + 1] = tau_s[tt * 2 * X::G + g * 2 + 1];
+      for (int tt = 0; tt < 4; tt++) {
+        tau_x[2 * tt] = tau_s[tt * 2 * X::G + g * 2];
+        tau_x[2 * tt + 1] = tau_s[tt * 2 * X::G + g * 2 + 1];
+      }
     }
     return nf == kScanWarps;
   };
 
   const uint32_t n32 = (uint32_t)p.n;
-  const float inf = __int_as_float(0x7f800000);
   const uint32_t flag_addr = smem_u32(&flag_s);
 
   int wdone = 0;                                         // codes of finished chunks of this warp
@@ -648,19 +891,56 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         for (int b8 = 0; b8 < 8; b8++) {
           const int S = hf * 8 + b8;
           const uint32_t a = (b8 & 1) ? (wr[b8 >> 1] >> 16) + base : ((wr[b8 >> 1] & 0xFFFFu) | base);
-          const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a);
-          const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
-          acc[0] = ffma2(acc[0], kp2, v0);
-          acc[1] = ffma2(acc[1], kp2, v1);
-          acc[2] = ffma2(acc[2], kp2, v2);
-          acc[3] = ffma2(acc[3], kp2, v3);
-          done[0] = ffma2(acc[0], cp2, done[0]);
-          done[1] = ffma2(acc[1], cp2, done[1]);
-          done[2] = ffma2(acc[2], cp2, done[2]);
-          done[3] = ffma2(acc[3], cp2, done[3]);
+          if constexpr (QPF) {
+            const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a);          // 2 x 4 queries
+            const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
+            acc[0] = ffma2(acc[0], kp2, v0);
+            acc[1] = ffma2(acc[1], kp2, v1);
+            done[0] = ffma2(acc[0], cp2, done[0]);
+            done[1] = ffma2(acc[1], cp2, done[1]);
+          } else {
+            const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a);
+            const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
+            acc[0] = ffma2(acc[0], kp2, v0);
+            acc[1] = ffma2(acc[1], kp2, v1);
+            acc[2] = ffma2(acc[2], kp2, v2);
+            acc[3] = ffma2(acc[3], kp2, v3);
+            done[0] = ffma2(acc[0], cp2, done[0]);
+            done[1] = ffma2(acc[1], cp2, done[1]);
+            done[2] = ffma2(acc[2], cp2, done[2]);
+            done[3] = ffma2(acc[3], cp2, done[3]);
+          }
         }
       }
-      if (t >= 1 && id < n32) {
+      if (QPF) {
+        if (t >= 1 && id < n32) {
+          // (T + 2048) - A per digit, exact in fp32 (integers < 2^24); + 2^24 aligns the integer with the mantissa (the
+          // one rounding, to even, can only turn a digit of 2047 into 2048: a spurious survivor, never a lost one)
+          const uint64_t neg1 = pack2(-1.0f, -1.0f);
+          uint64_t u0 = ffma2(done[0], neg1, thr2[0]), u1 = ffma2(done[1], neg1, thr2[1]);
+          if (NORMS) {
+            const float nqf = __fadd_rn(fmaf(nrm0, q_invs, q_c0), -12582912.0f);     // rint((norm - min norm)/s)
+            const uint64_t n2 = pack2(nqf, nqf), m4097 = pack2(-4097.0f, -4097.0f);
+            u0 = ffma2(n2, m4097, u0);
+            u1 = ffma2(n2, m4097, u1);
+          }
+          const uint64_t two24 = pack2(16777216.0f, 16777216.0f);
+          u0 = fadd2(u0, two24);
+          u1 = fadd2(u1, two24);
+          const uint32_t uw[4] = {(uint32_t)u0, (uint32_t)(u0 >> 32), (uint32_t)u1, (uint32_t)(u1 >> 32)};
+          if ((uw[0] | uw[1] | uw[2] | uw[3]) & 0x00400400u) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if ((uw[i >> 1] >> ((i & 1) ? 22 : 10)) & 1u) {
+                const int q = lane_query(i);
+                const int pos = atomicAdd(&pcnt_s[q], 1);
+                pend[(size_t)q * p.pcap + pos] = id;
+                if (pos >= p.psoft || (pos + 1 >= p.k && thr_s[q] == 2047)) atomicExch(&flag_s, 1);   // 2047: tau still +inf
+              }
+            }
+          }
+        }
+      } else if (t >= 1 && id < n32) {
         float dv[8];
         const uint64_t n2 = pack2(nrm0, nrm0);
         bool anyp = false;
@@ -698,8 +978,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
       if (raised || (warm && lds_volatile(flag_addr))) {
         service(wdone + t * X::NS);
+        if (QPF) {
+          thr2[0] = thr_x[0];
+          thr2[1] = thr_x[1];
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; i++) tau[i] = tau_x[i];
+          for (int i = 0; i < 8; i++) tau[i] = tau_x[i];
+        }
         warm = warm_x;
       }
     }
@@ -708,6 +993,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   if (lane == 0) atomicAdd(&nfin_s, 1);
   __syncwarp();
   while (!service(wdone)) {
+  }
+  if (QPF) {                                      // survivors noted since the last service()
+    drain();
+    block_sync();
   }
 
   // final phase: small buffers by their own warp (all at once), the rest block-wide
@@ -928,6 +1217,9 @@ struct rayuela_index {
   int64_t n = 0, id_offset = 0;
   int64_t nchunks = 0;   // 1024-code warp chunks of the skewed layout
   DevBuf norms, skew;    // fp32 norms (LSQ); skewed offset fields (skew_fields_kernel)
+  DevBuf codes;          // raw codes [n][m]: the pre-filter scan re-evaluates its survivors from them
+  float nmin = 0.f, nmax = 0.f;   // range of the norms (the pre-filter scan quantises them on the fly)
+  bool q16_ok = false;   // norms finite: the 16-bit pre-filter scan may be used
   // multi-device parent (rayuela_init / RAYUELA_B200_DEVICES, host arrays): one shard per device slot, no own buffers
   std::vector<rayuela_index*> shards;
   std::vector<DeviceSlot> slots;
@@ -952,8 +1244,9 @@ static int index_create_single(rayuela_index** out, int kind, const uint8_t* cod
   ix->id_offset = id_offset;
   cudaGetDevice(&ix->device);
   auto body = [&]() -> int {
-    InArg<uint8_t> raw;
-    RYL_TRY(raw.bind(codes, (size_t)n * m, dev, s));
+    RYL_TRY(ix->codes.alloc((size_t)n * m, s));
+    RYL_CUDA(cudaMemcpyAsync(ix->codes.p, codes, (size_t)n * m, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    struct { const uint8_t* d; } raw{ix->codes.as<uint8_t>()};
     ix->nchunks = (n + kChunkCodes - 1) / kChunkCodes;
     if (ix->period == 8) {
       const int64_t words = ix->nchunks * ScanX<8>::PERIODS * ScanX<8>::HALVES * ScanX<8>::NS;
@@ -970,6 +1263,20 @@ static int index_create_single(rayuela_index** out, int kind, const uint8_t* cod
       RYL_TRY(ix->norms.alloc((size_t)n * sizeof(float), s));
       RYL_CUDA(cudaMemcpyAsync(ix->norms.p, dbnorms, (size_t)n * sizeof(float),
                                dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+      DevBuf rng;
+      RYL_TRY(rng.alloc(2 * sizeof(unsigned int), s));
+      const unsigned int init[2] = {0xFFFFFFFFu, 0u};
+      RYL_CUDA(cudaMemcpyAsync(rng.p, init, sizeof init, cudaMemcpyHostToDevice, s));
+      RYL_LAUNCH(norm_range_kernel, (int)std::min<int64_t>((n + 255) / 256, sm_count() * 8), 256, 0, s,
+                 ix->norms.as<float>(), n, rng.as<unsigned int>());
+      unsigned int got[2];
+      RYL_CUDA(cudaMemcpyAsync(got, rng.p, sizeof got, cudaMemcpyDeviceToHost, s));
+      RYL_CUDA(cudaStreamSynchronize(s));
+      ix->nmin = ordered_to_f32(got[0]);
+      ix->nmax = ordered_to_f32(got[1]);
+      ix->q16_ok = got[0] <= got[1] && std::isfinite(ix->nmin) && std::isfinite(ix->nmax);
+    } else {
+      ix->q16_ok = true;
     }
     RYL_CUDA(cudaStreamSynchronize(s));
     return RAYUELA_OK;
@@ -995,6 +1302,7 @@ extern "C" int rayuela_index_free(rayuela_index* ix) {
     if (!ix->shards.empty()) cudaSetDevice(cur);
     ix->norms.release();
     ix->skew.release();
+    ix->codes.release();
     delete ix;
   }
   return RAYUELA_OK;
@@ -1137,6 +1445,25 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
     else
       RYL_LAUNCH(lut_kernel<RAYUELA_SCAN_PQ>, lg, 256, 0, s, qptr, cb_dev, lut.as<float>(), nqc, d, len, mh, tiled, bad, h);
     if (k > kmax) RYL_TRY(lb.alloc((size_t)nqc * sizeof(uint64_t), s));
+    // QPF: quantised twin of the tiles (exact results, half the shared-memory bytes per lookup; see scanx_kernel)
+    const char* q16_env = getenv("RAYUELA_B200_SCAN_PREFILTER");                        // tuning knob: 0 disables
+    const bool q16 = ix->q16_ok && !(q16_env && atoi(q16_env) == 0);
+    DevBuf lutq, tilep, qoff, qmu;
+    if (q16) {
+      RYL_TRY(lutq.alloc((size_t)qtiles * 16384 * sizeof(float), s));
+      RYL_TRY(tilep.alloc((size_t)qtiles * sizeof(float4), s));
+      RYL_TRY(qoff.alloc((size_t)qtiles * QT * sizeof(double), s));
+      RYL_TRY(qmu.alloc((size_t)qtiles * QT * sizeof(int), s));
+      if (period == 16) {
+        RYL_CUDA(cudaFuncSetAttribute(lut_quant_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        RYL_LAUNCH(lut_quant_kernel<16>, qtiles, 512, 131072, s, lut.as<float>(), lutq.as<float>(), tilep.as<float4>(),
+                   qoff.as<double>(), qmu.as<int>(), m, h, ix->nmin, ix->nmax, norms ? 1 : 0);
+      } else {
+        RYL_CUDA(cudaFuncSetAttribute(lut_quant_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
+        RYL_LAUNCH(lut_quant_kernel<8>, qtiles, 512, 131072, s, lut.as<float>(), lutq.as<float>(), tilep.as<float4>(),
+                   qoff.as<double>(), qmu.as<int>(), m, h, ix->nmin, ix->nmax, norms ? 1 : 0);
+      }
+    }
 
     for (int koff = 0; koff < k; koff += kmax) {
       const int kp = std::min(kmax, k - koff);
@@ -1177,7 +1504,10 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       slice_len = (slice_len + unit - 1) / unit * unit;
       S = (int)((ix->n + slice_len - 1) / slice_len);
 
-      DevBuf cand, part;
+      DevBuf cand, part, pend;
+      const int psoft = std::max(64, soft - (kp + (soft - kp) / 6));   // pending survivors + a buffer at the piggy limit fit cap
+      const int pcap = psoft + 3 * adds;
+      if (q16) RYL_TRY(pend.alloc((size_t)S * qtiles * QT * pcap * sizeof(uint32_t), s));
       RYL_TRY(cand.alloc((size_t)S * qtiles * QT * cap * sizeof(uint64_t), s));
       RYL_TRY(part.alloc((size_t)S * nqc * kp * sizeof(uint64_t), s));
       ScanXParams p;
@@ -1208,22 +1538,33 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       DevBuf redo;
       RYL_TRY(redo.alloc((size_t)S * qtiles * sizeof(int), s));
       p.redo = redo.as<int>();
-#define RYL_SCANX(PP, NN, SS)                                                                                        \
+      p.lutq = lutq.as<float>();
+      p.tilep = tilep.as<float4>();
+      p.qoff = qoff.as<double>();
+      p.qmu = qmu.as<int>();
+      p.codes = ix->codes.as<uint8_t>();
+      p.pend = pend.as<uint32_t>();
+      p.m = m;
+      p.pcap = pcap;
+      p.psoft = psoft;
+#define RYL_SCANX(PP, NN, SS, QQ)                                                                                    \
   {                                                                                                                  \
-    RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScanWarps * 32, smem, s, p);                           \
+    RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN, SS, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    RYL_LAUNCH((scanx_kernel<PP, NN, SS, QQ>), dim3(qtiles, S), kScanWarps * 32, smem, s, p);                       \
     if (SS) { /* redo launch: blocks whose speculation failed rerun exactly, all others exit at once */             \
       p.pass = 1;                                                                                                    \
-      RYL_LAUNCH((scanx_kernel<PP, NN, SS>), dim3(qtiles, S), kScanWarps * 32, smem, s, p);                         \
+      RYL_LAUNCH((scanx_kernel<PP, NN, SS, QQ>), dim3(qtiles, S), kScanWarps * 32, smem, s, p);                     \
     }                                                                                                                \
   }
+#define RYL_SCANX_Q(PP, NN, SS) { if (q16) RYL_SCANX(PP, NN, SS, true) else RYL_SCANX(PP, NN, SS, false) }
       if (period == 16) {
-        if (norms) { if (p.spec) RYL_SCANX(16, true, true) else RYL_SCANX(16, true, false) }
-        else { if (p.spec) RYL_SCANX(16, false, true) else RYL_SCANX(16, false, false) }
+        if (norms) { if (p.spec) RYL_SCANX_Q(16, true, true) else RYL_SCANX_Q(16, true, false) }
+        else { if (p.spec) RYL_SCANX_Q(16, false, true) else RYL_SCANX_Q(16, false, false) }
       } else {
-        if (norms) { if (p.spec) RYL_SCANX(8, true, true) else RYL_SCANX(8, true, false) }
-        else { if (p.spec) RYL_SCANX(8, false, true) else RYL_SCANX(8, false, false) }
+        if (norms) { if (p.spec) RYL_SCANX_Q(8, true, true) else RYL_SCANX_Q(8, true, false) }
+        else { if (p.spec) RYL_SCANX_Q(8, false, true) else RYL_SCANX_Q(8, false, false) }
       }
+#undef RYL_SCANX_Q
 #undef RYL_SCANX
       float* dq = d_dev + (size_t)qb * k + koff;
       int32_t* iq = i_dev + (size_t)qb * k + koff;

@@ -22,4 +22,4 @@ for i in (0, ils):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     print(f"m={m} n={n} ilsiter={i}: {ms:.2f} ms/step  {n/ms*1e3:,.0f} vectors/s  qerr={core.qerror(X, B, C):.4f}", flush=True)
-print("better% per iter:", [round(100*b/n,1) for _, b in r['stats']])
+print("steps executed/total:", core.last_icm_steps(), "exact:", core.last_icm_exact_steps())
