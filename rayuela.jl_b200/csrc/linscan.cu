@@ -440,6 +440,32 @@ __global__ void skew_fields_kernel(const uint8_t* __restrict__ codes, uint4* __r
   }
 }
 
+// Fq[chunk][t][half][p] (uint4 = 8 fields), the pre-filter scan's copy: stream p = codes chunk*1024 + NS*t + p
+// (t = 0..L-1), one code per period, its codebooks ROTATED by the lane: step S holds codebook (S + p) mod P, so the lanes
+// of a half-warp sit on P different bank-pairs at every step while all of them start and finish a code together.
+template <int P>
+__global__ void rot_fields_kernel(const uint8_t* __restrict__ codes, uint4* __restrict__ F, int64_t n, int m,
+                                  int64_t nchunks) {
+  using X = ScanX<P>;
+  const int64_t total = nchunks * X::L * X::HALVES * X::NS;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i % X::NS);
+    const int hf = (int)((i / X::NS) % X::HALVES);
+    const int t = (int)((i / (X::NS * X::HALVES)) % X::L);
+    const int64_t chunk = i / ((int64_t)X::NS * X::HALVES * X::L);
+    const int64_t id = chunk * kChunkCodes + (int64_t)X::NS * t + p;
+    uint32_t f[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int k = (hf * 8 + b + p) & (P - 1);
+      uint32_t field = (uint32_t)k << 3;
+      if (id < n && k < m) field |= (uint32_t)codes[id * m + k] << 7;
+      f[b] = field;
+    }
+    F[i] = make_uint4(f[0] | (f[1] << 16), f[2] | (f[3] << 16), f[4] | (f[5] << 16), f[6] | (f[7] << 16));
+  }
+}
+
 struct ScanXParams {
   const uint4* F;        // skewed offset fields
   const float* norms;    // [n] or nullptr
@@ -458,6 +484,7 @@ struct ScanXParams {
   // QPF (quantised pre-filter scan, see scanx_kernel): quantised tiles + their parameters, the raw codes for the exact
   // re-evaluation of the survivors, and the per-query lists of survivors awaiting it
   const float* lutq;     // tiled [qtiles][16384]: two queries per word (lut_quant_kernel)
+  const uint4* Fq;       // rotated offset fields (rot_fields_kernel)
   const float4* tilep;   // [qtiles] {s, 1/s, norm rounding constant, -}
   const double* qoff;    // [qtiles*QB] sum_k min_c LUT + min norm: the distance that quantises to 0
   const int* qmu;        // [qtiles*QB] threshold margin in units of s
@@ -865,6 +892,106 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   const uint32_t n32 = (uint32_t)p.n;
   const uint32_t flag_addr = smem_u32(&flag_s);
 
+  if constexpr (QPF) {
+    // Pre-filter loop.  Integer sums are exact in any order, so a lane's code needs no fixed codebook order here: the index
+    // holds a second, ROTATED copy of the offset fields (rot_fields_kernel) in which lane j = lane mod P visits codebook
+    // (S + j) mod P at step S -- the lanes of a half-warp are still at P different bank-pairs at every instant, but every
+    // lane starts and completes its code together with the period: no restart multiply, no capture, no skew tail; a step is
+    // 2 LDS.64 + 2 packed adds for 8 queries.  The fields come from L2 (latency ~ a period and a half of this loop), so they
+    // are fetched TWO periods ahead into two alternating register sets, reloaded as soon as the period's shared-memory
+    // addresses have been formed from them; same for the norms.
+    constexpr int LQ = X::L;                                  // periods per chunk = codes per stream
+    int wdone = 0;
+    const uint4* fq0 = nullptr;
+    const float* np0 = nullptr;
+    uint32_t id0 = 0;
+    auto period_q = [&](uint4 (&Wc)[X::HALVES], float& nc, const int t) {
+      const int raised = lds_volatile(flag_addr);
+      uint32_t ad[P];
+#pragma unroll
+      for (int hf = 0; hf < X::HALVES; hf++) {
+        const uint32_t wr[4] = {Wc[hf].x, Wc[hf].y, Wc[hf].z, Wc[hf].w};
+#pragma unroll
+        for (int b8 = 0; b8 < 8; b8++)
+          ad[hf * 8 + b8] = (b8 & 1) ? (wr[b8 >> 1] >> 16) + base : ((wr[b8 >> 1] & 0xFFFFu) | base);
+      }
+      const uint32_t id = id0 + (uint32_t)(t * X::NS);         // the code this period evaluates
+      const float nrm = nc;
+      if (t + 2 < LQ) {
+#pragma unroll
+        for (int hf = 0; hf < X::HALVES; hf++) Wc[hf] = __ldg(fq0 + (t + 2) * (X::HALVES * X::NS) + hf * X::NS);
+        if (NORMS) {
+          nc = 0.f;
+          if (id + 2 * X::NS < n32) nc = __ldg(np0 + (t + 2) * X::NS);
+        }
+      }
+      uint64_t a0 = lds64<0>(ad[0]), a1 = lds64<32768>(ad[0]);
+#pragma unroll
+      for (int S = 1; S < P; S++) {
+        a0 = fadd2(a0, lds64<0>(ad[S]));
+        a1 = fadd2(a1, lds64<32768>(ad[S]));
+      }
+        if (id < n32) {
+          // (T + 2048) - A per digit, exact in fp32 (integers < 2^24); + 2^24 aligns the integer with the mantissa (the
+          // one rounding, to even, can only turn a digit of 2047 into 2048: a spurious survivor, never a lost one)
+          const uint64_t neg1 = pack2(-1.0f, -1.0f);
+          uint64_t u0 = ffma2(a0, neg1, thr2[0]), u1 = ffma2(a1, neg1, thr2[1]);
+          if (NORMS) {
+            const float nqf = __fadd_rn(fmaf(nrm, q_invs, q_c0), -12582912.0f);     // rint((norm - min norm)/s)
+            const uint64_t n2 = pack2(nqf, nqf), m4097 = pack2(-4097.0f, -4097.0f);
+            u0 = ffma2(n2, m4097, u0);
+            u1 = ffma2(n2, m4097, u1);
+          }
+          const uint64_t two24 = pack2(16777216.0f, 16777216.0f);
+          u0 = fadd2(u0, two24);
+          u1 = fadd2(u1, two24);
+          const uint32_t uw[4] = {(uint32_t)u0, (uint32_t)(u0 >> 32), (uint32_t)u1, (uint32_t)(u1 >> 32)};
+          if ((uw[0] | uw[1] | uw[2] | uw[3]) & 0x00400400u) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              if ((uw[i >> 1] >> ((i & 1) ? 22 : 10)) & 1u) {
+                const int q = lane_query(i);
+                const int pos = atomicAdd(&pcnt_s[q], 1);
+                pend[(size_t)q * p.pcap + pos] = id;
+                if (pos >= p.psoft || (pos + 1 >= p.k && thr_s[q] == 2047)) atomicExch(&flag_s, 1);   // 2047: tau still +inf
+              }
+            }
+          }
+        }
+      // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
+      if (raised || (warm && lds_volatile(flag_addr))) {
+        service(wdone + (t + 1) * X::NS);
+        thr2[0] = thr_x[0];
+        thr2[1] = thr_x[1];
+        warm = warm_x;
+      }
+    };
+    for (int64_t chunk = c0 + w; chunk < c1; chunk += kScanWarps, wdone += kChunkCodes) {
+      fq0 = p.Fq + chunk * (LQ * X::HALVES * X::NS) + pidx;
+      np0 = p.norms + chunk * kChunkCodes + pidx;
+      id0 = (uint32_t)(chunk * kChunkCodes) + pidx;
+      uint4 WA[X::HALVES], WB[X::HALVES];
+#pragma unroll
+      for (int hf = 0; hf < X::HALVES; hf++) {
+        WA[hf] = __ldg(fq0 + hf * X::NS);
+        WB[hf] = __ldg(fq0 + X::HALVES * X::NS + hf * X::NS);
+      }
+      float nA = 0.f, nB = 0.f;
+      if (NORMS && id0 < n32) nA = __ldg(np0);
+      if (NORMS && id0 + X::NS < n32) nB = __ldg(np0 + X::NS);
+      for (int t = 0; t < LQ; t += 2) {
+        period_q(WA, nA, t);
+        period_q(WB, nB, t + 1);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&nfin_s, 1);
+    __syncwarp();
+    while (!service(wdone)) {
+    }
+    drain();                                      // survivors noted since the last service()
+    block_sync();
+  } else {
   int wdone = 0;                                         // codes of finished chunks of this warp
   for (int64_t chunk = c0 + w; chunk < c1; chunk += kScanWarps, wdone += kChunkCodes) {
     const uint4* fp = p.F + chunk * (X::PERIODS * X::HALVES * X::NS) + pidx;
@@ -891,56 +1018,19 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         for (int b8 = 0; b8 < 8; b8++) {
           const int S = hf * 8 + b8;
           const uint32_t a = (b8 & 1) ? (wr[b8 >> 1] >> 16) + base : ((wr[b8 >> 1] & 0xFFFFu) | base);
-          if constexpr (QPF) {
-            const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a);          // 2 x 4 queries
-            const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
-            acc[0] = ffma2(acc[0], kp2, v0);
-            acc[1] = ffma2(acc[1], kp2, v1);
-            done[0] = ffma2(acc[0], cp2, done[0]);
-            done[1] = ffma2(acc[1], cp2, done[1]);
-          } else {
-            const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a);
-            const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
-            acc[0] = ffma2(acc[0], kp2, v0);
-            acc[1] = ffma2(acc[1], kp2, v1);
-            acc[2] = ffma2(acc[2], kp2, v2);
-            acc[3] = ffma2(acc[3], kp2, v3);
-            done[0] = ffma2(acc[0], cp2, done[0]);
-            done[1] = ffma2(acc[1], cp2, done[1]);
-            done[2] = ffma2(acc[2], cp2, done[2]);
-            done[3] = ffma2(acc[3], cp2, done[3]);
-          }
+          const uint64_t v0 = lds64<0>(a), v1 = lds64<32768>(a), v2 = lds64<65536>(a), v3 = lds64<98304>(a);
+          const uint64_t kp2 = pack2(keep[S], keep[S]), cp2 = pack2(capf[S], capf[S]);
+          acc[0] = ffma2(acc[0], kp2, v0);
+          acc[1] = ffma2(acc[1], kp2, v1);
+          acc[2] = ffma2(acc[2], kp2, v2);
+          acc[3] = ffma2(acc[3], kp2, v3);
+          done[0] = ffma2(acc[0], cp2, done[0]);
+          done[1] = ffma2(acc[1], cp2, done[1]);
+          done[2] = ffma2(acc[2], cp2, done[2]);
+          done[3] = ffma2(acc[3], cp2, done[3]);
         }
       }
-      if (QPF) {
-        if (t >= 1 && id < n32) {
-          // (T + 2048) - A per digit, exact in fp32 (integers < 2^24); + 2^24 aligns the integer with the mantissa (the
-          // one rounding, to even, can only turn a digit of 2047 into 2048: a spurious survivor, never a lost one)
-          const uint64_t neg1 = pack2(-1.0f, -1.0f);
-          uint64_t u0 = ffma2(done[0], neg1, thr2[0]), u1 = ffma2(done[1], neg1, thr2[1]);
-          if (NORMS) {
-            const float nqf = __fadd_rn(fmaf(nrm0, q_invs, q_c0), -12582912.0f);     // rint((norm - min norm)/s)
-            const uint64_t n2 = pack2(nqf, nqf), m4097 = pack2(-4097.0f, -4097.0f);
-            u0 = ffma2(n2, m4097, u0);
-            u1 = ffma2(n2, m4097, u1);
-          }
-          const uint64_t two24 = pack2(16777216.0f, 16777216.0f);
-          u0 = fadd2(u0, two24);
-          u1 = fadd2(u1, two24);
-          const uint32_t uw[4] = {(uint32_t)u0, (uint32_t)(u0 >> 32), (uint32_t)u1, (uint32_t)(u1 >> 32)};
-          if ((uw[0] | uw[1] | uw[2] | uw[3]) & 0x00400400u) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              if ((uw[i >> 1] >> ((i & 1) ? 22 : 10)) & 1u) {
-                const int q = lane_query(i);
-                const int pos = atomicAdd(&pcnt_s[q], 1);
-                pend[(size_t)q * p.pcap + pos] = id;
-                if (pos >= p.psoft || (pos + 1 >= p.k && thr_s[q] == 2047)) atomicExch(&flag_s, 1);   // 2047: tau still +inf
-              }
-            }
-          }
-        }
-      } else if (t >= 1 && id < n32) {
+      if (t >= 1 && id < n32) {
         float dv[8];
         const uint64_t n2 = pack2(nrm0, nrm0);
         bool anyp = false;
@@ -978,13 +1068,8 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
       if (raised || (warm && lds_volatile(flag_addr))) {
         service(wdone + t * X::NS);
-        if (QPF) {
-          thr2[0] = thr_x[0];
-          thr2[1] = thr_x[1];
-        } else {
 #pragma unroll
-          for (int i = 0; i < 8; i++) tau[i] = tau_x[i];
-        }
+        for (int i = 0; i < 8; i++) tau[i] = tau_x[i];
         warm = warm_x;
       }
     }
@@ -994,9 +1079,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   __syncwarp();
   while (!service(wdone)) {
   }
-  if (QPF) {                                      // survivors noted since the last service()
-    drain();
-    block_sync();
+
   }
 
   // final phase: small buffers by their own warp (all at once), the rest block-wide
@@ -1218,6 +1301,7 @@ struct rayuela_index {
   int64_t nchunks = 0;   // 1024-code warp chunks of the skewed layout
   DevBuf norms, skew;    // fp32 norms (LSQ); skewed offset fields (skew_fields_kernel)
   DevBuf codes;          // raw codes [n][m]: the pre-filter scan re-evaluates its survivors from them
+  DevBuf rot;            // rotated offset fields of the pre-filter scan (rot_fields_kernel)
   float nmin = 0.f, nmax = 0.f;   // range of the norms (the pre-filter scan quantises them on the fly)
   bool q16_ok = false;   // norms finite: the 16-bit pre-filter scan may be used
   // multi-device parent (rayuela_init / RAYUELA_B200_DEVICES, host arrays): one shard per device slot, no own buffers
@@ -1253,11 +1337,17 @@ static int index_create_single(rayuela_index** out, int kind, const uint8_t* cod
       RYL_TRY(ix->skew.alloc((size_t)words * sizeof(uint4), s));
       int blocks = (int)std::min<int64_t>((words + 255) / 256, 148 * 16);
       RYL_LAUNCH(skew_fields_kernel<8>, blocks, 256, 0, s, raw.d, ix->skew.as<uint4>(), n, m, ix->nchunks);
+      const int64_t rwords = ix->nchunks * ScanX<8>::L * ScanX<8>::HALVES * ScanX<8>::NS;
+      RYL_TRY(ix->rot.alloc((size_t)rwords * sizeof(uint4), s));
+      RYL_LAUNCH(rot_fields_kernel<8>, blocks, 256, 0, s, raw.d, ix->rot.as<uint4>(), n, m, ix->nchunks);
     } else {
       const int64_t words = ix->nchunks * ScanX<16>::PERIODS * ScanX<16>::HALVES * ScanX<16>::NS;
       RYL_TRY(ix->skew.alloc((size_t)words * sizeof(uint4), s));
       int blocks = (int)std::min<int64_t>((words + 255) / 256, 148 * 16);
       RYL_LAUNCH(skew_fields_kernel<16>, blocks, 256, 0, s, raw.d, ix->skew.as<uint4>(), n, m, ix->nchunks);
+      const int64_t rwords = ix->nchunks * ScanX<16>::L * ScanX<16>::HALVES * ScanX<16>::NS;
+      RYL_TRY(ix->rot.alloc((size_t)rwords * sizeof(uint4), s));
+      RYL_LAUNCH(rot_fields_kernel<16>, blocks, 256, 0, s, raw.d, ix->rot.as<uint4>(), n, m, ix->nchunks);
     }
     if (kind == RAYUELA_SCAN_LSQ) {
       RYL_TRY(ix->norms.alloc((size_t)n * sizeof(float), s));
@@ -1303,6 +1393,7 @@ extern "C" int rayuela_index_free(rayuela_index* ix) {
     ix->norms.release();
     ix->skew.release();
     ix->codes.release();
+    ix->rot.release();
     delete ix;
   }
   return RAYUELA_OK;
@@ -1539,6 +1630,7 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       RYL_TRY(redo.alloc((size_t)S * qtiles * sizeof(int), s));
       p.redo = redo.as<int>();
       p.lutq = lutq.as<float>();
+      p.Fq = ix->rot.as<uint4>();
       p.tilep = tilep.as<float4>();
       p.qoff = qoff.as<double>();
       p.qmu = qmu.as<int>();

@@ -5,6 +5,9 @@
 //   V=3  8 FFMA2 per step, no LDS              (FFMA2 pipe alone)
 //   V=4  16 FFMA per step, no LDS
 //   V=5  4 LDS.64 + 4 FFMA2 + 4 FADD2
+//   V=6  2 LDS.64 + 4 FFMA2                    (the pre-filter scan's mix: 4 queries per LDS.64)
+//   V=7  2 LDS.64 + 2 FADD2                    (shared-memory pipe alone at that width)
+//   V=8  2 LDS.64 + 4 IMAD + 4 LOP3            (the same step on packed 16-bit integers)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o lds_ffma2 lds_ffma2.cu
 #include <cstdio>
 #include <cstdint>
@@ -28,6 +31,8 @@ __global__ void __launch_bounds__(512, 1) k(const uint32_t* __restrict__ codes, 
   uint64_t acc[4] = {0, 0, 0, 0}, done[4] = {0, 0, 0, 0};
   const uint64_t kp = pack2(lane == 40 ? 0.f : 1.f, lane == 40 ? 0.f : 1.f), cp = pack2(lane == 41 ? 1.f : 0.f, lane == 41 ? 1.f : 0.f);
   uint32_t w = codes[threadIdx.x + blockIdx.x * 512];
+  uint32_t ki = lane == 40 ? 0u : 1u, ci = lane == 41 ? 0xFFFFFFFFu : 0u;
+  asm volatile("" : "+r"(ki), "+r"(ci));
   long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
 #pragma unroll
@@ -35,7 +40,16 @@ __global__ void __launch_bounds__(512, 1) k(const uint32_t* __restrict__ codes, 
       const uint32_t a = ((w >> (s * 3)) & 0x7F80u) + off;
       uint64_t v0, v1, v2, v3;
       if (V <= 2 || V == 5) { v0 = lds64<0>(a); v1 = lds64<32768>(a); v2 = lds64<65536>(a); v3 = lds64<98304>(a); }
+      else if (V >= 6) { v0 = lds64<0>(a); v1 = lds64<32768>(a); v2 = 0; v3 = 0; }
       else { v0 = a; v1 = a + 1; v2 = a + 2; v3 = a + 3; }
+      if (V == 6) { acc[0] = ffma2(acc[0], kp, v0); acc[1] = ffma2(acc[1], kp, v1); done[0] = ffma2(acc[0], cp, done[0]); done[1] = ffma2(acc[1], cp, done[1]); }
+      if (V == 7) { acc[0] = fadd2(acc[0], v0); acc[1] = fadd2(acc[1], v1); }
+      if (V == 8) {
+        uint32_t x[4] = {(uint32_t)v0, (uint32_t)(v0 >> 32), (uint32_t)v1, (uint32_t)(v1 >> 32)};
+        uint32_t* a32 = reinterpret_cast<uint32_t*>(acc); uint32_t* d32 = reinterpret_cast<uint32_t*>(done);
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a32[i] = a32[i] * ki + x[i]; d32[i] |= a32[i] & ci; }
+      }
       if (V == 0) { acc[0] = fadd2(acc[0], v0); acc[1] = fadd2(acc[1], v1); acc[2] = fadd2(acc[2], v2); acc[3] = fadd2(acc[3], v3); }
       if (V == 1 || V == 3) {
         acc[0] = ffma2(acc[0], kp, v0); acc[1] = ffma2(acc[1], kp, v1); acc[2] = ffma2(acc[2], kp, v2); acc[3] = ffma2(acc[3], kp, v3);
@@ -87,5 +101,6 @@ int main() {
   const int iters = 20000;
   run<0>(codes, out, clk, iters); run<1>(codes, out, clk, iters); run<2>(codes, out, clk, iters);
   run<3>(codes, out, clk, iters); run<4>(codes, out, clk, iters); run<5>(codes, out, clk, iters);
+  run<6>(codes, out, clk, iters); run<7>(codes, out, clk, iters); run<8>(codes, out, clk, iters);
   return 0;
 }
