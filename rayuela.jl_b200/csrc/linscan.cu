@@ -917,20 +917,31 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       }
       const uint32_t id = id0 + (uint32_t)(t * X::NS);         // the code this period evaluates
       const float nrm = nc;
-      if (t + 2 < LQ) {
+#ifndef QPF_VARIANT
+#define QPF_VARIANT 3
+#endif
+      auto prefetch = [&]() {
+        if (t + 2 < LQ) {
 #pragma unroll
-        for (int hf = 0; hf < X::HALVES; hf++) Wc[hf] = __ldg(fq0 + (t + 2) * (X::HALVES * X::NS) + hf * X::NS);
-        if (NORMS) {
-          nc = 0.f;
-          if (id + 2 * X::NS < n32) nc = __ldg(np0 + (t + 2) * X::NS);
+          for (int hf = 0; hf < X::HALVES; hf++) Wc[hf] = __ldg(fq0 + (t + 2) * (X::HALVES * X::NS) + hf * X::NS);
+          if (NORMS) {
+            if (QPF_VARIANT & 2) {
+              nc = __ldg(p.norms + min(id + 2 * X::NS, n32 - 1));
+            } else {
+              nc = 0.f;
+              if (id + 2 * X::NS < n32) nc = __ldg(np0 + (t + 2) * X::NS);
+            }
+          }
         }
-      }
+      };
+      if (!(QPF_VARIANT & 1)) prefetch();
       uint64_t a0 = lds64<0>(ad[0]), a1 = lds64<32768>(ad[0]);
 #pragma unroll
       for (int S = 1; S < P; S++) {
         a0 = fadd2(a0, lds64<0>(ad[S]));
         a1 = fadd2(a1, lds64<32768>(ad[S]));
       }
+      if (QPF_VARIANT & 1) prefetch();
         if (id < n32) {
           // (T + 2048) - A per digit, exact in fp32 (integers < 2^24); + 2^24 aligns the integer with the mantissa (the
           // one rounding, to even, can only turn a digit of 2047 into 2048: a spurious survivor, never a lost one)
@@ -961,9 +972,13 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
       if (raised || (warm && lds_volatile(flag_addr))) {
         service(wdone + (t + 1) * X::NS);
-        thr2[0] = thr_x[0];
-        thr2[1] = thr_x[1];
-        warm = warm_x;
+        // The refreshed thresholds are rebuilt HERE from shared memory (conversions = real consumers on this cold path),
+        // not handed back through service()'s address-taken locals: those come back as local-memory loads whose
+        // scoreboard ptxas shares with the field prefetches, and the next period's threshold test then waits on it --
+        // every other period stalled until its own prefetch had landed (ncu: 25 % of the kernel on that one FFMA2).
+        thr2[0] = pack2(thr_word(0), thr_word(2));
+        thr2[1] = pack2(thr_word(4), thr_word(6));
+        warm = lds_volatile(smem_u32(&warm_s));
       }
     };
     for (int64_t chunk = c0 + w; chunk < c1; chunk += kScanWarps, wdone += kChunkCodes) {
