@@ -245,6 +245,78 @@ def test_scan_speculative_threshold_failure_is_redone_exactly(rb, monkeypatch, m
     assert np.array_equal(i1, i0) and np.array_equal(bits(d1), bits(d0))
 
 
+@pytest.mark.parametrize("case", ["outlier_norms", "offset_tables", "flat_tables", "outlier_query", "near_ties",
+                                  "negative_zero", "tiny_h"])
+@pytest.mark.parametrize("m,k", [(8, 1), (8, 200), (16, 50), (5, 1000)])
+def test_scan_prefilter_degenerate_inputs(rb, monkeypatch, case, m, k):
+    """The scan's quantised pre-filter (two queries per fp32 word, exact re-evaluation of its survivors) must return
+    the reference's bits whatever the quantisation does to the data: one huge norm stretching the tile's scale, tables
+    with a large common offset (fp32 rounding slack of the exact chain dominates the window), all-equal tables (scale
+    0 -> 1), one query with a 1e4 x larger range sharing the tile scale with the others, distances that differ in the
+    last bits only, and the -0.0 / h < 256 corners.  Same bits with the pre-filter off."""
+    r = np.random.default_rng(1000 + m + k)
+    n, nq, d, h = 60000, 21, 32, 256
+    kind = orc.LSQ
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    Xq = r.standard_normal((nq, d)).astype(np.float32)
+    cb = r.standard_normal((m * 256, d)).astype(np.float32)
+    nrm = (r.standard_normal(n) * 3).astype(np.float32)
+    if case == "outlier_norms":
+        nrm[r.integers(0, n, 3)] = np.float32(1e9)
+        nrm[r.integers(0, n, 3)] = np.float32(-1e9)
+    elif case == "offset_tables":
+        kind = orc.CQ                                  # LUT = ||q - c||^2 with a huge common part
+        cb += np.float32(300.0)
+        nrm = None
+    elif case == "flat_tables":
+        cb[:] = np.float32(0.25)
+        nrm[:] = np.float32(1.5)                       # every distance identical: pure id order
+    elif case == "outlier_query":
+        Xq[3] *= np.float32(1e4)
+    elif case == "near_ties":
+        cb = np.round(cb * 4) / np.float32(4)          # few distinct table values, many exact and near ties
+        Xq = np.round(Xq * 2) / np.float32(2)
+        B = r.integers(0, 6, (n, m), dtype=np.uint8)
+        nrm = (np.round(r.standard_normal(n) * 8) / 8).astype(np.float32)
+    elif case == "negative_zero":
+        Xq[5] = 0.0                                    # LUT entries -0.0 / +0.0
+        nrm[::7] = np.float32(-0.0)
+    elif case == "tiny_h":
+        h = 16
+        B = r.integers(0, h, (n, m), dtype=np.uint8)
+        cb = r.standard_normal((m * h, d)).astype(np.float32)
+    fn = orc.ref_linscan if orc.have_ref() else orc.linscan
+    d0, i0 = fn(kind, B, Xq, cb, k, nrm) if h == 256 else fn(kind, B, Xq, cb, k, nrm, h=h)
+    for val in ("1", "0"):
+        monkeypatch.setenv("RAYUELA_B200_SCAN_PREFILTER", val)
+        ix = rb.core.Index(kind, B, nrm, h=h) if h != 256 else rb.core.Index(kind, B, nrm)
+        d1, i1 = ix.search(Xq, cb, k)
+        assert np.array_equal(i1, i0), (case, val)
+        assert np.array_equal(bits(d1), bits(d0)), (case, val)
+
+
+@pytest.mark.parametrize("with_inf", [True, False])
+def test_scan_prefilter_non_finite_norms(rb, with_inf):
+    """An infinite norm cannot be quantised: the index then scans with the plain fp32 loop.  NaN norms are skipped when
+    the norm range is taken, so the pre-filter stays on; either way a NaN distance is never returned and +inf ones
+    sort last, as ever."""
+    r = np.random.default_rng(77)
+    n, nq, d, m, k = 20000, 9, 32, 8, 20
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    Xq = r.standard_normal((nq, d)).astype(np.float32)
+    cb = r.standard_normal((m * 256, d)).astype(np.float32)
+    nrm = (r.standard_normal(n) * 3).astype(np.float32)
+    nrm[100] = np.inf if with_inf else np.nan
+    nrm[200] = np.nan
+    fn = orc.ref_linscan if orc.have_ref() else orc.linscan
+    good = np.ones(n, bool)
+    good[[100, 200]] = False
+    d0, i0 = fn(orc.LSQ, B[good], Xq, cb, k, nrm[good])
+    ids = np.flatnonzero(good) + 1
+    d1, i1 = rb.core.Index(orc.LSQ, B, nrm).search(Xq, cb, k)
+    assert np.array_equal(i1, ids[i0 - 1]) and np.array_equal(bits(d1), bits(d0))
+
+
 def test_icm_prefilter_on_and_off_agree(rb, monkeypatch):
     r = np.random.default_rng(3)
     n, d, m = 5000, 48, 8
