@@ -481,6 +481,9 @@ def run_ours(args, cfg):
     del rec
     index = core.Index(core.SCAN_LSQ, Bwork, dbnorms, id_offset=g0)
     res = {}
+    if os.environ.get("BENCH_DUMP_SCAN"):                 # the scan's inputs, for tools/scan_file.py
+        np.savez(os.environ["BENCH_DUMP_SCAN"], B=Bwork.cpu().numpy(), nrm=dbnorms.cpu().numpy(), Q=Q.cpu().numpy(),
+                 C=C.cpu().numpy())
 
     def scan_step():
         dl, il = index.search(Q, C, k)
@@ -614,15 +617,20 @@ def run_ours(args, cfg):
     scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base
     tr2 = ncu_traffic("scan_m%d_n%d_nq%d_k%d" % (m, n, nq, k))
     lookups = float(nq) * n * m / (scan_per * 1e-3)
+    prefilter = os.environ.get("RAYUELA_B200_SCAN_PREFILTER", "1") != "0"
+    per_clk = 64 if prefilter else 32                         # (query, code byte) lookups per clock per SM the pipe can serve
     scan_roof = {"bound": "hbm", "achieved": scan_bytes / (scan_per * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
                  "unit": "GB/s", "traffic": tr2["bytes"] if tr2 else None, "traffic_source": tr2, "peak_source": pk_src,
-                 "kernel": "scanx_kernel<%d,true,%s>" % (8 if m <= 8 else 16, "true" if k >= 16 else "false"),
-                 "smem_lookups_per_s": lookups, "smem_lookup_peak": 148 * 32 * sm_mhz * 1e6,
-                 "smem_lookup_frac": lookups / (148 * 32 * sm_mhz * 1e6),
+                 "kernel": "scanx_kernel<%d,true,%s,%s>" % (8 if m <= 8 else 16, "true" if k >= 16 else "false",
+                                                            "true" if prefilter else "false"),
+                 "smem_lookups_per_s": lookups, "smem_lookup_peak": 148 * per_clk * sm_mhz * 1e6,
+                 "smem_lookup_frac": lookups / (148 * per_clk * sm_mhz * 1e6),
                  "note": "algorithmic bytes = nq*n*(m+4): what the reference streams per query "
                          "(pairwise_byte.cpp:56-83); whole search step (LUT + scan + merge) in the denominator; frac "
                          "can exceed 1 because codes are re-read from L2 across a query tile (see traffic); the "
-                         "ceiling that binds is the shared-memory gather rate (smem_lookup_frac, 32 lookups/clk/SM)"}
+                         "ceiling that binds is the shared-memory gather rate (smem_lookup_frac): 128 B/clk/SM = 32 "
+                         "fp32 lookups, or 64 lookups of the quantised pre-filter's 2-byte entries (two queries per "
+                         "fp32 word; survivors re-evaluated exactly, results bit-identical)"}
     scan_roof["frac"] = scan_roof["achieved"] / scan_roof["peak"]
 
     primary_icm = args.path == "icm"

@@ -109,24 +109,26 @@ __global__ void __launch_bounds__(256) lut_relayout_kernel(const float* __restri
 
 // K4q: quantised twin of one fp32 LUT tile for the pre-filter scan (QPF, see scanx_kernel).  One block per query tile:
 //   lo[q][k], hi[q][k] = min / max over the valid entries c < h of codebook k < m
-//   s      = max_q (sum_k (hi - lo) + norm range) / 2000              one scale per tile (1 if that is 0)
+//   s      = max_q (sum_k (hi - lo) + (norm cap - min norm)) / 2000   one scale per tile (1 if that is 0)
 //   v      = rint((LUT - lo[q][k]) / s)  (+ 1 for k = 0)              two queries per fp32 word as v_hi * 4096 + v_lo, laid
 //            out like the fp32 tile with 4 queries per 8-byte entry:
 //            P = 8: [tt2][c][g*8 + k][e2], queries tt2*8 + g*4 + 2*e2 (+1);   P = 16: [tt2][c][k][e2], queries tt2*4 + 2*e2 (+1)
-//   off_q  = sum_k lo[q][k] + min norm;   mu_q = ceil(0.5 m + 2.6) + 1 + ceil((m+1) 2^-23 (sum_k max|LUT| + max|norm|) / s)
-// so that A = sum_k v + rint((norm - min norm)/s) <= 2000 + m/2 + 3 < 2^11 and every code with exact fp32 distance
-// E <= tau has A <= floor((tau - off_q)/s) + mu_q: m roundings of 0.5 (+ the division's), 1.5 for the norm (its rint, the
-// rounded constant of the magic-number conversion), 1 for the offset of codebook 0, and the fp32 roundings of the exact chain.
+//   off_q  = sum_k lo[q][k] + norm0 (the norm that quantises to 0, <= the minimum);
+//   mu_q   = ceil(0.5 (m + 1) + 0.1) + 1 + ceil((m+1) 2^-23 (sum_k max|LUT| + max|norm|) / s)
+// so that A = sum_k v + min(rint((norm - norm0)/s), cap) <= 2000 + m/2 + 3 < 2^11 and every code with exact fp32 distance
+// E <= tau has A <= floor((tau - off_q)/s) + mu_q: m + 1 roundings of 0.5 (+ the divisions'), 1 for the offset of
+// codebook 0, and the fp32 roundings of the exact chain.
 template <int P>
 __global__ void __launch_bounds__(512) lut_quant_kernel(const float* __restrict__ lut, float* __restrict__ lutq,
                                                         float4* __restrict__ tilep, double* __restrict__ qoff,
                                                         int* __restrict__ qmu, int m, int h, float nmin, float nmax,
-                                                        int has_norms) {
+                                                        float ncap, int has_norms) {
   constexpr int QB = P == 8 ? 16 : 8;
   extern __shared__ __align__(16) float tile_s[];          // 32768 floats
   __shared__ unsigned int mn_s[16 * 16], mx_s[16 * 16];    // ordered-uint images, [q][k]
   __shared__ double rng_s[16], off_s[16], bmax_s[16];
   __shared__ float s_s;
+  __shared__ double koff_s;
   const int tid = threadIdx.x;
   const float4* src = reinterpret_cast<const float4*>(lut + (size_t)blockIdx.x * 32768);
   for (int i = tid; i < 8192; i += 512) reinterpret_cast<float4*>(tile_s)[i] = __ldg(src + i);
@@ -172,7 +174,9 @@ __global__ void __launch_bounds__(512) lut_quant_kernel(const float* __restrict_
     bmax_s[tid] = bm;
   }
   __syncthreads();
-  const double nrange = has_norms ? (double)nmax - (double)nmin : 0.0;
+  // norms are quantised up to ncap only (index_create: mean + 4 sigma, at most the maximum) and SATURATE above it: a
+  // saturated code merely looks closer than it is (a spurious survivor at worst), and a few outliers no longer set the scale
+  const double nrange = has_norms ? (double)ncap - (double)nmin : 0.0;
   if (tid == 0) {
     double r = 0;
     for (int q = 0; q < QB; q++) r = fmax(r, rng_s[q]);
@@ -180,15 +184,20 @@ __global__ void __launch_bounds__(512) lut_quant_kernel(const float* __restrict_
     if (!(sc > 0.f) || !(sc < __int_as_float(0x7f800000))) sc = 1.0f;
     s_s = sc;
     const float inv = __fdiv_rn(1.0f, sc);
-    tilep[blockIdx.x] = make_float4(sc, inv, has_norms ? (float)(12582912.0 - (double)nmin * (double)inv) : 12582912.0f, 0.f);
+    // rint(norm * inv - K) with K = floor(min norm * inv): the magic constant 1.5 * 2^23 - K is an exact integer, so the
+    // conversion's only error is its own rint; the norm that quantises to 0 is K / inv (<= the minimum)
+    const double K = has_norms ? floor((double)nmin * (double)inv) : 0.0;
+    koff_s = K / (double)inv;
+    const float cap_units = has_norms ? (float)(ceil((double)ncap * (double)inv - K) + 1.0) : 0.f;
+    tilep[blockIdx.x] = make_float4(sc, inv, (float)(12582912.0 - K), cap_units);
   }
   __syncthreads();
   const float sc = s_s;
   if (tid < QB) {
     const double nb = has_norms ? fmax(fabs((double)nmin), fabs((double)nmax)) : 0.0;
     const double fp = ceil((double)(m + 1) * 1.1920928955078125e-07 * (bmax_s[tid] + nb) / (double)sc);
-    qoff[(size_t)blockIdx.x * QB + tid] = off_s[tid] + (has_norms ? (double)nmin : 0.0);
-    qmu[(size_t)blockIdx.x * QB + tid] = (int)ceil(0.5 * m + 2.6) + 1 + (int)fmin(fp, 40000.0);
+    qoff[(size_t)blockIdx.x * QB + tid] = off_s[tid] + (has_norms ? koff_s : 0.0);
+    qmu[(size_t)blockIdx.x * QB + tid] = (int)ceil(0.5 * (m + (has_norms ? 1 : 0)) + 0.1) + 1 + (int)fmin(fp, 40000.0);
   }
   for (int o = tid; o < 16384; o += 512) {
     const int tt2 = o >> 13, c = (o >> 5) & 255, bp = (o >> 1) & 15, e2 = o & 1;
@@ -209,12 +218,30 @@ __global__ void __launch_bounds__(512) lut_quant_kernel(const float* __restrict_
 }
 
 // min / max of the database norms (ordered-uint images; NaN norms are skipped -- such codes can never be returned)
-__global__ void __launch_bounds__(256) norm_range_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ out) {
+__global__ void __launch_bounds__(256) norm_range_kernel(const float* __restrict__ v, int64_t n, unsigned int* __restrict__ out,
+                                                         double* __restrict__ sums) {
   float lo = __int_as_float(0x7f800000), hi = -__int_as_float(0x7f800000);
+  double s1 = 0, s2 = 0, cnt = 0;                       // of the finite norms: for the saturation point of the pre-filter
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const float x = v[i];
     lo = fminf(lo, x);
     hi = fmaxf(hi, x);
+    if (fabsf(x) < __int_as_float(0x7f800000)) {
+      s1 += x;
+      s2 += (double)x * x;
+      cnt += 1;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums, s1);
+    atomicAdd(sums + 1, s2);
+    atomicAdd(sums + 2, cnt);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -491,6 +518,7 @@ struct ScanXParams {
   const uint8_t* codes;  // [n][m] raw codes
   uint32_t* pend;        // [slices][qtiles*QB][pcap] ids that passed the 16-bit filter
   int m, pcap, psoft;
+  unsigned long long* qstats;   // [2] or null (RAYUELA_B200_SCAN_STATS): survivors of the pre-filter, of those accepted
 };
 
 // QPF = true: the same scan with a quantised INTEGER pre-filter in front of the exact arithmetic -- results bit-identical.
@@ -530,6 +558,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   __shared__ int fail_s;     // a speculative threshold turned out too tight for some query: redo the block
   __shared__ int pcnt_s[16]; // QPF: survivors pending exact evaluation, per query
   __shared__ int thr_s[16];  // QPF: integer thresholds T_q (0: nothing passes, 2047: everything does)
+  __shared__ int plim_s[16]; // QPF: pending survivors at which query q asks for service: its buffer would then pass its soft limit
 
   // dynamic shared memory: [sort buffer 64 KB][pad][LUT tile 128 KB, 32 KB-aligned] -- the alignment makes the
   // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
@@ -572,6 +601,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     if (QPF) {
       pcnt_s[tid] = 0;
       thr_s[tid] = tid < QB ? thr_of(tid) : 0;
+      plim_s[tid] = min(p.psoft, p.soft);
     }
   }
   if (SPEC && p.pass == 1 && p.redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // redo launch: nothing to redo
@@ -630,11 +660,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   auto thr_word = [=](int i) -> float {      // word holding queries i (low digit) and i + 1
     return (float)((thr_s[lane_query(i + 1)] + 2048) * 4096 + thr_s[lane_query(i)] + 2048);
   };
-  float q_invs = 0.f, q_c0 = 0.f;
+  float q_invs = 0.f, q_c0 = 0.f, q_ncap = 0.f;
   if (QPF) {
     const float4 tp = __ldg(p.tilep + blockIdx.x);
     q_invs = tp.y;
     q_c0 = tp.z;
+    q_ncap = tp.w;
     thr2[0] = pack2(thr_word(0), thr_word(2));
     thr2[1] = pack2(thr_word(4), thr_word(6));
   }
@@ -839,8 +870,10 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       if (d <= tau_s[q]) {
         const uint64_t key = make_key(d, id);
         if (!p.lb || key > lb_s[q]) cand[(size_t)q * p.cap + atomicAdd(&cnt_s[q], 1)] = key;
+        if (p.qstats) atomicAdd(p.qstats + 1, 1ull);
       }
     }
+    if (p.qstats && tid == 0) atomicAdd(p.qstats, (unsigned long long)total);
     block_sync();
     if (tid < 16) pcnt_s[tid] = 0;
   };
@@ -872,7 +905,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         for (int q = 0; q < QB; q++) warm |= tau_s[q] == __int_as_float(0x7f800000);
         warm_s = warm;
       }
-      if (QPF && tid < QB) thr_s[tid] = thr_of(tid);
+      if (QPF && tid < QB) {
+        thr_s[tid] = thr_of(tid);
+        // the fp32 loop raises the flag when a BUFFER passes its soft limit (lower while a speculative threshold waits for
+        // confirmation); here buffers only grow in drain(), so the same point is reached at soft - (keys already held)
+        plim_s[tid] = max(X::ADDS, min(p.psoft, (SPEC ? softq_s[tid] : p.soft) - cnt_s[tid]));
+      }
     }
     block_sync();
     warm_x = warm_s;
@@ -948,7 +986,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
           const uint64_t neg1 = pack2(-1.0f, -1.0f);
           uint64_t u0 = ffma2(a0, neg1, thr2[0]), u1 = ffma2(a1, neg1, thr2[1]);
           if (NORMS) {
-            const float nqf = __fadd_rn(fmaf(nrm, q_invs, q_c0), -12582912.0f);     // rint((norm - min norm)/s)
+            const float nqf = fminf(__fadd_rn(fmaf(nrm, q_invs, q_c0), -12582912.0f), q_ncap);   // min(rint((norm - norm0)/s), cap)
             const uint64_t n2 = pack2(nqf, nqf), m4097 = pack2(-4097.0f, -4097.0f);
             u0 = ffma2(n2, m4097, u0);
             u1 = ffma2(n2, m4097, u1);
@@ -964,7 +1002,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
                 const int q = lane_query(i);
                 const int pos = atomicAdd(&pcnt_s[q], 1);
                 pend[(size_t)q * p.pcap + pos] = id;
-                if (pos >= p.psoft || (pos + 1 >= p.k && thr_s[q] == 2047)) atomicExch(&flag_s, 1);   // 2047: tau still +inf
+                if (pos >= plim_s[q] || (pos + 1 >= p.k && thr_s[q] == 2047)) atomicExch(&flag_s, 1);   // 2047: tau still +inf
               }
             }
           }
@@ -1317,7 +1355,8 @@ struct rayuela_index {
   DevBuf norms, skew;    // fp32 norms (LSQ); skewed offset fields (skew_fields_kernel)
   DevBuf codes;          // raw codes [n][m]: the pre-filter scan re-evaluates its survivors from them
   DevBuf rot;            // rotated offset fields of the pre-filter scan (rot_fields_kernel)
-  float nmin = 0.f, nmax = 0.f;   // range of the norms (the pre-filter scan quantises them on the fly)
+  float nmin = 0.f, nmax = 0.f, ncap = 0.f;   // range of the norms (the pre-filter scan quantises them on the fly) and
+                                              // the value above which their quantised image saturates
   bool q16_ok = false;   // norms finite: the 16-bit pre-filter scan may be used
   // multi-device parent (rayuela_init / RAYUELA_B200_DEVICES, host arrays): one shard per device slot, no own buffers
   std::vector<rayuela_index*> shards;
@@ -1368,18 +1407,28 @@ static int index_create_single(rayuela_index** out, int kind, const uint8_t* cod
       RYL_TRY(ix->norms.alloc((size_t)n * sizeof(float), s));
       RYL_CUDA(cudaMemcpyAsync(ix->norms.p, dbnorms, (size_t)n * sizeof(float),
                                dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
-      DevBuf rng;
+      DevBuf rng, sums;
       RYL_TRY(rng.alloc(2 * sizeof(unsigned int), s));
+      RYL_TRY(sums.alloc(3 * sizeof(double), s));
       const unsigned int init[2] = {0xFFFFFFFFu, 0u};
       RYL_CUDA(cudaMemcpyAsync(rng.p, init, sizeof init, cudaMemcpyHostToDevice, s));
+      RYL_CUDA(cudaMemsetAsync(sums.p, 0, 3 * sizeof(double), s));
       RYL_LAUNCH(norm_range_kernel, (int)std::min<int64_t>((n + 255) / 256, sm_count() * 8), 256, 0, s,
-                 ix->norms.as<float>(), n, rng.as<unsigned int>());
+                 ix->norms.as<float>(), n, rng.as<unsigned int>(), sums.as<double>());
       unsigned int got[2];
+      double sm[3];
       RYL_CUDA(cudaMemcpyAsync(got, rng.p, sizeof got, cudaMemcpyDeviceToHost, s));
+      RYL_CUDA(cudaMemcpyAsync(sm, sums.p, sizeof sm, cudaMemcpyDeviceToHost, s));
       RYL_CUDA(cudaStreamSynchronize(s));
       ix->nmin = ordered_to_f32(got[0]);
       ix->nmax = ordered_to_f32(got[1]);
       ix->q16_ok = got[0] <= got[1] && std::isfinite(ix->nmin) && std::isfinite(ix->nmax);
+      ix->ncap = ix->nmax;
+      if (ix->q16_ok && sm[2] >= 2) {
+        const double mean = sm[0] / sm[2], var = std::max(0.0, sm[1] / sm[2] - mean * mean);
+        const double cap = mean + 4.0 * std::sqrt(var);
+        if (cap < (double)ix->nmax && cap > (double)ix->nmin) ix->ncap = (float)cap;
+      }
     } else {
       ix->q16_ok = true;
     }
@@ -1553,7 +1602,11 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
     if (k > kmax) RYL_TRY(lb.alloc((size_t)nqc * sizeof(uint64_t), s));
     // QPF: quantised twin of the tiles (exact results, half the shared-memory bytes per lookup; see scanx_kernel)
     const char* q16_env = getenv("RAYUELA_B200_SCAN_PREFILTER");                        // tuning knob: 0 disables
-    const bool q16 = ix->q16_ok && !(q16_env && atoi(q16_env) == 0);
+    // (large k: the survivors' exact re-evaluation outgrows what the narrower loop saves once the quantisation window holds
+    // about as many codes as the result list -- measured crossover between k = 100 and 1000 on LSQ-encoded bases)
+    int q16_maxk = 256;
+    if (const char* e = getenv("RAYUELA_B200_SCAN_PREFILTER_MAXK")) q16_maxk = atoi(e);     // tuning knob
+    const bool q16 = ix->q16_ok && !(q16_env && atoi(q16_env) == 0) && std::min(k, kmax) <= q16_maxk;
     DevBuf lutq, tilep, qoff, qmu;
     if (q16) {
       RYL_TRY(lutq.alloc((size_t)qtiles * 16384 * sizeof(float), s));
@@ -1563,11 +1616,11 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       if (period == 16) {
         RYL_CUDA(cudaFuncSetAttribute(lut_quant_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
         RYL_LAUNCH(lut_quant_kernel<16>, qtiles, 512, 131072, s, lut.as<float>(), lutq.as<float>(), tilep.as<float4>(),
-                   qoff.as<double>(), qmu.as<int>(), m, h, ix->nmin, ix->nmax, norms ? 1 : 0);
+                   qoff.as<double>(), qmu.as<int>(), m, h, ix->nmin, ix->nmax, ix->ncap, norms ? 1 : 0);
       } else {
         RYL_CUDA(cudaFuncSetAttribute(lut_quant_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072));
         RYL_LAUNCH(lut_quant_kernel<8>, qtiles, 512, 131072, s, lut.as<float>(), lutq.as<float>(), tilep.as<float4>(),
-                   qoff.as<double>(), qmu.as<int>(), m, h, ix->nmin, ix->nmax, norms ? 1 : 0);
+                   qoff.as<double>(), qmu.as<int>(), m, h, ix->nmin, ix->nmax, ix->ncap, norms ? 1 : 0);
       }
     }
 
@@ -1654,6 +1707,13 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       p.m = m;
       p.pcap = pcap;
       p.psoft = psoft;
+      DevBuf qstats;
+      p.qstats = nullptr;
+      if (q16 && getenv("RAYUELA_B200_SCAN_STATS")) {
+        RYL_TRY(qstats.alloc(2 * sizeof(unsigned long long), s));
+        RYL_CUDA(cudaMemsetAsync(qstats.p, 0, 2 * sizeof(unsigned long long), s));
+        p.qstats = qstats.as<unsigned long long>();
+      }
 #define RYL_SCANX(PP, NN, SS, QQ)                                                                                    \
   {                                                                                                                  \
     RYL_CUDA(cudaFuncSetAttribute(scanx_kernel<PP, NN, SS, QQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -1673,6 +1733,13 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       }
 #undef RYL_SCANX_Q
 #undef RYL_SCANX
+      if (p.qstats) {
+        unsigned long long h2[2];
+        RYL_CUDA(cudaMemcpyAsync(h2, qstats.p, sizeof h2, cudaMemcpyDeviceToHost, s));
+        RYL_CUDA(cudaStreamSynchronize(s));
+        fprintf(stderr, "[scan stats] nq=%d k=%d S=%d: pre-filter survivors %.1f per query, accepted %.1f per query\n", nqc, kp, S,
+                (double)h2[0] / nqc, (double)h2[1] / nqc);
+      }
       float* dq = d_dev + (size_t)qb * k + koff;
       int32_t* iq = i_dev + (size_t)qb * k + koff;
       RYL_TRY(merge_lists(part.as<uint64_t>(), nullptr, nullptr, S, nqc, kp, dq, iq, id_add, s, k));
