@@ -517,7 +517,7 @@ struct ScanXParams {
   const int* qmu;        // [qtiles*QB] threshold margin in units of s
   const uint8_t* codes;  // [n][m] raw codes
   uint32_t* pend;        // [slices][qtiles*QB][pcap] ids that passed the 16-bit filter
-  int m, pcap, psoft;
+  int m, pcap, psoft, pmin;
   unsigned long long* qstats;   // [2] or null (RAYUELA_B200_SCAN_STATS): survivors of the pre-filter, of those accepted
 };
 
@@ -909,7 +909,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         thr_s[tid] = thr_of(tid);
         // the fp32 loop raises the flag when a BUFFER passes its soft limit (lower while a speculative threshold waits for
         // confirmation); here buffers only grow in drain(), so the same point is reached at soft - (keys already held)
-        plim_s[tid] = max(X::ADDS, min(p.psoft, (SPEC ? softq_s[tid] : p.soft) - cnt_s[tid]));
+        plim_s[tid] = max(p.pmin, min(p.psoft, (SPEC ? softq_s[tid] : p.soft) - cnt_s[tid]));
       }
     }
     block_sync();
@@ -1707,6 +1707,8 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       p.m = m;
       p.pcap = pcap;
       p.psoft = psoft;
+      p.pmin = adds;
+      if (const char* e = getenv("RAYUELA_B200_SCAN_PMIN")) p.pmin = std::max(1, std::min(atoi(e), psoft));   // tuning knob
       DevBuf qstats;
       p.qstats = nullptr;
       if (q16 && getenv("RAYUELA_B200_SCAN_STATS")) {
