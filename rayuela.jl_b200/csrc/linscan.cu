@@ -1603,8 +1603,9 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
     // QPF: quantised twin of the tiles (exact results, half the shared-memory bytes per lookup; see scanx_kernel)
     const char* q16_env = getenv("RAYUELA_B200_SCAN_PREFILTER");                        // tuning knob: 0 disables
     // (large k: the survivors' exact re-evaluation outgrows what the narrower loop saves once the quantisation window holds
-    // about as many codes as the result list -- measured crossover between k = 100 and 1000 on LSQ-encoded bases)
-    int q16_maxk = 256;
+    // about as many codes as the result list -- measured crossover at k = 100..128 on an LSQ-encoded base, beyond 256 on
+    // isotropic random codes)
+    int q16_maxk = 128;
     if (const char* e = getenv("RAYUELA_B200_SCAN_PREFILTER_MAXK")) q16_maxk = atoi(e);     // tuning knob
     const bool q16 = ix->q16_ok && !(q16_env && atoi(q16_env) == 0) && std::min(k, kmax) <= q16_maxk;
     DevBuf lutq, tilep, qoff, qmu;
