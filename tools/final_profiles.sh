@@ -10,9 +10,11 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:icm_
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:icm_warp_kernel -s 3 -c 1 -o gpurun_out/r2_icm16 -f python tools/icm_bench.py 125000 16 32 1 > gpurun_out/r2_ncu_icm16.log 2>&1
 fi
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scanx_kernel -s 2 -c 1 -o gpurun_out/r2_scanx8 -f python tools/scan_bench.py 1000000 10000 8 1 1 > /dev/null 2>&1
+RAYUELA_B200_SCAN_PREFILTER=0 timeout 300 ncu --set full --clock-control none --import-source on -k regex:scanx_kernel -s 2 -c 1 -o gpurun_out/r2_scanx8_fp32 -f python tools/scan_bench.py 1000000 10000 8 1 1 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:unary_tc_kernel -s 1 -c 1 -o gpurun_out/r2_unary_tc -f python tools/unary_bench.py 1000000 8 > /dev/null 2>&1
 timeout 300 ncu --set full --clock-control none -k regex:unary_kernel -s 1 -c 1 -o gpurun_out/r2_unary_exact -f python tools/unary_bench.py 1000000 8 > /dev/null 2>&1
 timeout 300 python tools/configs01.py > gpurun_out/r2_configs01.json 2> gpurun_out/r2_configs01.err
 timeout 400 python bench_rows.py > gpurun_out/r2_rows.json 2> gpurun_out/r2_rows.err
 timeout 300 python tools/scan_bench.py 1000000 10000 8,16 1,10,100,1000,4000 5 > gpurun_out/r2_scan_bench.txt 2>&1
+{ echo '# RAYUELA_B200_SCAN_PREFILTER=0 (fp32 loop for every k)'; RAYUELA_B200_SCAN_PREFILTER=0 timeout 300 python tools/scan_bench.py 1000000 10000 8,16 1,10,100 5; } >> gpurun_out/r2_scan_bench.txt 2>&1
 cat gpurun_out/r2_pytest_gpu.txt; ls -la gpurun_out | grep r2_
