@@ -516,8 +516,7 @@ struct ScanXParams {
   const double* qoff;    // [qtiles*QB] sum_k min_c LUT + min norm: the distance that quantises to 0
   const int* qmu;        // [qtiles*QB] threshold margin in units of s
   const uint8_t* codes;  // [n][m] raw codes
-  uint32_t* pend;        // [slices][qtiles*QB][pcap] ids that passed the 16-bit filter
-  int m, pcap, psoft, pmin;
+  int m;
   unsigned long long* qstats;   // [2] or null (RAYUELA_B200_SCAN_STATS): survivors of the pre-filter, of those accepted
 };
 
@@ -532,10 +531,11 @@ struct ScanXParams {
 // where E is the exact fp32 distance of the reference chain and off_q = sum_k min_c LUT + min norm.  A code is a
 // SURVIVOR of query q when A <= T_q = floor((tau_q - off_q)/s) + mu_q (mu_q = that margin, lut_quant_kernel), which every
 // code with E <= tau_q is.  The test is one exact subtraction per pair, (T + 2048) - A per base-4096 digit: a digit keeps
-// its 2048 bit iff A <= T and never borrows from its neighbour.  Survivors are only noted (id appended to the query's
-// pending list); service() re-evaluates them with the exact fp32 chain from the fp32 tile in L2 (ascending k from 0,
-// + norm last -- the arithmetic of the fp32 hot loop) and hands those with E <= tau_q to the unchanged candidate
-// buffers / compaction / speculation.  The window is ~4e-3 of the tile's distance range.
+// its 2048 bit iff A <= T and never borrows from its neighbour.  Survivors are only noted ((query, id) pushed to the
+// warp's own 64-entry ring); every 32 of them the warp re-evaluates them itself, one lane per survivor, with the exact
+// fp32 chain from the fp32 tile in L2 (ascending k from 0, + norm last -- the arithmetic of the fp32 hot loop) and hands
+// those with E <= tau_q to the unchanged candidate buffers / compaction / speculation.  The window is ~4e-3 of the
+// tile's distance range.
 template <int P, bool NORMS, bool SPEC, bool QPF = false>
 __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p) {
   using X = ScanX<P>;
@@ -556,9 +556,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   __shared__ int seen_s;     // codes of this block's slice scanned so far (all warps)
   __shared__ int softq_s[16];// per-query soft limit (lower while a speculative threshold waits for confirmation)
   __shared__ int fail_s;     // a speculative threshold turned out too tight for some query: redo the block
-  __shared__ int pcnt_s[16]; // QPF: survivors pending exact evaluation, per query
   __shared__ int thr_s[16];  // QPF: integer thresholds T_q (0: nothing passes, 2047: everything does)
-  __shared__ int plim_s[16]; // QPF: pending survivors at which query q asks for service: its buffer would then pass its soft limit
 
   // dynamic shared memory: [sort buffer 64 KB][pad][LUT tile 128 KB, 32 KB-aligned] -- the alignment makes the
   // tile base and the 15-bit offset fields disjoint bit ranges, so a step's address is ONE instruction
@@ -573,7 +571,6 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   const int q0 = blockIdx.x * QB;
   const int slice = blockIdx.y;
   uint64_t* cand = p.cand + ((size_t)slice * gridDim.x * QB + (size_t)blockIdx.x * QB) * p.cap;
-  uint32_t* pend = QPF ? p.pend + ((size_t)slice * gridDim.x * QB + (size_t)blockIdx.x * QB) * p.pcap : nullptr;
   const float inf = __int_as_float(0x7f800000);
   // QPF: T_q from the current exact threshold (double arithmetic: once per query per service())
   auto thr_of = [=](int q) -> int {
@@ -599,9 +596,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     taukey_s[tid] = make_key(p.tau0, 0xFFFFFFFFu);
     lb_s[tid] = (p.lb && tid < QB) ? p.lb[min(q0 + tid, p.nq - 1)] : 0ull;
     if (QPF) {
-      pcnt_s[tid] = 0;
       thr_s[tid] = tid < QB ? thr_of(tid) : 0;
-      plim_s[tid] = min(p.psoft, p.soft);
     }
   }
   if (SPEC && p.pass == 1 && p.redo[blockIdx.y * gridDim.x + blockIdx.x] == 0) return;   // redo launch: nothing to redo
@@ -824,58 +819,42 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
   // instructions; it hands the refreshed thresholds back through tau_x / warm_x (address-taken locals) so that the
   // hot loop's own copies stay in registers; everything else is captured BY VALUE (also by the helpers it calls) so
   // that taking the closure's address does not push the kernel's locals into local memory.
-  // QPF: exact re-evaluation of the pending survivors, all threads of the block over the flattened (query, slot) pairs;
-  // callers hold every warp at a barrier.  ((0 + t_0) + t_1) + ... in ascending k, + dbnorms[i] last
-  // (pairwise_byte.cpp:70-74): the fp32 hot loop's arithmetic.
-  auto drain = [=]() {
+  // QPF: exact distance of code id for block query q: ((0 + t_0) + t_1) + ... in ascending k from the fp32 tile in L2,
+  // + dbnorms[i] last (pairwise_byte.cpp:70-74) -- the fp32 hot loop's arithmetic.  All code bytes first, then all table
+  // entries: two load levels per survivor.
+  auto exact_dist = [=](int q, uint32_t id) -> float {
     const float* lt = p.lut + (size_t)blockIdx.x * (kLutTileBytes / 4);
-    int total = 0;
+    const float* lq = (P == 8) ? lt + (q >> 2) * 8192 + (((q & 3) >> 1) << 4) + (q & 1) : lt + (q >> 1) * 8192 + (q & 1);
+    const uint8_t* cb = p.codes + (size_t)id * p.m;
+    float nrm = 0.f;
+    if (NORMS) nrm = __ldg(p.norms + id);
+    uint32_t cw[P / 4];
+    if (P == 8 && p.m == 8) {
+      const uint2 c8 = __ldg(reinterpret_cast<const uint2*>(cb));
+      cw[0] = c8.x;
+      cw[1] = c8.y;
+    } else if (P == 16 && p.m == 16) {
+      const uint4 c16 = __ldg(reinterpret_cast<const uint4*>(cb));
+      cw[0] = c16.x; cw[1] = c16.y; cw[2] = c16.z; cw[3] = c16.w;
+    } else {
 #pragma unroll
-    for (int q = 0; q < QB; q++) total += pcnt_s[q];
-    for (int f = tid; f < total; f += NT) {
-      int q = 0, t = f;
-      while (t >= pcnt_s[q]) t -= pcnt_s[q++];
-      const uint32_t id = pend[(size_t)q * p.pcap + t];
-      const float* lq = (P == 8) ? lt + (q >> 2) * 8192 + (((q & 3) >> 1) << 4) + (q & 1) : lt + (q >> 1) * 8192 + (q & 1);
-      const uint8_t* cb = p.codes + (size_t)id * p.m;
-      float nrm = 0.f;
-      if (NORMS) nrm = __ldg(p.norms + id);
-      // all code bytes first, then all table entries: two load levels per survivor instead of 2 m dependent ones
-      uint32_t cw[P / 4];
-      if (P == 8 && p.m == 8) {
-        const uint2 c8 = __ldg(reinterpret_cast<const uint2*>(cb));
-        cw[0] = c8.x;
-        cw[1] = c8.y;
-      } else if (P == 16 && p.m == 16) {
-        const uint4 c16 = __ldg(reinterpret_cast<const uint4*>(cb));
-        cw[0] = c16.x; cw[1] = c16.y; cw[2] = c16.z; cw[3] = c16.w;
-      } else {
+      for (int w4 = 0; w4 < P / 4; w4++) {
+        uint32_t x = 0;
 #pragma unroll
-        for (int w4 = 0; w4 < P / 4; w4++) {
-          uint32_t x = 0;
-#pragma unroll
-          for (int b = 0; b < 4; b++)
-            if (w4 * 4 + b < p.m) x |= (uint32_t)__ldg(cb + w4 * 4 + b) << (8 * b);
-          cw[w4] = x;
-        }
-      }
-      float tv[P];
-#pragma unroll
-      for (int k = 0; k < P; k++) tv[k] = k < p.m ? __ldg(lq + (int)((cw[k >> 2] >> (8 * (k & 3))) & 255u) * 32 + (k << 1)) : 0.f;
-      float d = 0.f;
-#pragma unroll
-      for (int k = 0; k < P; k++)
-        if (k < p.m) d = __fadd_rn(d, tv[k]);
-      if (NORMS) d = __fadd_rn(d, nrm);
-      if (d <= tau_s[q]) {
-        const uint64_t key = make_key(d, id);
-        if (!p.lb || key > lb_s[q]) cand[(size_t)q * p.cap + atomicAdd(&cnt_s[q], 1)] = key;
-        if (p.qstats) atomicAdd(p.qstats + 1, 1ull);
+        for (int b = 0; b < 4; b++)
+          if (w4 * 4 + b < p.m) x |= (uint32_t)__ldg(cb + w4 * 4 + b) << (8 * b);
+        cw[w4] = x;
       }
     }
-    if (p.qstats && tid == 0) atomicAdd(p.qstats, (unsigned long long)total);
-    block_sync();
-    if (tid < 16) pcnt_s[tid] = 0;
+    float tv[P];
+#pragma unroll
+    for (int k = 0; k < P; k++) tv[k] = k < p.m ? __ldg(lq + (int)((cw[k >> 2] >> (8 * (k & 3))) & 255u) * 32 + (k << 1)) : 0.f;
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < P; k++)
+      if (k < p.m) d = __fadd_rn(d, tv[k]);
+    if (NORMS) d = __fadd_rn(d, nrm);
+    return d;
   };
 
   float tau_x[8];
@@ -890,10 +869,6 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
       block_sync();
     }
     if (fl) {
-      if (QPF) {
-        drain();
-        block_sync();
-      }
       if (w < QB && cnt_s[w] <= kWarpKeys && needs_compaction(w)) warp_sort_keep(w);   // warp w <-> query w
       block_sync();
       for (int q = 0; q < QB; q++)
@@ -905,12 +880,7 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         for (int q = 0; q < QB; q++) warm |= tau_s[q] == __int_as_float(0x7f800000);
         warm_s = warm;
       }
-      if (QPF && tid < QB) {
-        thr_s[tid] = thr_of(tid);
-        // the fp32 loop raises the flag when a BUFFER passes its soft limit (lower while a speculative threshold waits for
-        // confirmation); here buffers only grow in drain(), so the same point is reached at soft - (keys already held)
-        plim_s[tid] = max(p.pmin, min(p.psoft, (SPEC ? softq_s[tid] : p.soft) - cnt_s[tid]));
-      }
+      if (QPF && tid < QB) thr_s[tid] = thr_of(tid);
     }
     block_sync();
     warm_x = warm_s;
@@ -943,6 +913,46 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
     const uint4* fq0 = nullptr;
     const float* np0 = nullptr;
     uint32_t id0 = 0;
+    // Survivors go to a 64-entry ring of (query, id) pairs PER WARP (in the half of the tile area the 2-byte tables leave
+    // free); whenever it holds 32 the warp itself re-evaluates them exactly, one lane per survivor, and appends those with
+    // E <= tau to the candidate buffers exactly as the fp32 loop does -- no block barrier, the other 15 warps keep scanning
+    // under the two dependent L2 round trips.  Ring state is warp-uniform (registers).
+    uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw + (lut_addr - smem_u32(smem_raw)) + 65536) + w * 64;
+    uint32_t rhead = 0, rfill = 0;
+    auto flush_batch = [&]() {
+      __syncwarp();
+      const uint32_t cnt = min(rfill, 32u);
+      bool ok = false;
+      if (lane < cnt) {
+        const uint64_t e = ring[(rhead + lane) & 63u];
+        const int q = (int)(e >> 32);
+        const uint32_t id = (uint32_t)e;
+        const float d = exact_dist(q, id);
+        const float tq = tau_s[q];
+        if (d <= tq) {
+          const uint64_t key = make_key(d, id);
+          if (!p.lb || key > lb_s[q]) {
+            ok = true;
+            const int pos = atomicAdd(&cnt_s[q], 1);
+            cand[(size_t)q * p.cap + pos] = key;
+            if (pos >= (SPEC ? softq_s[q] : p.soft) || (tq == inf && pos + 1 >= p.k)) atomicExch(&flag_s, 1);
+          }
+        }
+      }
+      if (p.qstats) {
+        const uint32_t acc_n = __popc(__ballot_sync(0xffffffffu, ok));
+        if (lane == 0) {
+          atomicAdd(p.qstats, (unsigned long long)cnt);
+          atomicAdd(p.qstats + 1, (unsigned long long)acc_n);
+        }
+      }
+      rhead = (rhead + cnt) & 63u;
+      rfill -= cnt;
+      __syncwarp();
+    };
+    auto flush_all = [&]() {
+      while (rfill) flush_batch();
+    };
     auto period_q = [&](uint4 (&Wc)[X::HALVES], float& nc, const int t) {
       const int raised = lds_volatile(flag_addr);
       uint32_t ad[P];
@@ -980,35 +990,46 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         a1 = fadd2(a1, lds64<32768>(ad[S]));
       }
       if (QPF_VARIANT & 1) prefetch();
-        if (id < n32) {
-          // (T + 2048) - A per digit, exact in fp32 (integers < 2^24); + 2^24 aligns the integer with the mantissa (the
-          // one rounding, to even, can only turn a digit of 2047 into 2048: a spurious survivor, never a lost one)
-          const uint64_t neg1 = pack2(-1.0f, -1.0f);
-          uint64_t u0 = ffma2(a0, neg1, thr2[0]), u1 = ffma2(a1, neg1, thr2[1]);
-          if (NORMS) {
-            const float nqf = fminf(__fadd_rn(fmaf(nrm, q_invs, q_c0), -12582912.0f), q_ncap);   // min(rint((norm - norm0)/s), cap)
-            const uint64_t n2 = pack2(nqf, nqf), m4097 = pack2(-4097.0f, -4097.0f);
-            u0 = ffma2(n2, m4097, u0);
-            u1 = ffma2(n2, m4097, u1);
-          }
-          const uint64_t two24 = pack2(16777216.0f, 16777216.0f);
-          u0 = fadd2(u0, two24);
-          u1 = fadd2(u1, two24);
-          const uint32_t uw[4] = {(uint32_t)u0, (uint32_t)(u0 >> 32), (uint32_t)u1, (uint32_t)(u1 >> 32)};
-          if ((uw[0] | uw[1] | uw[2] | uw[3]) & 0x00400400u) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-              if ((uw[i >> 1] >> ((i & 1) ? 22 : 10)) & 1u) {
-                const int q = lane_query(i);
-                const int pos = atomicAdd(&pcnt_s[q], 1);
-                pend[(size_t)q * p.pcap + pos] = id;
-                if (pos >= plim_s[q] || (pos + 1 >= p.k && thr_s[q] == 2047)) atomicExch(&flag_s, 1);   // 2047: tau still +inf
-              }
-            }
-          }
+      {
+        // (T + 2048) - A per digit, exact in fp32 (integers < 2^24); + 2^24 aligns the integer with the mantissa (the
+        // one rounding, to even, can only turn a digit of 2047 into 2048: a spurious survivor, never a lost one)
+        const uint64_t neg1 = pack2(-1.0f, -1.0f);
+        uint64_t u0 = ffma2(a0, neg1, thr2[0]), u1 = ffma2(a1, neg1, thr2[1]);
+        if (NORMS) {
+          const float nqf = fminf(__fadd_rn(fmaf(nrm, q_invs, q_c0), -12582912.0f), q_ncap);   // min(rint((norm - norm0)/s), cap)
+          const uint64_t n2 = pack2(nqf, nqf), m4097 = pack2(-4097.0f, -4097.0f);
+          u0 = ffma2(n2, m4097, u0);
+          u1 = ffma2(n2, m4097, u1);
         }
+        const uint64_t two24 = pack2(16777216.0f, 16777216.0f);
+        u0 = fadd2(u0, two24);
+        u1 = fadd2(u1, two24);
+        const uint32_t uw[4] = {(uint32_t)u0, (uint32_t)(u0 >> 32), (uint32_t)u1, (uint32_t)(u1 >> 32)};
+        const bool has = id < n32 && ((uw[0] | uw[1] | uw[2] | uw[3]) & 0x00400400u) != 0u;
+        if (__any_sync(0xffffffffu, has)) {                       // warp-uniform from here on
+          uint32_t bits = 0;                                      // bit i: query i of this lane survived
+          if (has) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) bits |= ((uw[i >> 1] >> ((i & 1) ? 22 : 10)) & 1u) << i;
+          }
+          uint32_t present = __reduce_or_sync(0xffffffffu, bits);
+          while (present) {                                        // one query slot at a time: <= 32 entries per round
+            const int b = __ffs(present) - 1;
+            present &= present - 1;
+            const bool mine = (bits >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+            const uint32_t nb = __popc(bal);
+            if (rfill + nb > 64u) flush_batch();
+            if (mine)
+              ring[(rhead + rfill + __popc(bal & ((1u << lane) - 1u))) & 63u] = ((uint64_t)(uint32_t)lane_query(b) << 32) | id;
+            rfill += nb;
+          }
+          if (rfill >= 32u) flush_batch();
+        }
+      }
       // while some tau is still +inf every code of every warp is a candidate: do not wait a period to react
       if (raised || (warm && lds_volatile(flag_addr))) {
+        flush_all();                                              // every survivor noted so far is in the buffers
         service(wdone + (t + 1) * X::NS);
         // The refreshed thresholds are rebuilt HERE from shared memory (conversions = real consumers on this cold path),
         // not handed back through service()'s address-taken locals: those come back as local-memory loads whose
@@ -1037,13 +1058,12 @@ __global__ void __launch_bounds__(kScanWarps * 32, 1) scanx_kernel(ScanXParams p
         period_q(WB, nB, t + 1);
       }
     }
+    flush_all();
     __syncwarp();
     if (lane == 0) atomicAdd(&nfin_s, 1);
     __syncwarp();
     while (!service(wdone)) {
     }
-    drain();                                      // survivors noted since the last service()
-    block_sync();
   } else {
   int wdone = 0;                                         // codes of finished chunks of this warp
   for (int64_t chunk = c0 + w; chunk < c1; chunk += kScanWarps, wdone += kChunkCodes) {
@@ -1603,9 +1623,9 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
     // QPF: quantised twin of the tiles (exact results, half the shared-memory bytes per lookup; see scanx_kernel)
     const char* q16_env = getenv("RAYUELA_B200_SCAN_PREFILTER");                        // tuning knob: 0 disables
     // (large k: the survivors' exact re-evaluation outgrows what the narrower loop saves once the quantisation window holds
-    // about as many codes as the result list -- measured crossover at k = 100..128 on an LSQ-encoded base, beyond 256 on
-    // isotropic random codes)
-    int q16_maxk = 128;
+    // about as many codes as the result list -- measured crossover between k = 256 and 1000 on an LSQ-encoded base, beyond
+    // 1000 on isotropic random codes)
+    int q16_maxk = 256;
     if (const char* e = getenv("RAYUELA_B200_SCAN_PREFILTER_MAXK")) q16_maxk = atoi(e);     // tuning knob
     const bool q16 = ix->q16_ok && !(q16_env && atoi(q16_env) == 0) && std::min(k, kmax) <= q16_maxk;
     DevBuf lutq, tilep, qoff, qmu;
@@ -1632,10 +1652,12 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       // `soft` keys -- up to 4k: fewer, relatively cheaper selections; measured optimum, gpurun r2_soft.log -- and
       // the capacity leaves room for the periods of appends that can land before every warp has reacted to the flag.
       // (small k: 384, so that a buffer past the limit still fits the 512-key slice one warp can compact alone)
-      int soft = std::max(384, std::min(4 * kp, kScanSortKeys - 3 * adds));
+      // (pre-filter loop: + the 16 x 64 survivors that may sit in the warps' rings when the flag goes up)
+      const int slack = 3 * adds + (q16 ? kScanWarps * 64 : 0);
+      int soft = std::max(384, std::min(4 * kp, kScanSortKeys - slack));
       if (const char* e = getenv("RAYUELA_B200_SCAN_SOFT"))   // tuning knob
-        soft = std::max(kp, std::min(atoi(e), kScanSortKeys - 3 * adds));
-      const int cap = soft + 3 * adds;
+        soft = std::max(kp, std::min(atoi(e), kScanSortKeys - slack));
+      const int cap = soft + slack;
       // sort buffer + up to 32 KB of padding so the LUT tile starts on a 32 KB boundary + the tile
       const size_t smem = (size_t)kScanSortKeys * sizeof(uint64_t) + 32768 + (size_t)kLutTileBytes;
       // DB slices.  A launch of qtiles x S blocks takes ceil(qtiles*S / SMs) waves of (1/S + c) base passes each,
@@ -1664,10 +1686,7 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       slice_len = (slice_len + unit - 1) / unit * unit;
       S = (int)((ix->n + slice_len - 1) / slice_len);
 
-      DevBuf cand, part, pend;
-      const int psoft = std::max(64, soft - (kp + (soft - kp) / 6));   // pending survivors + a buffer at the piggy limit fit cap
-      const int pcap = psoft + 3 * adds;
-      if (q16) RYL_TRY(pend.alloc((size_t)S * qtiles * QT * pcap * sizeof(uint32_t), s));
+      DevBuf cand, part;
       RYL_TRY(cand.alloc((size_t)S * qtiles * QT * cap * sizeof(uint64_t), s));
       RYL_TRY(part.alloc((size_t)S * nqc * kp * sizeof(uint64_t), s));
       ScanXParams p;
@@ -1704,12 +1723,7 @@ static int index_search_dev(rayuela_index* ix, const float* q_dev, const float* 
       p.qoff = qoff.as<double>();
       p.qmu = qmu.as<int>();
       p.codes = ix->codes.as<uint8_t>();
-      p.pend = pend.as<uint32_t>();
       p.m = m;
-      p.pcap = pcap;
-      p.psoft = psoft;
-      p.pmin = adds;
-      if (const char* e = getenv("RAYUELA_B200_SCAN_PMIN")) p.pmin = std::max(1, std::min(atoi(e), psoft));   // tuning knob
       DevBuf qstats;
       p.qstats = nullptr;
       if (q16 && getenv("RAYUELA_B200_SCAN_STATS")) {
