@@ -395,8 +395,13 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int dpad = (p.d + 3) & ~3;                         // per-warp slot, 16-byte aligned (warp_cost loads float4)
-  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * dpad;
-  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)nwarps * dpad);
+  // UQS (m <= 8): the warp keeps its vector's unaries in shared memory, already in the pre-filter's integer units
+  // (16 bit, relative to the codebook's smallest one): [M][32 lanes] x 16 B in front of the cost scratch
+  constexpr bool UQS = PF && M <= 8;
+  unsigned char* smem_f = smem_raw + (UQS ? (size_t)nwarps * M * 512 : 0);
+  uint4* uqw = reinterpret_cast<uint4*>(smem_raw + (size_t)warp * (UQS ? M * 512 : 0)) + lane;
+  float* sq = reinterpret_cast<float*>(smem_f) + (size_t)warp * dpad;
+  int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_f) + (size_t)nwarps * dpad);
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
   __syncthreads();
 
@@ -418,6 +423,34 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
     uint32_t vsteps = 0, vexact = 0;                            // this vector's step counters (32 bit in the hot loop)
     float slack = 0.f;                                          // 2.002 * 2^-20 * umax (PF)
     if (PF) slack = __uint_as_float(__ldg(p.umax + l)) * (2.002f * 9.5367431640625e-07f);
+    if constexpr (UQS) {
+      // The pre-filter only ever needs rint(u(c) / scale_j), and only up to a constant per (vector, j): the warp reads
+      // its vector's 8 KB of fp32 unaries ONCE (streaming), rounds them exactly as the step used to (one fma with
+      // 1.5 * 2^23), subtracts the codebook's minimum and keeps the result as 16-bit fields in the row layout of the
+      // quantised tables -- a step then adds the unary like one more row (LDS.128 instead of two LDG.128 from L2:
+      // -22 % of the step's L2 bytes, no per-step conversion).  A candidate more than 65534 units above the minimum
+      // saturates: its S is then a LOWER bound, so it can only add window members (exact path), and a winner that
+      // is itself saturated is sent to the exact path (checked below).  Garbage for a j whose window test fails
+      // (umax / scale_j >= 2^21, NaN) is never used: that test is per step and unchanged.
+      __syncwarp();
+#pragma unroll 1
+      for (int j = 0; j < M; j++) {
+        const float inv = __ldg(&p.pfc[j].x);
+        const float4 u0 = __ldcs(Ul + j * 64 + lane), u1 = __ldcs(Ul + j * 64 + 32 + lane);
+        const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+        int q[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) q[i] = __float_as_int(fmaf(uu[i], inv, 12582912.0f)) - 0x4B400000;
+        const int lm = min(min(min(q[0], q[1]), min(q[2], q[3])), min(min(q[4], q[5]), min(q[6], q[7])));
+        const int base = __reduce_min_sync(0xffffffffu, lm);
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          w[i] = min((uint32_t)(q[i] - base), 65535u) | (min((uint32_t)(q[4 + i] - base), 65535u) << 16);
+        uqw[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+    }
 
     for (int it = 0; it < p.ilsiter; it++) {
       Code nb = cur;                                            // copyto!(B, oldB), src/LSQ.jl:207
@@ -443,12 +476,14 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
           if (!((dirty >> j) & 1u)) continue;
           vsteps++;
           float4 a0, a1;
-          if (M > 8) {
-            a0 = ldg_f4_hint(Ul + j * 64 + lane, pol_keep);
-            a1 = ldg_f4_hint(Ul + j * 64 + 32 + lane, pol_keep);
-          } else {
-            a0 = __ldg(Ul + j * 64 + lane);
-            a1 = __ldg(Ul + j * 64 + 32 + lane);
+          if constexpr (!UQS) {
+            if (M > 8) {
+              a0 = ldg_f4_hint(Ul + j * 64 + lane, pol_keep);
+              a1 = ldg_f4_hint(Ul + j * 64 + 32 + lane, pol_keep);
+            } else {
+              a0 = __ldg(Ul + j * 64 + lane);
+              a1 = __ldg(Ul + j * 64 + 32 + lane);
+            }
           }
           int bc = -1;
           if (PF) {
@@ -457,6 +492,11 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
             if (wf < pc.y + 4.0f) {                               // umax/scale_j < 2^21: integer sums fit (else exact)
               // ---- quantised pass: lane owns c = 4*lane + w (lo halves) and 128 + 4*lane + w (hi halves) ---------
               uint32_t sl[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};   // sl = sum lo + (sum hi << 16) (mod 2^32)
+              if constexpr (UQS) {                                  // the unary is row 0 of the sum
+                const uint4 xu = uqw[j * 32];
+                sl[0] = xu.x; sl[1] = xu.y; sl[2] = xu.z; sl[3] = xu.w;
+                sh[0] = xu.x >> 16; sh[1] = xu.y >> 16; sh[2] = xu.z >> 16; sh[3] = xu.w >> 16;
+              }
               const char* tqj = reinterpret_cast<const char*>(p.Tq) + (size_t)j * (M * kH * 512) + lane * 16;
               asm volatile("" : "+l"(tqj));   // keep the base in a register pair: row address = one IMAD.WIDE
               if constexpr (M <= 8 && JSPEC) {                     // one copy of the row loop per j (jump table)
@@ -484,13 +524,21 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
               }
               // S(c) = rint(u(c)/scale_j) + sum_k (q_k(c) - 32768): the unary is rounded by the 1.5*2^23 trick inside
               // one fma, whose integer image carries the constant 0x4B400000
-              constexpr int K = -0x4B400000 - (M - 1) * 32768;
-              const float uu[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
               int S[8];
+              if constexpr (UQS) {                                  // constants per step do not move the argmin
 #pragma unroll
-              for (int w4 = 0; w4 < 4; w4++) {
-                S[w4] = (int)(sl[w4] - (sh[w4] << 16)) + (__float_as_int(fmaf(uu[w4], pc.x, 12582912.0f)) + K);
-                S[4 + w4] = (int)sh[w4] + (__float_as_int(fmaf(uu[4 + w4], pc.x, 12582912.0f)) + K);
+                for (int w4 = 0; w4 < 4; w4++) {
+                  S[w4] = (int)(sl[w4] - (sh[w4] << 16));
+                  S[4 + w4] = (int)sh[w4];
+                }
+              } else {
+                constexpr int K = -0x4B400000 - (M - 1) * 32768;
+                const float uu[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int w4 = 0; w4 < 4; w4++) {
+                  S[w4] = (int)(sl[w4] - (sh[w4] << 16)) + (__float_as_int(fmaf(uu[w4], pc.x, 12582912.0f)) + K);
+                  S[4 + w4] = (int)sh[w4] + (__float_as_int(fmaf(uu[4 + w4], pc.x, 12582912.0f)) + K);
+                }
               }
               const int lm = min(min(min(S[0], S[1]), min(S[2], S[3])), min(min(S[4], S[5]), min(S[6], S[7])));
               const int key = __reduce_min_sync(0xffffffffu, (lm << 5) | lane);      // |S| < 2^22
@@ -503,11 +551,19 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
                 const int wl = key & 31;
                 const int i = __shfl_sync(0xffffffffu, __ffs(mask) - 1, wl);
                 bc = (i < 4 ? 0 : 128) + wl * 4 + (i & 3);
+                if constexpr (UQS) {                                // a saturated winner's S is only a lower bound
+                  const uint16_t vw = reinterpret_cast<const uint16_t*>(uqw - lane + j * 32 + wl)[2 * (i & 3) + (i >> 2)];
+                  if (vw == 65535u) bc = -1;
+                }
               }
             }
           }
           if (bc < 0) {
             if (PF) vexact++;
+            if constexpr (UQS) {
+              a0 = __ldg(Ul + j * 64 + lane);
+              a1 = __ldg(Ul + j * 64 + 32 + lane);
+            }
 #pragma unroll
             for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j, encode_icm.cpp:28-45
               const int k = kk + (kk >= j);
@@ -1013,9 +1069,10 @@ static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
 template <int M>
 static int launch_icm(const IcmParams& p, cudaStream_t s) {
   const int warps = 8;
-  const size_t smem = (size_t)warps * ((p.d + 3) & ~3) * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
-  RYL_ARG(smem <= 200 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
+  size_t smem = (size_t)warps * ((p.d + 3) & ~3) * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
+  RYL_ARG(smem <= 160 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
   if (!p.Tq) return launch_icm_v<M, false, false>(p, smem, s);
+  if (M <= 8) smem += (size_t)warps * M * 512;             // the warps' quantised unaries (UQS)
   if constexpr (M <= 8) {
     if (!env_off("RAYUELA_B200_ICM_JSPEC")) return launch_icm_v<M, true, true>(p, smem, s);
   }
