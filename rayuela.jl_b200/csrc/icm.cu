@@ -183,7 +183,14 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ C
 // Tq[j][k][b][pos] = rint(T[j][k][b][c] / scale_j) + 32768 (uint16, 1..65535), the row permuted so that the 16 bytes
 // lane L loads are the 32-bit words w = 0..3 = { lo: c = 4L + w, hi: c = 128 + 4L + w } -- the same candidates the
 // lane owns in the exact path.  |scale_j*(q-32768) - T| <= 0.51*scale_j (rint + one fp32 division rounding).
-static constexpr float kQ = 32767.0f;
+#ifndef RYL_K3_QBITS
+#define RYL_K3_QBITS 14
+#endif
+// m <= 8 (RYL_K3_QBITS = 14): 14-bit fields q + 8192 in 1..16383 -- up to four rows add inside their 16-bit fields
+// without a carry, so the rows of a step are summed TWO candidates per integer add (see pf_rows14); the unit is 4x
+// coarser (more near-ties go to the exact path: ~5 % instead of ~1.5 % of the steps) but a step has 32 instructions
+// less.  m > 8: 16-bit fields q + 32768, hi / lo halves accumulated separately.
+__host__ __device__ inline float pf_q(int m) { return (m <= 8 && RYL_K3_QBITS == 14) ? 8191.0f : 32767.0f; }
 __global__ void __launch_bounds__(256) tmax_kernel(const float* __restrict__ T, int m, unsigned int* __restrict__ tmax) {
   const int j = blockIdx.y / m, k = blockIdx.y % m;
   if (j == k) return;
@@ -205,14 +212,16 @@ __global__ void __launch_bounds__(256) quant_tables_kernel(const float* __restri
   const int j = blockIdx.z / m, k = blockIdx.z % m;
   if (j == k) return;
   const float tm = __uint_as_float(tmax[j]);
+  const float kQ = pf_q(m);
+  const int off = (int)kQ + 1;
   const float scale = (tm > 0.f && tm < __int_as_float(0x7f800000)) ? __fdiv_rn(tm, kQ) : 1.0f;
   // one thread per 32-bit output word: row b = blockIdx.x*? ...  grid.x * 256 threads cover 256 rows * 128 words
   for (int i = blockIdx.x * 256 + threadIdx.x; i < kH * (kH / 2); i += gridDim.x * 256) {
     const int b = i >> 7, word = i & 127, L = word >> 2, w = word & 3;
     const float* row = T + (((size_t)j * m + k) * kH + b) * kH;
     const float qlo = rintf(__fdiv_rn(row[4 * L + w], scale)), qhi = rintf(__fdiv_rn(row[128 + 4 * L + w], scale));
-    const uint32_t lo = (uint32_t)((int)fminf(fmaxf(qlo, -kQ), kQ) + 32768);
-    const uint32_t hi = (uint32_t)((int)fminf(fmaxf(qhi, -kQ), kQ) + 32768);
+    const uint32_t lo = (uint32_t)((int)fminf(fmaxf(qlo, -kQ), kQ) + off);
+    const uint32_t hi = (uint32_t)((int)fminf(fmaxf(qhi, -kQ), kQ) + off);
     Tq[(((size_t)j * m + k) * kH + b) * (kH / 2) + word] = lo | (hi << 16);
   }
 }
@@ -225,6 +234,7 @@ __global__ void pf_consts_kernel(const unsigned int* __restrict__ tmax, int m, f
   if (j >= m) return;
   const float tm = __uint_as_float(tmax[j]);
   const bool ok = m > 1 && tm > 0.f && tm < __int_as_float(0x7f800000);
+  const float kQ = pf_q(m);
   const float w0 = 2.002f * ((float)(m - 1) * 0.51f + 0.75f + 9.5367431640625e-07f * (float)(m - 1) * kQ);
   pfc[j] = ok ? make_float2(__fdiv_rn(kQ, tm), w0) : make_float2(0.f, __int_as_float(0x7f800000));
 }
@@ -382,6 +392,46 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
   }
 }
 
+// 14-bit fields (m <= 8): the rows of codebooks k < 4 and k >= 4 are summed as whole 32-bit words into A and B -- at most
+// four rows each, 4 * 16383 < 2^16, so neither 16-bit field carries -- and only the three words A, B and the unary are
+// split into their halves: 8 instead of 16 instructions per word and step.
+#ifndef RYL_K3_ADD
+#define RYL_K3_ADD 0
+#endif
+__device__ __forceinline__ uint32_t pf_add(uint32_t acc, uint32_t x, const uint32_t one, int r) {
+  if (RYL_K3_ADD == 1 || (RYL_K3_ADD == 2 && (r & 1))) return x * one + acc;   // IMAD (FMA pipe)
+  return acc + x;                                                              // IADD3 (ALU pipe; fuses two adds)
+}
+template <int M, int J>
+__device__ __forceinline__ void pf_rows14(const char* tqj, const Code& nb, const uint4 xu, int (&S)[8],
+                                          const uint32_t one) {
+  uint32_t A[4] = {0, 0, 0, 0}, Bq[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < M; k++) {
+    if (k != J) {
+      const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
+      const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+      const bool first = (k == 0) || (k == 1 && J == 0) || (k == 4) || (k == 5 && J == 4);
+      uint32_t (&G)[4] = k < 4 ? A : Bq;
+      if (first) { G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; }
+      else {
+        G[0] = pf_add(G[0], x.x, one, k); G[1] = pf_add(G[1], x.y, one, k);
+        G[2] = pf_add(G[2], x.z, one, k); G[3] = pf_add(G[3], x.w, one, k);
+      }
+    }
+  }
+  const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    uint32_t h = (xw[w] >> 16) + (A[w] >> 16);
+    uint32_t t = pf_add(A[w], xw[w], one, 1);
+    if (M > 4) { h += Bq[w] >> 16; t = pf_add(t, Bq[w], one, 0); }
+    S[w] = (int)(t - (h << 16));
+    S[4 + w] = (int)h;
+  }
+}
+
 // PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the 16-bit
 // tables (half the bytes of the fp32 rows): S(c) = rint(U_j[c]/scale_j) + sum_k q_jk[b_k][c], with
 //   |scale_j*S(c) - exact(c)| <= scale_j * ((M-1)*0.51 + 0.75)      quantisation of the rows (K2q) and of the unary
@@ -390,16 +440,26 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 // candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~1-3 % of
 // the steps, tools/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
 // construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
+#ifndef RYL_K3_BLOCKS
+#define RYL_K3_BLOCKS 4
+#endif
+// resident blocks per SM the register allocation is aimed at (m <= 8 with the pre-filter; the others need 64 registers)
+template <int M, bool PF>
+constexpr int k3_blocks() { return (PF && M <= 8) ? RYL_K3_BLOCKS : 4; }
+
 template <int M, bool PF, bool JSPEC = false>
-__global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
+__global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(IcmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int dpad = (p.d + 3) & ~3;                         // per-warp slot, 16-byte aligned (warp_cost loads float4)
   // UQS (m <= 8): the warp keeps its vector's unaries in shared memory, already in the pre-filter's integer units
   // (16 bit, relative to the codebook's smallest one): [M][32 lanes] x 16 B in front of the cost scratch
   constexpr bool UQS = PF && M <= 8;
-  unsigned char* smem_f = smem_raw + (UQS ? (size_t)nwarps * M * 512 : 0);
+  constexpr bool P14 = UQS && RYL_K3_QBITS == 14;      // 14-bit table fields (pf_rows14)
+  unsigned char* smem_f = smem_raw + (UQS ? (size_t)nwarps * (M * 512 + 64) : 0);
   uint4* uqw = reinterpret_cast<uint4*>(smem_raw + (size_t)warp * (UQS ? M * 512 : 0)) + lane;
+  // + the warp's own copy of {1/scale_j, W0_j}, W0 = +inf for a codebook whose unaries saturate for this vector
+  float2* pcw = reinterpret_cast<float2*>(smem_raw + (UQS ? (size_t)nwarps * M * 512 + (size_t)warp * 64 : 0));
   float* sq = reinterpret_cast<float*>(smem_f) + (size_t)warp * dpad;
   int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_f) + (size_t)nwarps * dpad);
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
@@ -428,21 +488,25 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
       // its vector's 8 KB of fp32 unaries ONCE (streaming), rounds them exactly as the step used to (one fma with
       // 1.5 * 2^23), subtracts the codebook's minimum and keeps the result as 16-bit fields in the row layout of the
       // quantised tables -- a step then adds the unary like one more row (LDS.128 instead of two LDG.128 from L2:
-      // -22 % of the step's L2 bytes, no per-step conversion).  A candidate more than 65534 units above the minimum
-      // saturates: its S is then a LOWER bound, so it can only add window members (exact path), and a winner that
-      // is itself saturated is sent to the exact path (checked below).  Garbage for a j whose window test fails
-      // (umax / scale_j >= 2^21, NaN) is never used: that test is per step and unchanged.
+      // -22 % of the step's L2 bytes, no per-step conversion).  If a candidate lies more than 65535 units above the
+      // minimum (8 * tmax_j with 14-bit tables) the fields cannot hold it: the warp's copy of the window constant
+      // is set to +inf for that codebook, which sends its steps down the exact path.  Garbage for a j whose window
+      // test fails anyway (umax / scale_j >= 2^21, NaN) is never used: that test is per step and unchanged.
       __syncwarp();
 #pragma unroll 1
       for (int j = 0; j < M; j++) {
-        const float inv = __ldg(&p.pfc[j].x);
+        const float2 pcj = __ldg(p.pfc + j);
+        const float inv = pcj.x;
         const float4 u0 = __ldcs(Ul + j * 64 + lane), u1 = __ldcs(Ul + j * 64 + 32 + lane);
         const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
         int q[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) q[i] = __float_as_int(fmaf(uu[i], inv, 12582912.0f)) - 0x4B400000;
         const int lm = min(min(min(q[0], q[1]), min(q[2], q[3])), min(min(q[4], q[5]), min(q[6], q[7])));
+        const int lx = max(max(max(q[0], q[1]), max(q[2], q[3])), max(max(q[4], q[5]), max(q[6], q[7])));
         const int base = __reduce_min_sync(0xffffffffu, lm);
+        const bool sat = (uint32_t)(__reduce_max_sync(0xffffffffu, lx) - base) > 65535u;
+        if (lane == 0) pcw[j] = make_float2(inv, sat ? __int_as_float(0x7f800000) : pcj.y);
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -487,75 +551,113 @@ __global__ void __launch_bounds__(256, 4) icm_warp_kernel(IcmParams p) {
           }
           int bc = -1;
           if (PF) {
-            const float2 pc = __ldg(p.pfc + j);                   // {1/scale_j, W0_j}
+            const float2 pc = UQS ? pcw[j] : __ldg(p.pfc + j);    // {1/scale_j, W0_j}
             const float wf = fmaf(slack, pc.x, pc.y);             // window, in units of scale_j
-            if (wf < pc.y + 4.0f) {                               // umax/scale_j < 2^21: integer sums fit (else exact)
+            // umax/scale_j < 2^21: integer sums fit (else exact).  UQS: the rows are fetched before the test is known
+            // (it only fails for degenerate inputs) so that the shared-memory load is off the critical path
+            if (UQS || wf < pc.y + 4.0f) {
               // ---- quantised pass: lane owns c = 4*lane + w (lo halves) and 128 + 4*lane + w (hi halves) ---------
-              uint32_t sl[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};   // sl = sum lo + (sum hi << 16) (mod 2^32)
-              if constexpr (UQS) {                                  // the unary is row 0 of the sum
-                const uint4 xu = uqw[j * 32];
-                sl[0] = xu.x; sl[1] = xu.y; sl[2] = xu.z; sl[3] = xu.w;
-                sh[0] = xu.x >> 16; sh[1] = xu.y >> 16; sh[2] = xu.z >> 16; sh[3] = xu.w >> 16;
-              }
               const char* tqj = reinterpret_cast<const char*>(p.Tq) + (size_t)j * (M * kH * 512) + lane * 16;
               asm volatile("" : "+l"(tqj));   // keep the base in a register pair: row address = one IMAD.WIDE
-              if constexpr (M <= 8 && JSPEC) {                     // one copy of the row loop per j (jump table)
-                switch (j) {
-                  case 0: pf_rows<M, 0>(tqj, nb, sl, sh, one); break;
-                  case 1: pf_rows<M, 1>(tqj, nb, sl, sh, one); break;
-                  case 2: pf_rows<M, 2>(tqj, nb, sl, sh, one); break;
-                  case 3: pf_rows<M, 3>(tqj, nb, sl, sh, one); break;
-                  case 4: pf_rows<M, 4>(tqj, nb, sl, sh, one); break;
-                  case 5: pf_rows<M, 5>(tqj, nb, sl, sh, one); break;
-                  case 6: pf_rows<M, 6>(tqj, nb, sl, sh, one); break;
-                  default: pf_rows<M, 7>(tqj, nb, sl, sh, one); break;
+              int S[8];
+              if constexpr (P14) {                                  // 14-bit fields: rows summed as whole words
+                const uint4 xu = uqw[j * 32];
+                if constexpr (JSPEC) {                              // one copy of the row loop per j (jump table)
+                  switch (j) {
+                    case 0: pf_rows14<M, 0>(tqj, nb, xu, S, one); break;
+                    case 1: pf_rows14<M, (M > 1 ? 1 : 0)>(tqj, nb, xu, S, one); break;
+                    case 2: pf_rows14<M, (M > 2 ? 2 : 0)>(tqj, nb, xu, S, one); break;
+                    case 3: pf_rows14<M, (M > 3 ? 3 : 0)>(tqj, nb, xu, S, one); break;
+                    case 4: pf_rows14<M, (M > 4 ? 4 : 0)>(tqj, nb, xu, S, one); break;
+                    case 5: pf_rows14<M, (M > 5 ? 5 : 0)>(tqj, nb, xu, S, one); break;
+                    case 6: pf_rows14<M, (M > 6 ? 6 : 0)>(tqj, nb, xu, S, one); break;
+                    default: pf_rows14<M, (M > 7 ? 7 : 0)>(tqj, nb, xu, S, one); break;
+                  }
+                } else {
+                  uint32_t A[4] = {0, 0, 0, 0}, Bq[4] = {0, 0, 0, 0};
+#pragma unroll
+                  for (int k = 0; k < M; k++) {
+                    if (k != j) {
+                      const uint32_t word = (uint32_t)(nb.lo >> (32 * (k >> 2)));
+                      const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+                      const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+                      uint32_t (&G)[4] = k < 4 ? A : Bq;
+                      G[0] += x.x; G[1] += x.y; G[2] += x.z; G[3] += x.w;
+                    }
+                  }
+                  const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
+#pragma unroll
+                  for (int w = 0; w < 4; w++) {
+                    const uint32_t h = (xw[w] >> 16) + (A[w] >> 16) + (Bq[w] >> 16);
+                    S[w] = (int)(A[w] + Bq[w] + xw[w] - (h << 16));
+                    S[4 + w] = (int)h;
+                  }
                 }
               } else {
+                uint32_t sl[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0};   // sl = sum lo + (sum hi << 16) (mod 2^32)
+                if constexpr (UQS) {                                  // the unary is row 0 of the sum
+                  const uint4 xu = uqw[j * 32];
+                  sl[0] = xu.x; sl[1] = xu.y; sl[2] = xu.z; sl[3] = xu.w;
+                  sh[0] = xu.x >> 16; sh[1] = xu.y >> 16; sh[2] = xu.z >> 16; sh[3] = xu.w >> 16;
+                }
+                if constexpr (M <= 8 && JSPEC) {                     // one copy of the row loop per j (jump table)
+                  switch (j) {
+                    case 0: pf_rows<M, 0>(tqj, nb, sl, sh, one); break;
+                    case 1: pf_rows<M, 1>(tqj, nb, sl, sh, one); break;
+                    case 2: pf_rows<M, 2>(tqj, nb, sl, sh, one); break;
+                    case 3: pf_rows<M, 3>(tqj, nb, sl, sh, one); break;
+                    case 4: pf_rows<M, 4>(tqj, nb, sl, sh, one); break;
+                    case 5: pf_rows<M, 5>(tqj, nb, sl, sh, one); break;
+                    case 6: pf_rows<M, 6>(tqj, nb, sl, sh, one); break;
+                    default: pf_rows<M, 7>(tqj, nb, sl, sh, one); break;
+                  }
+                } else {
 #pragma unroll
-                for (int k = 0; k < M; k++) {                      // k is a literal: byte extract + immediate offsets
-                  if (k != j) {
-                    const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
-                    const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
-                    sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
-                    sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
+                  for (int k = 0; k < M; k++) {                      // k is a literal: byte extract + immediate offsets
+                    if (k != j) {
+                      const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
+                      const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+                      const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+                      sl[0] += x.x; sl[1] += x.y; sl[2] += x.z; sl[3] += x.w;
+                      sh[0] += x.x >> 16; sh[1] += x.y >> 16; sh[2] += x.z >> 16; sh[3] += x.w >> 16;
+                    }
+                  }
+                }
+                // S(c) = rint(u(c)/scale_j) + sum_k (q_k(c) - 32768): the unary is rounded by the 1.5*2^23 trick inside
+                // one fma, whose integer image carries the constant 0x4B400000
+                if constexpr (UQS) {                                  // constants per step do not move the argmin
+#pragma unroll
+                  for (int w4 = 0; w4 < 4; w4++) {
+                    S[w4] = (int)(sl[w4] - (sh[w4] << 16));
+                    S[4 + w4] = (int)sh[w4];
+                  }
+                } else {
+                  constexpr int K = -0x4B400000 - (M - 1) * 32768;
+                  const float uu[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                  for (int w4 = 0; w4 < 4; w4++) {
+                    S[w4] = (int)(sl[w4] - (sh[w4] << 16)) + (__float_as_int(fmaf(uu[w4], pc.x, 12582912.0f)) + K);
+                    S[4 + w4] = (int)sh[w4] + (__float_as_int(fmaf(uu[4 + w4], pc.x, 12582912.0f)) + K);
                   }
                 }
               }
-              // S(c) = rint(u(c)/scale_j) + sum_k (q_k(c) - 32768): the unary is rounded by the 1.5*2^23 trick inside
-              // one fma, whose integer image carries the constant 0x4B400000
-              int S[8];
-              if constexpr (UQS) {                                  // constants per step do not move the argmin
+              // candidate keys S * 8 + (slot in the lane): the warp minimum names the winner (lane, slot) directly
+              int K[8];
 #pragma unroll
-                for (int w4 = 0; w4 < 4; w4++) {
-                  S[w4] = (int)(sl[w4] - (sh[w4] << 16));
-                  S[4 + w4] = (int)sh[w4];
-                }
-              } else {
-                constexpr int K = -0x4B400000 - (M - 1) * 32768;
-                const float uu[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-                for (int w4 = 0; w4 < 4; w4++) {
-                  S[w4] = (int)(sl[w4] - (sh[w4] << 16)) + (__float_as_int(fmaf(uu[w4], pc.x, 12582912.0f)) + K);
-                  S[4 + w4] = (int)sh[w4] + (__float_as_int(fmaf(uu[4 + w4], pc.x, 12582912.0f)) + K);
-                }
-              }
-              const int lm = min(min(min(S[0], S[1]), min(S[2], S[3])), min(min(S[4], S[5]), min(S[6], S[7])));
+              for (int i = 0; i < 8; i++) K[i] = S[i] * 8 + i;
+              // smallest (lm) and second smallest (m2) key of the lane: a tournament that does not wait for the warp
+              // reduction; the keys of a lane are distinct
+              const int p0 = min(K[0], K[1]), P0 = max(K[0], K[1]), p1 = min(K[2], K[3]), P1 = max(K[2], K[3]);
+              const int p2 = min(K[4], K[5]), P2 = max(K[4], K[5]), p3 = min(K[6], K[7]), P3 = max(K[6], K[7]);
+              const int q0 = min(p0, p1), Q0 = min(min(max(p0, p1), P0), P1);
+              const int q1 = min(p2, p3), Q1 = min(min(max(p2, p3), P2), P3);
+              const int lm = min(q0, q1), m2 = min(min(max(q0, q1), Q0), Q1);
               const int key = __reduce_min_sync(0xffffffffu, (lm << 5) | lane);      // |S| < 2^22
-              const int thr = (key >> 5) + (int)wf + 1;
-              uint32_t mask = 0;
-#pragma unroll
-              for (int i = 0; i < 8; i++) mask |= (S[i] <= thr) ? (1u << i) : 0u;
-              const int total = __reduce_add_sync(0xffffffffu, __popc(mask));
-              if (total == 1) {                                    // the only candidate inside the window: the argmin
-                const int wl = key & 31;
-                const int i = __shfl_sync(0xffffffffu, __ffs(mask) - 1, wl);
-                bc = (i < 4 ? 0 : 128) + wl * 4 + (i & 3);
-                if constexpr (UQS) {                                // a saturated winner's S is only a lower bound
-                  const uint16_t vw = reinterpret_cast<const uint16_t*>(uqw - lane + j * 32 + wl)[2 * (i & 3) + (i >> 2)];
-                  if (vw == 65535u) bc = -1;
-                }
-              }
+              const int thr8 = ((key >> 8) + (int)wf + 1) * 8;      // K < thr8  <=>  S <= min S + window
+              const int wl = key & 31;
+              // exactly one candidate inside the window: the winner's lane holds no second one, the others none
+              const bool unique = __all_sync(0xffffffffu, (lane == wl ? m2 : lm) >= thr8);
+              if (unique && (!UQS || wf < pc.y + 4.0f)) bc = (key & 128) | (wl << 2) | ((key >> 5) & 3);
             }
           }
           if (bc < 0) {
@@ -1059,8 +1161,8 @@ static int launch_icm_v(const IcmParams& p, size_t smem, cudaStream_t s) {
   const int warps = 8;
   RYL_CUDA(cudaFuncSetAttribute(icm_warp_kernel<M, PF, JSPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t need = (p.nc + warps - 1) / warps;
-  int per_sm = 4;                                                           // 4 blocks of 8 warps per SM
-  if (const char* e = getenv("RAYUELA_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(4, atoi(e)));   // knob
+  int per_sm = k3_blocks<M, PF>();                                          // blocks of 8 warps per SM
+  if (const char* e = getenv("RAYUELA_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, std::min(per_sm, atoi(e)));   // knob
   const int grid = (int)std::min<int64_t>(need, (int64_t)sm_count() * per_sm);
   RYL_LAUNCH((icm_warp_kernel<M, PF, JSPEC>), grid, warps * 32, smem, s, p);
   return RAYUELA_OK;
@@ -1072,7 +1174,7 @@ static int launch_icm(const IcmParams& p, cudaStream_t s) {
   size_t smem = (size_t)warps * ((p.d + 3) & ~3) * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 160 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
   if (!p.Tq) return launch_icm_v<M, false, false>(p, smem, s);
-  if (M <= 8) smem += (size_t)warps * M * 512;             // the warps' quantised unaries (UQS)
+  if (M <= 8) smem += (size_t)warps * (M * 512 + 64);      // the warps' quantised unaries + window constants (UQS)
   if constexpr (M <= 8) {
     if (!env_off("RAYUELA_B200_ICM_JSPEC")) return launch_icm_v<M, true, true>(p, smem, s);
   }
