@@ -210,7 +210,11 @@ __global__ void __launch_bounds__(256) quant_tables_kernel(const float* __restri
                                                            const unsigned int* __restrict__ tmax,
                                                            uint32_t* __restrict__ Tq) {
   const int j = blockIdx.z / m, k = blockIdx.z % m;
-  if (j == k) return;
+  if (j == k) {   // the diagonal blocks are all-zero words: a row that adds nothing (K3's uniform row loop reads it)
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < kH * (kH / 2); i += gridDim.x * 256)
+      Tq[(((size_t)j * m + k) * kH) * (kH / 2) + i] = 0u;
+    return;
+  }
   const float tm = __uint_as_float(tmax[j]);
   const float kQ = pf_q(m);
   const int off = (int)kQ + 1;
@@ -298,9 +302,15 @@ __global__ void __launch_bounds__(256) perturb_draws_kernel(unsigned long long* 
 
 // veccost for one vector, cooperatively by one warp; result uniform across the warp.
 // cb = ((0 + C_0[t,b_0]) + C_1[t,b_1]) + ... ; cost = sequential sum over t of (cb - x[t])^2, unfused.
+#ifndef RYL_K3_COSTSMALL
+#define RYL_K3_COSTSMALL 0
+#endif
 template <int M>
-__device__ __forceinline__ float warp_cost(const float* __restrict__ x, const float* __restrict__ C, const Code& code,
+__device__ __forceinline__ float warp_cost(const float* __restrict__ x, const float* __restrict__ C, const Code code,
                                            int d, float* sq, int lane) {
+#if RYL_K3_COSTSMALL
+#pragma unroll 1
+#endif
   for (int t = lane; t < d; t += 32) {
     float cb = 0.f;
 #pragma unroll
@@ -312,6 +322,9 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
   // sequential sum over t (every lane computes the same chain; 16-byte broadcast loads, same order of additions)
   float acc = 0.f;
   const int d4 = d & ~3;
+#if RYL_K3_COSTSMALL
+#pragma unroll 2
+#endif
   for (int t = 0; t < d4; t += 4) {
     const float4 v = *reinterpret_cast<const float4*>(sq + t);
     acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
@@ -319,6 +332,17 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
   for (int t = d4; t < d; t++) acc = __fadd_rn(acc, sq[t]);
   __syncwarp();
   return acc;
+}
+
+// one out-of-line copy for K3 (called at the start of a vector and once per ILS iteration): the kernel's hot instruction
+// footprint (8 specialised row loops + tail) sits at the instruction cache's capacity, every inlined copy costs throughput
+#ifndef RYL_K3_COSTCALL
+#define RYL_K3_COSTCALL 1
+#endif
+template <int M>
+__device__ __noinline__ float warp_cost_call(const float* __restrict__ x, const float* __restrict__ C, uint64_t lo,
+                                             uint64_t hi, int d, float* sq, int lane) {
+  return warp_cost<M>(x, C, Code{lo, hi}, d, sq, lane);
 }
 
 // L2 eviction-priority hints: with m = 16 the in-flight vectors' unaries (32 warps x 148 SMs x 16 KB = 78 MB) plus the
@@ -398,6 +422,15 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 #ifndef RYL_K3_ADD
 #define RYL_K3_ADD 0
 #endif
+#ifndef RYL_K3_LM3
+#define RYL_K3_LM3 0
+#endif
+#ifndef RYL_K3_LITE
+#define RYL_K3_LITE 1
+#endif
+#ifndef RYL_K3_COLD
+#define RYL_K3_COLD 1
+#endif
 __device__ __forceinline__ uint32_t pf_add(uint32_t acc, uint32_t x, const uint32_t one, int r) {
   if (RYL_K3_ADD == 1 || (RYL_K3_ADD == 2 && (r & 1))) return x * one + acc;   // IMAD (FMA pipe)
   return acc + x;                                                              // IADD3 (ALU pipe; fuses two adds)
@@ -430,6 +463,41 @@ __device__ __forceinline__ void pf_rows14(const char* tqj, const Code& nb, const
     S[w] = (int)(t - (h << 16));
     S[4 + w] = (int)h;
   }
+}
+
+// The exact step (fp32 rows in ascending k, first-minimum argmin -- encode_icm.cpp:28-58) out of line: with the windowed
+// evaluation of near-ties it runs for ~0.1 % of the steps of the m <= 8 kernels, so it stays out of their instruction
+// footprint and register allocation.
+template <int M>
+__device__ __noinline__ int exact_step_cold(const float* __restrict__ T, const float4* __restrict__ Uj, uint64_t codes,
+                                            int j, int lane) {
+  float4 a0 = __ldg(Uj + lane), a1 = __ldg(Uj + 32 + lane);
+#pragma unroll 1
+  for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j
+    const int k = kk + (kk >= j);
+    const float4* row = reinterpret_cast<const float4*>(T + (((size_t)j * M + k) * kH + ((codes >> (8 * k)) & 255u)) * kH);
+    const float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
+    a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
+    a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
+    a1.x = __fadd_rn(a1.x, r1.x); a1.y = __fadd_rn(a1.y, r1.y);
+    a1.z = __fadd_rn(a1.z, r1.z); a1.w = __fadd_rn(a1.w, r1.w);
+  }
+  float bv = a0.x;
+  int bc = lane * 4;
+  if (a0.y < bv) { bv = a0.y; bc = lane * 4 + 1; }
+  if (a0.z < bv) { bv = a0.z; bc = lane * 4 + 2; }
+  if (a0.w < bv) { bv = a0.w; bc = lane * 4 + 3; }
+  if (a1.x < bv) { bv = a1.x; bc = 128 + lane * 4; }
+  if (a1.y < bv) { bv = a1.y; bc = 128 + lane * 4 + 1; }
+  if (a1.z < bv) { bv = a1.z; bc = 128 + lane * 4 + 2; }
+  if (a1.w < bv) { bv = a1.w; bc = 128 + lane * 4 + 3; }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+    int oc = __shfl_xor_sync(0xffffffffu, bc, off);
+    if (ov < bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+  }
+  return __shfl_sync(0xffffffffu, bc, 0);   // NaN sums compare false everywhere: lane 0's view (c = 0 first)
 }
 
 // PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the 16-bit
@@ -478,7 +546,8 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
     if (l >= p.nc) break;
     const float* x = p.X + (size_t)l * p.d;
     Code cur = load_code<M>(p.B + (size_t)l * M);
-    float curcost = warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
+    float curcost = RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, cur.lo, cur.hi, p.d, sq, lane)
+                                    : warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
     const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
     uint32_t vsteps = 0, vexact = 0;                            // this vector's step counters (32 bit in the hot loop)
     float slack = 0.f;                                          // 2.002 * 2^-20 * umax (PF)
@@ -574,16 +643,17 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
                     default: pf_rows14<M, (M > 7 ? 7 : 0)>(tqj, nb, xu, S, one); break;
                   }
                 } else {
+                  // uniform row loop: all M rows, the diagonal one (k == j) is a row of zero words -- no dispatch on j,
+                  // one copy of the code, at the price of one more 512 B row per step
                   uint32_t A[4] = {0, 0, 0, 0}, Bq[4] = {0, 0, 0, 0};
 #pragma unroll
                   for (int k = 0; k < M; k++) {
-                    if (k != j) {
-                      const uint32_t word = (uint32_t)(nb.lo >> (32 * (k >> 2)));
-                      const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
-                      const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
-                      uint32_t (&G)[4] = k < 4 ? A : Bq;
-                      G[0] += x.x; G[1] += x.y; G[2] += x.z; G[3] += x.w;
-                    }
+                    const uint32_t word = (uint32_t)(nb.lo >> (32 * (k >> 2)));
+                    const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+                    uint32_t (&G)[4] = k < 4 ? A : Bq;
+                    if (k == 0 || k == 4) { G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; }
+                    else { G[0] += x.x; G[1] += x.y; G[2] += x.z; G[3] += x.w; }
                   }
                   const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
 #pragma unroll
@@ -651,17 +721,72 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
               const int p2 = min(K[4], K[5]), P2 = max(K[4], K[5]), p3 = min(K[6], K[7]), P3 = max(K[6], K[7]);
               const int q0 = min(p0, p1), Q0 = min(min(max(p0, p1), P0), P1);
               const int q1 = min(p2, p3), Q1 = min(min(max(p2, p3), P2), P3);
-              const int lm = min(q0, q1), m2 = min(min(max(q0, q1), Q0), Q1);
+              const int m2 = min(min(max(q0, q1), Q0), Q1);
+#if RYL_K3_LM3
+              // the smallest key by its own two-level tree: the warp reduction starts before the tournament is through
+              const int lm = min(min(min(min(K[0], K[1]), K[2]), min(min(K[3], K[4]), K[5])), min(K[6], K[7]));
+#else
+              const int lm = min(q0, q1);
+#endif
               const int key = __reduce_min_sync(0xffffffffu, (lm << 5) | lane);      // |S| < 2^22
               const int thr8 = ((key >> 8) + (int)wf + 1) * 8;      // K < thr8  <=>  S <= min S + window
               const int wl = key & 31;
               // exactly one candidate inside the window: the winner's lane holds no second one, the others none
               const bool unique = __all_sync(0xffffffffu, (lane == wl ? m2 : lm) >= thr8);
-              if (unique && (!UQS || wf < pc.y + 4.0f)) bc = (key & 128) | (wl << 2) | ((key >> 5) & 3);
+              const bool pf_ok = !UQS || wf < pc.y + 4.0f;
+              if (unique && pf_ok) bc = (key & 128) | (wl << 2) | ((key >> 5) & 3);
+#if RYL_K3_LITE
+              if constexpr (UQS) {
+                if (!unique && pf_ok) {
+                  // Near-tie: every candidate that can be the exact first-minimum is inside the window.  With at most
+                  // four of them only THEIR exact sums are formed -- eight lanes per candidate fetch its unary and its
+                  // M-1 table entries (32 B sectors instead of the M-1 whole fp32 rows), the chain ((u + r_1) + r_2) + ...
+                  // is added in ascending k by shuffles inside the group, and the smallest (value, c) wins.
+                  uint32_t mm = 0;
+#pragma unroll
+                  for (int i = 0; i < 8; i++) mm |= (K[i] < thr8) ? (1u << i) : 0u;
+                  const int total = __reduce_add_sync(0xffffffffu, __popc(mm));
+                  if (total <= 4) {
+                    uint32_t cs = 0;                                // the candidates, 8 bits each
+                    for (int r = 0; r < total; r++) {
+                      const int L = __ffs(__ballot_sync(0xffffffffu, mm != 0)) - 1;
+                      const int i = __shfl_sync(0xffffffffu, __ffs(mm) - 1, L);
+                      if (lane == L) mm &= mm - 1;
+                      cs |= (uint32_t)(((i & 4) << 5) | (L << 2) | (i & 3)) << (8 * r);
+                    }
+                    const int r = lane >> 3, t = lane & 7;
+                    const int c = (int)(cs >> (8 * r)) & 255;
+                    float v = 0.f;
+                    if (r < total) {
+                      if (t == 7) v = __ldg(p.U + ((size_t)l * M + j) * kH + c);
+                      else if (t < M - 1) {
+                        const int k = t + (t >= j);
+                        v = __ldg(p.T + (((size_t)j * M + k) * kH + code_get<M>(nb, k)) * kH + c);
+                      }
+                    }
+                    float acc = __shfl_sync(0xffffffffu, v, 7, 8);
+#pragma unroll
+                    for (int tt = 0; tt < M - 1; tt++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, tt, 8));
+                    float bv = r < total ? acc : __int_as_float(0x7f800000);
+                    int bcc = r < total ? c : 256 + r;
+#pragma unroll
+                    for (int off = 8; off <= 16; off <<= 1) {
+                      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                      const int oc = __shfl_xor_sync(0xffffffffu, bcc, off);
+                      if (ov < bv || (ov == bv && oc < bcc)) { bv = ov; bcc = oc; }
+                    }
+                    bc = __shfl_sync(0xffffffffu, bcc, 0);
+                  }
+                }
+              }
+#endif
             }
           }
           if (bc < 0) {
             if (PF) vexact++;
+            if constexpr (UQS && RYL_K3_COLD) {
+              bc = exact_step_cold<M>(p.T, Ul + j * 64, nb.lo, j, lane);
+            } else {
             if constexpr (UQS) {
               a0 = __ldg(Ul + j * 64 + lane);
               a1 = __ldg(Ul + j * 64 + 32 + lane);
@@ -703,6 +828,7 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
             }
             bc = __shfl_sync(0xffffffffu, bc, 0);   // NaN sums compare false everywhere: take lane 0's view (c = 0
                                                     // first, like the sequential scan of encode_icm.cpp:47-58)
+            }
           }
           dirty &= ~(1u << j);
           if ((uint32_t)bc != code_get<M>(nb, j)) {
@@ -714,7 +840,9 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
       // newcost, src/LSQ.jl:237.  When ICM led back to the codes the iteration started from (the perturbation was
       // undone -- the common case late in the search) the cost is the same arithmetic on the same inputs: reuse it.
       const bool same = nb.lo == cur.lo && nb.hi == cur.hi;
-      const float newcost = same ? curcost : warp_cost<M>(x, p.C, nb, p.d, sq, lane);
+      const float newcost = same ? curcost
+                                 : (RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, nb.lo, nb.hi, p.d, sq, lane)
+                                                    : warp_cost<M>(x, p.C, nb, p.d, sq, lane));
       if (lane == 0) {
         if (newcost == curcost) atomicAdd(&stats_s[2 * it], 1);
         if (newcost < curcost) atomicAdd(&stats_s[2 * it + 1], 1);
