@@ -429,9 +429,14 @@ def run_ours(args, cfg):
     steps_done, steps_total = core.last_icm_steps()
     steps_exact = core.last_icm_exact_steps()
     lib_ms = core.last_icm_timings()                        # the library's own CUDA-event phase timers (cross-check)
-    # bytes the kernel actually gathers: a 512 B quantised row per (step, other codebook) + the step's 1 KB unary row,
-    # and the 1 KB fp32 rows again for the steps the pre-filter left undecided; memoised steps read nothing
-    gather_bytes = float(steps_done) * ((m - 1) * H * 2 + H * 4) + float(steps_exact) * (m - 1) * H * 4
+    # bytes the kernel actually gathers: a 512 B quantised row per (step, other codebook) + the step's 1 KB unary row
+    # (m > 8), and the 1 KB fp32 rows again for the steps the pre-filter left undecided AND whose near-tie held more
+    # candidates than the windowed evaluation takes (steps_exact; the windowed near-ties read ~1 KB of sectors each and
+    # are not counted); memoised steps read nothing
+    if m <= 8:   # the unaries are read once per vector (the warp keeps them in shared memory as 16-bit integers)
+        gather_bytes = float(steps_done) * (m - 1) * H * 2 + float(n) * m * H * 4 + float(steps_exact) * m * H * 4
+    else:
+        gather_bytes = float(steps_done) * ((m - 1) * H * 2 + H * 4) + float(steps_exact) * (m - 1) * H * 4
     # SURVEY 8d algorithmic figure: every reference step gathers (m-1) fp32 rows of 256 entries
     gather_bytes_ref = float(n) * cfg["ilsiter"] * cfg["icmiter"] * m * (m - 1) * H * 4
     qerr = core.qerror(X, Bwork, C)
@@ -599,7 +604,8 @@ def run_ours(args, cfg):
     onchip_peak = 148 * 128 * sm_mhz * 1e6 / 1e9          # GB/s of L1/shared load bandwidth at the sampled clock
     tr = ncu_traffic("icm_m%d_n%d_ils%d" % (m, n, cfg["ilsiter"]))
     achieved = gather_bytes_ref / (k3_ms * 1e-3) / 1e9
-    icm_roof = {"bound": "issue/L2 (on-chip gather; DRAM < 1 % busy, so neither HBM nor tensor)",
+    icm_roof = {"bound": "L2 gather bandwidth / issue (ncu at HEAD: lts throughput %s %%, issue active %s %%; DRAM ~1 %% busy, so "
+                         "neither HBM nor tensor)" % ((tr or {}).get("lts_throughput_pct", "?"), (tr or {}).get("issue_active_pct", "?")),
                 "achieved": achieved, "peak": onchip_peak, "unit": "GB/s", "frac": achieved / onchip_peak,
                 "frac_actual": gather_bytes / (k3_ms * 1e-3) / 1e9 / onchip_peak,
                 "traffic": tr["bytes"] if tr else None, "traffic_source": tr,
@@ -611,9 +617,10 @@ def run_ours(args, cfg):
                 "gathered_actual": gather_bytes / (k3_ms * 1e-3) / 1e9,
                 "note": "achieved = SURVEY 8d algorithmic (work-equivalent) bytes n*ilsiter*icmiter*m*(m-1)*256*4 -- what "
                         "the reference's steps gather -- / K3 time, against the on-chip load ceiling.  frac_actual = "
-                        "the bytes the kernel really gathers (memoised steps skipped, 512 B 16-bit rows, fp32 rows "
-                        "only for near-ties) against the same ceiling; rows are served by L2 and the kernel is "
-                        "instruction-issue bound (profiles/).  `traffic` = ncu dram bytes of one K3 launch at HEAD"}
+                        "the bytes the kernel really gathers (memoised steps skipped, 512 B rows of 14-bit fields, "
+                        "unaries once per vector, near-ties resolved on the window's candidates) against the same "
+                        "ceiling; rows are served by L2, whose gather bandwidth (ncu lts throughput) is what binds "
+                        "(profiles/).  `traffic` = ncu dram bytes of one K3 launch at HEAD"}
     scan_bytes = float(nq) * n * (m + 4)                      # per rank: its shard of the base
     tr2 = ncu_traffic("scan_m%d_n%d_nq%d_k%d" % (m, n, nq, k))
     lookups = float(nq) * n * m / (scan_per * 1e-3)

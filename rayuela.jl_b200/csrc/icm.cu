@@ -142,6 +142,126 @@ __global__ void __launch_bounds__(256) unary_kernel(const float* __restrict__ C,
   }
 }
 
+// K1, d % 16 == 0: same outputs bit for bit (every output is still ONE fmaf chain over ascending t), restructured for
+// the FMA pipe: BK = 16 with two shared-memory stages (one block barrier per 16 steps instead of two per 8), and the
+// 8x8 register tile updated by 32 packed fma.rn.f32x2 per step (FFMA2: two independent chains per instruction, exact
+// per element) instead of 64 FFMA -- the issue slots that frees go to the shared-memory loads.
+__device__ __forceinline__ unsigned long long k1_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long k1_dup(float a) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(a));
+  return d;
+}
+__device__ __forceinline__ unsigned long long k1_pack(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__global__ void __launch_bounds__(256, 2) unary_kernel2(const float* __restrict__ C, const float* __restrict__ X,
+                                                        const float* __restrict__ nrm, float* __restrict__ U, int64_t n,
+                                                        int d, int mh, unsigned int* __restrict__ umax) {
+  constexpr int BM = 128, BN = 128, BK = 16, LD = 132;
+  __shared__ __align__(16) float As[2][BK][LD];
+  __shared__ __align__(16) float Bs[2][BK][LD];
+  __shared__ float Rs[16][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int e0 = blockIdx.x * BM;
+  const int64_t l0 = (int64_t)blockIdx.y * BN;
+  const int lr = tid >> 1, lk = (tid & 1) * 8;       // loader: row, first of its 8 k
+  unsigned long long acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0ull;    // (+0, +0)
+  const float* arow = C + (size_t)(e0 + lr) * d + lk;
+  const int64_t lv = l0 + lr;
+  const float* brow = X + (size_t)(lv < n ? lv : n - 1) * d + lk;
+  float4 ga[2], gb[2];
+  auto fetch = [&](int k0) {
+    ga[0] = *reinterpret_cast<const float4*>(arow + k0);
+    ga[1] = *reinterpret_cast<const float4*>(arow + k0 + 4);
+    gb[0] = *reinterpret_cast<const float4*>(brow + k0);
+    gb[1] = *reinterpret_cast<const float4*>(brow + k0 + 4);
+  };
+  auto stage = [&](int buf) {
+    const float av[8] = {ga[0].x, ga[0].y, ga[0].z, ga[0].w, ga[1].x, ga[1].y, ga[1].z, ga[1].w};
+    const float bv[8] = {gb[0].x, gb[0].y, gb[0].z, gb[0].w, gb[1].x, gb[1].y, gb[1].z, gb[1].w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      As[buf][lk + i][lr] = av[i];
+      Bs[buf][lk + i][lr] = bv[i];
+    }
+  };
+  fetch(0);
+  stage(0);
+  __syncthreads();
+  const int nt = d / BK;
+  for (int kt = 0; kt < nt; kt++) {
+    const int buf = kt & 1;
+    if (kt + 1 < nt) fetch((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const unsigned long long bp[4] = {k1_pack(b0.x, b0.y), k1_pack(b0.z, b0.w), k1_pack(b1.x, b1.y), k1_pack(b1.z, b1.w)};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const unsigned long long ad = k1_dup(av[i]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = k1_fma2(ad, bp[j], acc[i][j]);
+      }
+    }
+    if (kt + 1 < nt) stage(buf ^ 1);
+    __syncthreads();
+  }
+  float nr[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) nr[i] = nrm[e0 + ty * 8 + i];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int vt = (j < 4 ? 0 : 60) + tx * 4 + j;               // vector within the tile (see the Bs reads)
+    int64_t l = l0 + vt;
+    float mx = 0.f;
+    if (l < n) {
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const unsigned long long pr = acc[i][j >> 1];
+        const float a = __uint_as_float((j & 1) ? (unsigned)(pr >> 32) : (unsigned)pr);
+        o[i] = fmaf(-2.0f, a, nr[i]);                            // -2*dot exact, one rounding
+      }
+      float* dst = U + (size_t)l * mh + e0 + ty * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        mx = fmaxf(mx, fabsf(o[i]));
+        bad |= o[i] != o[i];
+      }
+      if (bad) mx = __int_as_float(0x7f800000);                 // NaN unaries -> +inf slack -> exact path
+    }
+    if (umax) Rs[ty][vt] = mx;
+  }
+  if (umax) {   // one atomic per vector per block: max over the block's 128 entries
+    __syncthreads();
+    if (tid < BN) {
+      float mx = 0.f;
+#pragma unroll
+      for (int t = 0; t < 16; t++) mx = fmaxf(mx, Rs[t][tid]);
+      if (l0 + tid < n) atomicMax(umax + l0 + tid, __float_as_uint(mx));
+    }
+  }
+}
+
 // ---- K2: pairwise tables, both orientations ------------------------------------------------------------
 // T[((j*m + k)*256 + b)*256 + c] = 2 * <C_j[:,c], C_k[:,b]>; the product is commutative inside fmaf, so
 // T[j][k][b][c] == T[k][j][c][b] bit for bit, i.e. this is binaries / binaries_t of the reference.
@@ -736,47 +856,47 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
               const bool pf_ok = !UQS || wf < pc.y + 4.0f;
               if (unique && pf_ok) bc = (key & 128) | (wl << 2) | ((key >> 5) & 3);
 #if RYL_K3_LITE
-              if constexpr (UQS) {
-                if (!unique && pf_ok) {
-                  // Near-tie: every candidate that can be the exact first-minimum is inside the window.  With at most
-                  // four of them only THEIR exact sums are formed -- eight lanes per candidate fetch its unary and its
-                  // M-1 table entries (32 B sectors instead of the M-1 whole fp32 rows), the chain ((u + r_1) + r_2) + ...
-                  // is added in ascending k by shuffles inside the group, and the smallest (value, c) wins.
-                  uint32_t mm = 0;
+              if (!unique && pf_ok) {
+                // Near-tie: every candidate that can be the exact first-minimum is inside the window.  With at most
+                // four of them (two for m > 8) only THEIR exact sums are formed -- G = 8 (16) lanes per candidate fetch
+                // its unary and its M-1 table entries (32 B sectors instead of the M-1 whole fp32 rows), the chain
+                // ((u + r_1) + r_2) + ... is added in ascending k by shuffles inside the group, and the smallest
+                // (value, c) wins.
+                constexpr int G = M <= 8 ? 8 : 16;
+                uint32_t mm = 0;
 #pragma unroll
-                  for (int i = 0; i < 8; i++) mm |= (K[i] < thr8) ? (1u << i) : 0u;
-                  const int total = __reduce_add_sync(0xffffffffu, __popc(mm));
-                  if (total <= 4) {
-                    uint32_t cs = 0;                                // the candidates, 8 bits each
-                    for (int r = 0; r < total; r++) {
-                      const int L = __ffs(__ballot_sync(0xffffffffu, mm != 0)) - 1;
-                      const int i = __shfl_sync(0xffffffffu, __ffs(mm) - 1, L);
-                      if (lane == L) mm &= mm - 1;
-                      cs |= (uint32_t)(((i & 4) << 5) | (L << 2) | (i & 3)) << (8 * r);
-                    }
-                    const int r = lane >> 3, t = lane & 7;
-                    const int c = (int)(cs >> (8 * r)) & 255;
-                    float v = 0.f;
-                    if (r < total) {
-                      if (t == 7) v = __ldg(p.U + ((size_t)l * M + j) * kH + c);
-                      else if (t < M - 1) {
-                        const int k = t + (t >= j);
-                        v = __ldg(p.T + (((size_t)j * M + k) * kH + code_get<M>(nb, k)) * kH + c);
-                      }
-                    }
-                    float acc = __shfl_sync(0xffffffffu, v, 7, 8);
-#pragma unroll
-                    for (int tt = 0; tt < M - 1; tt++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, tt, 8));
-                    float bv = r < total ? acc : __int_as_float(0x7f800000);
-                    int bcc = r < total ? c : 256 + r;
-#pragma unroll
-                    for (int off = 8; off <= 16; off <<= 1) {
-                      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                      const int oc = __shfl_xor_sync(0xffffffffu, bcc, off);
-                      if (ov < bv || (ov == bv && oc < bcc)) { bv = ov; bcc = oc; }
-                    }
-                    bc = __shfl_sync(0xffffffffu, bcc, 0);
+                for (int i = 0; i < 8; i++) mm |= (K[i] < thr8) ? (1u << i) : 0u;
+                const int total = __reduce_add_sync(0xffffffffu, __popc(mm));
+                if (total <= 32 / G) {
+                  uint32_t cs = 0;                                // the candidates, 8 bits each
+                  for (int r = 0; r < total; r++) {
+                    const int L = __ffs(__ballot_sync(0xffffffffu, mm != 0)) - 1;
+                    const int i = __shfl_sync(0xffffffffu, __ffs(mm) - 1, L);
+                    if (lane == L) mm &= mm - 1;
+                    cs |= (uint32_t)(((i & 4) << 5) | (L << 2) | (i & 3)) << (8 * r);
                   }
+                  const int r = lane / G, t = lane % G;
+                  const int c = (int)(cs >> (8 * r)) & 255;
+                  float v = 0.f;
+                  if (r < total) {
+                    if (t == G - 1) v = __ldg(p.U + ((size_t)l * M + j) * kH + c);
+                    else if (t < M - 1) {
+                      const int k = t + (t >= j);
+                      v = __ldg(p.T + (((size_t)j * M + k) * kH + code_get<M>(nb, k)) * kH + c);
+                    }
+                  }
+                  float acc = __shfl_sync(0xffffffffu, v, G - 1, G);
+#pragma unroll
+                  for (int tt = 0; tt < M - 1; tt++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, tt, G));
+                  float bv = r < total ? acc : __int_as_float(0x7f800000);
+                  int bcc = r < total ? c : 256 + r;
+#pragma unroll
+                  for (int off = G; off <= 16; off <<= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oc = __shfl_xor_sync(0xffffffffu, bcc, off);
+                    if (ov < bv || (ov == bv && oc < bcc)) { bv = ov; bcc = oc; }
+                  }
+                  bc = __shfl_sync(0xffffffffu, bcc, 0);
                 }
               }
 #endif
@@ -1282,6 +1402,19 @@ static bool env_off(const char* name) {
   return e && *e && atoi(e) == 0;
 }
 
+// K1 dispatch: the FFMA2 kernel for d % 16 == 0 (RAYUELA_B200_K1_V2=0: the round-1 kernel), else the generic tiles
+static int launch_unary(const float* C, const float* X, const float* nrm, float* U, int64_t n, int d, int mh,
+                        unsigned int* umax, cudaStream_t s) {
+  dim3 ug(mh / 128, (unsigned)((n + 127) / 128));
+  if (d % 16 == 0 && !env_off("RAYUELA_B200_K1_V2"))
+    RYL_LAUNCH(unary_kernel2, ug, 256, 0, s, C, X, nrm, U, n, d, mh, umax);
+  else if (d % 4 == 0)
+    RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, C, X, nrm, U, n, d, mh, umax);
+  else
+    RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, C, X, nrm, U, n, d, mh, umax);
+  return RAYUELA_OK;
+}
+
 // tuning knobs: RAYUELA_B200_ICM_PF=0 disables the quantised pre-filter (every step reads the exact fp32 rows),
 // RAYUELA_B200_ICM_JSPEC=0 the per-j specialised row loop (m <= 8: -3 % at m = 8, -7 % at m = 7)
 template <int M, bool PF, bool JSPEC>
@@ -1542,17 +1675,12 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
     float* U = U_d[c & (nbuf - 1)].as<float>();
     unsigned int* umax = umax_d[c & (nbuf - 1)].as<unsigned int>();
     if (piped && !dev) RYL_CUDA(cudaStreamWaitEvent(cs, ev_up[c].e, 0));
-    dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
     if (pf) RYL_CUDA(cudaMemsetAsync(umax, 0, (size_t)nc * sizeof(unsigned int), cs));
     if (stats) RYL_CUDA(cudaEventRecord(t_u0[c].e, cs));
     if (fast)
       RYL_TRY(unary_tc_launch(x_in.d + (size_t)l0 * d, Cp_d, nrm_d.as<float>(), U, umax, nc, d, mh, cs));
-    else if (d % 4 == 0)
-      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
-                 umax);
     else
-      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, cs, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh,
-                 umax);
+      RYL_TRY(launch_unary(c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U, nc, d, mh, umax, cs));
     if (stats) RYL_CUDA(cudaEventRecord(t_u1[c].e, cs));
     unsigned long long* draws = draws_d[c & (nbuf - 1)].as<unsigned long long>();
     if (predraw)
@@ -1859,13 +1987,7 @@ extern "C" int rayuela_get_unaries(const float* X, const float* C, int64_t n, in
     RYL_TRY(unary_tc_pack_codebooks(c_in.d, d, mh, &Cp_d, s));
     RYL_TRY(unary_tc_launch(x_in.d, Cp_d, nrm_d.as<float>(), u_out.d, nullptr, n, d, mh, s));
   } else {
-    dim3 ug(mh / 128, (unsigned)((n + 127) / 128));
-    if (d % 4 == 0)
-      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d, nrm_d.as<float>(), u_out.d, n, d, mh,
-                 (unsigned int*)nullptr);
-    else
-      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d, nrm_d.as<float>(), u_out.d, n, d, mh,
-                 (unsigned int*)nullptr);
+    RYL_TRY(launch_unary(c_in.d, x_in.d, nrm_d.as<float>(), u_out.d, n, d, mh, nullptr, s));
   }
   RYL_TRY(u_out.flush(s));
   if (!dev) RYL_CUDA(cudaStreamSynchronize(s));
@@ -1977,13 +2099,7 @@ extern "C" int rayuela_quantize_chainq(const float* X, const float* C, int64_t n
   const int64_t tt_stride = (int64_t)(m + 1) * kH * kH;
   for (int64_t l0 = 0; l0 < n; l0 += chunk) {
     const int64_t nc = std::min(chunk, n - l0);
-    dim3 ug(mh / 128, (unsigned)((nc + 127) / 128));
-    if (d % 4 == 0)
-      RYL_LAUNCH(unary_kernel<true>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh, (unsigned int*)nullptr);
-    else
-      RYL_LAUNCH(unary_kernel<false>, ug, 256, 0, s, c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(),
-                 U_d.as<float>(), nc, d, mh, (unsigned int*)nullptr);
+    RYL_TRY(launch_unary(c_in.d, x_in.d + (size_t)l0 * d, nrm_d.as<float>(), U_d.as<float>(), nc, d, mh, nullptr, s));
     RYL_TRY(launch_viterbi(U_d.as<float>(), TT, tt_stride, nc, m, b_out.d + (size_t)l0 * m, s));
   }
   RYL_TRY(b_out.flush(s));
