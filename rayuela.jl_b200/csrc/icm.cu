@@ -310,7 +310,12 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ C
 // without a carry, so the rows of a step are summed TWO candidates per integer add (see pf_rows14); the unit is 4x
 // coarser (more near-ties go to the exact path: ~5 % instead of ~1.5 % of the steps) but a step has 32 instructions
 // less.  m > 8: 16-bit fields q + 32768, hi / lo halves accumulated separately.
-__host__ __device__ inline float pf_q(int m) { return (m <= 8 && RYL_K3_QBITS == 14) ? 8191.0f : 32767.0f; }
+#ifndef RYL_K3_UQS16
+#define RYL_K3_UQS16 1
+#endif
+__host__ __device__ inline float pf_q(int m) {
+  return ((m <= 8 || RYL_K3_UQS16) && RYL_K3_QBITS == 14) ? 8191.0f : 32767.0f;
+}
 __global__ void __launch_bounds__(256) tmax_kernel(const float* __restrict__ T, int m, unsigned int* __restrict__ tmax) {
   const int j = blockIdx.y / m, k = blockIdx.y % m;
   if (j == k) return;
@@ -590,12 +595,13 @@ __device__ __forceinline__ void pf_rows14(const char* tqj, const Code& nb, const
 // footprint and register allocation.
 template <int M>
 __device__ __noinline__ int exact_step_cold(const float* __restrict__ T, const float4* __restrict__ Uj, uint64_t codes,
-                                            int j, int lane) {
+                                            uint64_t codes_hi, int j, int lane) {
   float4 a0 = __ldg(Uj + lane), a1 = __ldg(Uj + 32 + lane);
 #pragma unroll 1
   for (int kk = 0; kk < M - 1; kk++) {                  // ascending k != j
     const int k = kk + (kk >= j);
-    const float4* row = reinterpret_cast<const float4*>(T + (((size_t)j * M + k) * kH + ((codes >> (8 * k)) & 255u)) * kH);
+    const uint32_t b = (uint32_t)((k < 8 ? codes >> (8 * k) : codes_hi >> (8 * (k - 8))) & 255u);
+    const float4* row = reinterpret_cast<const float4*>(T + (((size_t)j * M + k) * kH + b) * kH);
     const float4 r0 = __ldg(row + lane), r1 = __ldg(row + 32 + lane);
     a0.x = __fadd_rn(a0.x, r0.x); a0.y = __fadd_rn(a0.y, r0.y);
     a0.z = __fadd_rn(a0.z, r0.z); a0.w = __fadd_rn(a0.w, r0.w);
@@ -633,7 +639,7 @@ __device__ __noinline__ int exact_step_cold(const float* __restrict__ T, const f
 #endif
 // resident blocks per SM the register allocation is aimed at (m <= 8 with the pre-filter; the others need 64 registers)
 template <int M, bool PF>
-constexpr int k3_blocks() { return (PF && M <= 8) ? RYL_K3_BLOCKS : 4; }
+constexpr int k3_blocks() { return (PF && M <= 8) ? RYL_K3_BLOCKS : (PF && RYL_K3_UQS16) ? 3 : 4; }
 
 template <int M, bool PF, bool JSPEC = false>
 __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(IcmParams p) {
@@ -642,12 +648,13 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
   const int dpad = (p.d + 3) & ~3;                         // per-warp slot, 16-byte aligned (warp_cost loads float4)
   // UQS (m <= 8): the warp keeps its vector's unaries in shared memory, already in the pre-filter's integer units
   // (16 bit, relative to the codebook's smallest one): [M][32 lanes] x 16 B in front of the cost scratch
-  constexpr bool UQS = PF && M <= 8;
+  constexpr bool UQS = PF && (M <= 8 || RYL_K3_UQS16);
   constexpr bool P14 = UQS && RYL_K3_QBITS == 14;      // 14-bit table fields (pf_rows14)
-  unsigned char* smem_f = smem_raw + (UQS ? (size_t)nwarps * (M * 512 + 64) : 0);
+  constexpr int PCB = M <= 8 ? 64 : 128;               // bytes of window constants per warp
+  unsigned char* smem_f = smem_raw + (UQS ? (size_t)nwarps * (M * 512 + PCB) : 0);
   uint4* uqw = reinterpret_cast<uint4*>(smem_raw + (size_t)warp * (UQS ? M * 512 : 0)) + lane;
   // + the warp's own copy of {1/scale_j, W0_j}, W0 = +inf for a codebook whose unaries saturate for this vector
-  float2* pcw = reinterpret_cast<float2*>(smem_raw + (UQS ? (size_t)nwarps * M * 512 + (size_t)warp * 64 : 0));
+  float2* pcw = reinterpret_cast<float2*>(smem_raw + (UQS ? (size_t)nwarps * M * 512 + (size_t)warp * PCB : 0));
   float* sq = reinterpret_cast<float*>(smem_f) + (size_t)warp * dpad;
   int* stats_s = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_f) + (size_t)nwarps * dpad);
   for (int i = threadIdx.x; i < 2 * p.ilsiter; i += blockDim.x) stats_s[i] = 0;
@@ -765,21 +772,23 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
                 } else {
                   // uniform row loop: all M rows, the diagonal one (k == j) is a row of zero words -- no dispatch on j,
                   // one copy of the code, at the price of one more 512 B row per step
-                  uint32_t A[4] = {0, 0, 0, 0}, Bq[4] = {0, 0, 0, 0};
+                  constexpr int NG = (M + 3) / 4;                  // groups of <= 4 rows: no carry out of a 14-bit field sum
+                  uint32_t G[NG][4];
 #pragma unroll
                   for (int k = 0; k < M; k++) {
-                    const uint32_t word = (uint32_t)(nb.lo >> (32 * (k >> 2)));
+                    const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
                     const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
                     const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
-                    uint32_t (&G)[4] = k < 4 ? A : Bq;
-                    if (k == 0 || k == 4) { G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; }
-                    else { G[0] += x.x; G[1] += x.y; G[2] += x.z; G[3] += x.w; }
+                    if ((k & 3) == 0) { G[k >> 2][0] = x.x; G[k >> 2][1] = x.y; G[k >> 2][2] = x.z; G[k >> 2][3] = x.w; }
+                    else { G[k >> 2][0] += x.x; G[k >> 2][1] += x.y; G[k >> 2][2] += x.z; G[k >> 2][3] += x.w; }
                   }
                   const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
 #pragma unroll
                   for (int w = 0; w < 4; w++) {
-                    const uint32_t h = (xw[w] >> 16) + (A[w] >> 16) + (Bq[w] >> 16);
-                    S[w] = (int)(A[w] + Bq[w] + xw[w] - (h << 16));
+                    uint32_t h = xw[w] >> 16, t = xw[w];
+#pragma unroll
+                    for (int g = 0; g < NG; g++) { h += G[g][w] >> 16; t += G[g][w]; }
+                    S[w] = (int)(t - (h << 16));
                     S[4 + w] = (int)h;
                   }
                 }
@@ -858,7 +867,7 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
 #if RYL_K3_LITE
               if (!unique && pf_ok) {
                 // Near-tie: every candidate that can be the exact first-minimum is inside the window.  With at most
-                // four of them (two for m > 8) only THEIR exact sums are formed -- G = 8 (16) lanes per candidate fetch
+                // four (m > 8: eight) of them only THEIR exact sums are formed, 32 / G at a time -- G = 8 (16) lanes per candidate fetch
                 // its unary and its M-1 table entries (32 B sectors instead of the M-1 whole fp32 rows), the chain
                 // ((u + r_1) + r_2) + ... is added in ascending k by shuffles inside the group, and the smallest
                 // (value, c) wins.
@@ -867,36 +876,43 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
 #pragma unroll
                 for (int i = 0; i < 8; i++) mm |= (K[i] < thr8) ? (1u << i) : 0u;
                 const int total = __reduce_add_sync(0xffffffffu, __popc(mm));
-                if (total <= 32 / G) {
-                  uint32_t cs = 0;                                // the candidates, 8 bits each
+                if (total <= (M <= 8 ? 4 : 8)) {                  // m <= 8: one round of four
+                  unsigned long long cs = 0;                      // the candidates, 8 bits each
                   for (int r = 0; r < total; r++) {
                     const int L = __ffs(__ballot_sync(0xffffffffu, mm != 0)) - 1;
                     const int i = __shfl_sync(0xffffffffu, __ffs(mm) - 1, L);
                     if (lane == L) mm &= mm - 1;
-                    cs |= (uint32_t)(((i & 4) << 5) | (L << 2) | (i & 3)) << (8 * r);
+                    cs |= (unsigned long long)(((i & 4) << 5) | (L << 2) | (i & 3)) << (8 * r);
                   }
-                  const int r = lane / G, t = lane % G;
-                  const int c = (int)(cs >> (8 * r)) & 255;
-                  float v = 0.f;
-                  if (r < total) {
-                    if (t == G - 1) v = __ldg(p.U + ((size_t)l * M + j) * kH + c);
-                    else if (t < M - 1) {
-                      const int k = t + (t >= j);
-                      v = __ldg(p.T + (((size_t)j * M + k) * kH + code_get<M>(nb, k)) * kH + c);
+                  float best_v = __int_as_float(0x7f800000);
+                  int best_c = 512;
+                  for (int base = 0; base < (M <= 8 ? 1 : total); base += 32 / G) {   // 32 / G candidates per round
+                    const int r = base + lane / G, t = lane % G;
+                    const int c = (int)(cs >> (8 * (r & 7))) & 255;
+                    float v = 0.f;
+                    if (r < total) {
+                      if (t == G - 1) v = __ldg(p.U + ((size_t)l * M + j) * kH + c);
+                      else if (t < M - 1) {
+                        const int k = t + (t >= j);
+                        v = __ldg(p.T + (((size_t)j * M + k) * kH + code_get<M>(nb, k)) * kH + c);
+                      }
                     }
-                  }
-                  float acc = __shfl_sync(0xffffffffu, v, G - 1, G);
+                    float acc = __shfl_sync(0xffffffffu, v, G - 1, G);
 #pragma unroll
-                  for (int tt = 0; tt < M - 1; tt++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, tt, G));
-                  float bv = r < total ? acc : __int_as_float(0x7f800000);
-                  int bcc = r < total ? c : 256 + r;
+                    for (int tt = 0; tt < M - 1; tt++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, v, tt, G));
+                    float bv = r < total ? acc : __int_as_float(0x7f800000);
+                    int bcc = r < total ? c : 256 + r;
 #pragma unroll
-                  for (int off = G; off <= 16; off <<= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                    const int oc = __shfl_xor_sync(0xffffffffu, bcc, off);
-                    if (ov < bv || (ov == bv && oc < bcc)) { bv = ov; bcc = oc; }
+                    for (int off = G; off <= 16; off <<= 1) {
+                      const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                      const int oc = __shfl_xor_sync(0xffffffffu, bcc, off);
+                      if (ov < bv || (ov == bv && oc < bcc)) { bv = ov; bcc = oc; }
+                    }
+                    bv = __shfl_sync(0xffffffffu, bv, 0);
+                    bcc = __shfl_sync(0xffffffffu, bcc, 0);
+                    if (bv < best_v || (bv == best_v && bcc < best_c)) { best_v = bv; best_c = bcc; }
                   }
-                  bc = __shfl_sync(0xffffffffu, bcc, 0);
+                  bc = best_c;
                 }
               }
 #endif
@@ -905,7 +921,7 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
           if (bc < 0) {
             if (PF) vexact++;
             if constexpr (UQS && RYL_K3_COLD) {
-              bc = exact_step_cold<M>(p.T, Ul + j * 64, nb.lo, j, lane);
+              bc = exact_step_cold<M>(p.T, Ul + j * 64, nb.lo, nb.hi, j, lane);
             } else {
             if constexpr (UQS) {
               a0 = __ldg(Ul + j * 64 + lane);
@@ -1435,7 +1451,7 @@ static int launch_icm(const IcmParams& p, cudaStream_t s) {
   size_t smem = (size_t)warps * ((p.d + 3) & ~3) * sizeof(float) + (size_t)2 * p.ilsiter * sizeof(int);
   RYL_ARG(smem <= 160 * 1024, "encode_icm: d * 8 warps (+ ilsiter) exceeds shared memory");
   if (!p.Tq) return launch_icm_v<M, false, false>(p, smem, s);
-  if (M <= 8) smem += (size_t)warps * (M * 512 + 64);      // the warps' quantised unaries + window constants (UQS)
+  if (M <= 8 || RYL_K3_UQS16) smem += (size_t)warps * (M * 512 + (M <= 8 ? 64 : 128));   // quantised unaries + window constants (UQS)
   if constexpr (M <= 8) {
     if (!env_off("RAYUELA_B200_ICM_JSPEC")) return launch_icm_v<M, true, true>(p, smem, s);
   }

@@ -22,7 +22,7 @@ def _case(m, seed, scale_u=1.0, scale_t=1.0, integers=False):
 @pytest.mark.parametrize("m", [2, 7, 8, 16])
 @pytest.mark.parametrize("kind", ["gauss", "big_unaries", "small_tables", "integers"])
 def test_prefilter_window_contains_the_exact_argmin(m, kind):
-    Q = 8191.0 if m <= 8 else 32767.0                                 # pf_q(m): 14-bit fields for m <= 8
+    Q = 8191.0                                                        # pf_q(m): 14-bit fields
     T, u = _case(m, seed=m * 10 + len(kind),
                  scale_u=40.0 if kind == "big_unaries" else 1.0,
                  scale_t=0.05 if kind == "small_tables" else 1.0,
@@ -63,12 +63,12 @@ def test_prefilter_window_contains_the_exact_argmin(m, kind):
         assert unique.mean() > 0.9                                    # the filter decides almost every step
 
 
-@pytest.mark.parametrize("m", [2, 5, 7, 8])
+@pytest.mark.parametrize("m", [2, 5, 7, 8, 12, 16])
 def test_packed_14bit_sums_equal_the_plain_integer_sums(m):
-    """icm_warp_kernel / pf_rows14 (m <= 8): the rows are offset fields q + 8192 in 1..16383, two per 32-bit word; the
-    rows of codebooks k < 4 and k >= 4 are added as whole words (A, B: at most four rows each, no carry between the
+    """icm_warp_kernel / pf_rows14: the rows are offset fields q + 8192 in 1..16383, two per 32-bit word; the rows of
+    every group of four codebooks (k >> 2) are added as whole words (at most four rows each, no carry between the
     fields), the unary is a 16-bit field pair relative to the codebook minimum.  The kernel's split
-    h = (xu >> 16) + (A >> 16) + (B >> 16), lo = (A + B + xu) - (h << 16) (mod 2^32) must reproduce the plain sums, and
+    h = (xu >> 16) + sum_g (G_g >> 16), lo = (sum_g G_g + xu) - (h << 16) (mod 2^32) must reproduce the plain sums, and
     keys S * 8 + slot / the second-smallest test must name the unique window member."""
     r = np.random.default_rng(m)
     nv, off = 2000, 8192
@@ -79,15 +79,16 @@ def test_packed_14bit_sums_equal_the_plain_integer_sums(m):
         uq = r.integers(0, 65536, (nv, 2)).astype(np.int64)
         uq[:5] = 65535
         words = ((q + off) | ((q + off)[..., 1:2] << 16))[..., 0].astype(np.uint64)     # lo | hi << 16
-        A = words[:4].sum(0) & 0xFFFFFFFF
-        B = words[4:].sum(0) & 0xFFFFFFFF if m > 4 else np.zeros(nv, np.uint64)
         xu = (uq[:, 0] | (uq[:, 1] << 16)).astype(np.uint64)
-        h = (xu >> 16) + (A >> 16) + (B >> 16)
-        lo = (A + B + xu - (h << 16)) & 0xFFFFFFFF
+        h, t = xu >> 16, xu.copy()
+        for g in range(0, m, 4):
+            G = words[g:g + 4].sum(0) & 0xFFFFFFFF
+            h, t = h + (G >> 16), t + G
+        lo = (t - (h << 16)) & 0xFFFFFFFF
         want_lo = uq[:, 0] + (q[:, :, 0] + off).sum(0)
         want_hi = uq[:, 1] + (q[:, :, 1] + off).sum(0)
         assert (lo.astype(np.int64) == want_lo).all() and (h.astype(np.int64) == want_hi).all()
-        assert want_hi.max() < 2 ** 18                                # keys S * 8 + slot, << 5 | lane stay below 2^26
+        assert want_hi.max() < 2 ** 19                                # keys S * 8 + slot, << 5 | lane stay below 2^27
 
 
 def test_unary_fields_saturation_is_flagged_per_codebook():
