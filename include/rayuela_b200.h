@@ -96,9 +96,11 @@ int rayuela_encode_icm(const float* X, const float* C, uint8_t* B, int64_t n, in
  * did not change since its last evaluation is skipped (its result is provably unchanged). Measurement aid. */
 int rayuela_encode_icm_steps(uint64_t* executed, uint64_t* total);
 
-/* Of the executed steps of that call, how many took the exact fp32 rows: a step is first evaluated from a 16-bit
- * quantised copy of the tables with a rigorous error window, and only steps with more than one candidate inside the
- * window (near-ties) re-read the fp32 rows -- the result is bit-identical either way. Measurement aid. */
+/* Of the executed steps of that call, how many took the exact fp32 rows: a step is first evaluated from a 14-bit
+ * quantised copy of the tables with a rigorous error window; steps with more than one candidate inside the window
+ * (near-ties) evaluate the exact fp32 chains of those candidates, and only with more than 4 (m > 8: 8) of them, or
+ * when the integer fields cannot hold the vector's unaries, re-read the whole fp32 rows -- the result is bit-identical
+ * either way. Measurement aid. */
 int rayuela_encode_icm_exact_steps(uint64_t* exact);
 
 /* CUDA-event timings (ms) of the last rayuela_encode_icm call of this thread that requested `stats`:

@@ -298,18 +298,18 @@ __global__ void __launch_bounds__(256) tables_kernel(const float* __restrict__ C
   }
 }
 
-// ---- K2q: 16-bit quantised copy of the tables for the K3 pre-filter -----------------------------------------
-// tmax[j] = max |T[j][k][.][.]| over k != j;  scale_j = tmax[j] / 32767;
-// Tq[j][k][b][pos] = rint(T[j][k][b][c] / scale_j) + 32768 (uint16, 1..65535), the row permuted so that the 16 bytes
-// lane L loads are the 32-bit words w = 0..3 = { lo: c = 4L + w, hi: c = 128 + 4L + w } -- the same candidates the
-// lane owns in the exact path.  |scale_j*(q-32768) - T| <= 0.51*scale_j (rint + one fp32 division rounding).
+// ---- K2q: quantised copy of the tables for the K3 pre-filter ------------------------------------------------------
+// tmax[j] = max |T[j][k][.][.]| over k != j;  scale_j = tmax[j] / Q;  Q = 8191 (14-bit fields; 32767 with RYL_K3_QBITS = 16)
+// Tq[j][k][b][pos] = rint(T[j][k][b][c] / scale_j) + Q + 1 (1..2Q+1, two 16-bit containers per word), the row permuted so
+// that the 16 bytes lane L loads are the 32-bit words w = 0..3 = { lo: c = 4L + w, hi: c = 128 + 4L + w } -- the same
+// candidates the lane owns in the exact path.  |scale_j*(q - Q - 1) - T| <= 0.51*scale_j (rint + one fp32 division rounding).
 #ifndef RYL_K3_QBITS
 #define RYL_K3_QBITS 14
 #endif
-// m <= 8 (RYL_K3_QBITS = 14): 14-bit fields q + 8192 in 1..16383 -- up to four rows add inside their 16-bit fields
-// without a carry, so the rows of a step are summed TWO candidates per integer add (see pf_rows14); the unit is 4x
-// coarser (more near-ties go to the exact path: ~5 % instead of ~1.5 % of the steps) but a step has 32 instructions
-// less.  m > 8: 16-bit fields q + 32768, hi / lo halves accumulated separately.
+// 14-bit fields q + 8192 in 1..16383: up to four rows add inside their 16-bit containers without a carry, so the rows of a
+// step are summed TWO candidates per integer add (pf_rows14 / the uniform loop of m > 8); the unit is 4x coarser than
+// with 16-bit fields (more near-ties: ~5 % instead of ~1.5 % of the steps, resolved on the window's candidates) but a
+// step has 32 instructions less.  RYL_K3_UQS16 = 0 keeps the round-2 kernel for m > 8 (16-bit fields, fp32 unaries).
 #ifndef RYL_K3_UQS16
 #define RYL_K3_UQS16 1
 #endif
@@ -626,18 +626,18 @@ __device__ __noinline__ int exact_step_cold(const float* __restrict__ T, const f
   return __shfl_sync(0xffffffffu, bc, 0);   // NaN sums compare false everywhere: lane 0's view (c = 0 first)
 }
 
-// PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the 16-bit
+// PF: quantised pre-filter.  The step's 256 sums are first formed in INTEGERS, in units of scale_j, from the quantised
 // tables (half the bytes of the fp32 rows): S(c) = rint(U_j[c]/scale_j) + sum_k q_jk[b_k][c], with
 //   |scale_j*S(c) - exact(c)| <= scale_j * ((M-1)*0.51 + 0.75)      quantisation of the rows (K2q) and of the unary
 //                              + 2^-20 * (umax + (M-1)*tmax_j)       fp32 roundings of the exact chain
 // =: delta.  Every candidate that can be the exact first-minimum has S <= min(S) + 2*delta/scale_j.  If exactly ONE
-// candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~1-3 % of
-// the steps, tools/q16_prefilter_probe.py) the step is redone with the exact fp32 rows.  Bit-identical by
-// construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
+// candidate is inside that window it IS the reference's argmin and the step is done; otherwise (near-ties, ~5 % of
+// the steps, tools/q16_prefilter_probe.py) the exact fp32 chains of the window's candidates decide (or, beyond 4 / 8
+// candidates, the exact fp32 rows).  Bit-identical by construction; the window W0_j + slack*inv_j is prepared per codebook by pf_consts_kernel.
 #ifndef RYL_K3_BLOCKS
 #define RYL_K3_BLOCKS 4
 #endif
-// resident blocks per SM the register allocation is aimed at (m <= 8 with the pre-filter; the others need 64 registers)
+// resident blocks per SM the register allocation is aimed at (m > 8 with shared-memory unaries: 3, 70 KB each)
 template <int M, bool PF>
 constexpr int k3_blocks() { return (PF && M <= 8) ? RYL_K3_BLOCKS : (PF && RYL_K3_UQS16) ? 3 : 4; }
 

@@ -361,6 +361,54 @@ def test_icm_prefilter_degenerate_inputs(rb, case):
     assert np.array_equal(bits(got["cost"][ok]), bits(want["cost"][ok]))
 
 
+@pytest.mark.parametrize("m", [5, 7, 8, 12, 16])
+@pytest.mark.parametrize("kind", ["ties", "wide_unaries", "gauss"])
+def test_icm_window_and_saturation_paths(rb, m, kind):
+    """The three ways a step of the pre-filter kernels can end, for the m <= 8 (per-j row loops) and the m > 8 (uniform
+    loop) kernels: a unique window member (gauss), a near-tie decided on the window's candidates by their exact
+    chains -- lowest index on exactly equal sums (ties: small integers), more than 4 / 8 of them falling back to the
+    whole rows -- and codebooks whose unaries do not fit the 16-bit fields of the shared-memory copy (wide_unaries:
+    flagged per vector and codebook, every such step takes the exact rows)."""
+    r = np.random.default_rng(100 + m)
+    n, d = 2500, 32
+    X = r.standard_normal((n, d)).astype(np.float32)
+    C = (r.standard_normal((m * 256, d)) / 3).astype(np.float32)
+    if kind == "ties":
+        X, C = np.round(X * 2), np.round(C * 3)
+    elif kind == "wide_unaries":
+        X *= 40.0
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    want = orc.encode_icm(X, C, B, 2, 3, 4, True, seed=21)
+    got = rb.core.encode_icm(X, C, B, 2, 3, 4, True, seed=21, want_cost=True, want_stats=True)
+    assert np.array_equal(got["B"], want["B"])
+    assert np.array_equal(bits(got["cost"]), bits(want["cost"]))
+    ex, _ = rb.core.last_icm_steps()
+    exact = rb.core.last_icm_exact_steps()
+    if kind == "gauss":
+        assert exact < ex // 20, (ex, exact)             # whole-row fallbacks are rare on ordinary data
+    if kind == "wide_unaries":
+        assert exact > ex // 4, (ex, exact)              # the saturation flag sends these steps to the exact rows
+
+
+@pytest.mark.parametrize("knob", ["RAYUELA_B200_ICM_JSPEC", "RAYUELA_B200_K1_V2"])
+def test_icm_alternative_kernels_agree(rb, monkeypatch, knob):
+    """RAYUELA_B200_ICM_JSPEC=0: the uniform row loop (zero diagonal blocks) for m <= 8; RAYUELA_B200_K1_V2=0: the
+    round-1 unary kernel.  Same bits as the default kernels and the oracle."""
+    r = np.random.default_rng(8)
+    n, d, m = 4000, 64, 8
+    X = r.standard_normal((n, d)).astype(np.float32)
+    C = (r.standard_normal((m * 256, d)) / 3).astype(np.float32)
+    B = r.integers(0, 256, (n, m), dtype=np.uint8)
+    want = orc.encode_icm(X, C, B, 2, 4, 4, True, seed=4)
+    for val in ("0", "1"):
+        monkeypatch.setenv(knob, val)
+        got = rb.core.encode_icm(X, C, B, 2, 4, 4, True, seed=4, want_cost=True)
+        assert np.array_equal(got["B"], want["B"]), (knob, val)
+        assert np.array_equal(bits(got["cost"]), bits(want["cost"])), (knob, val)
+        U = np.asarray(rb.core.get_unaries(X[:300], C, m)).reshape(300, m, 256).transpose(1, 0, 2)   # -> (m, n, 256)
+        assert np.array_equal(bits(np.ascontiguousarray(U)), bits(orc.get_unaries(X[:300], C, m))), (knob, val)
+
+
 def test_scan_compat_symbols(rb):
     for kind, fn in ((orc.PQ, "pq"), (orc.LSQ, "lsq"), (orc.CQ, "cq")):
         B, Xq, cb, nrm = _scan_case(kind, 20000, 9, 8, 128, seed=kind)

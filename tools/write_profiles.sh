@@ -15,7 +15,9 @@ def grab(path):
     t=open(path).read(); mul={'Gbyte':1e9,'Mbyte':1e6,'Kbyte':1e3,'byte':1}
     r=re.search(r"dram__bytes_read.sum\s+([\d.]+) (\w+)", t); w=re.search(r"dram__bytes_write.sum\s+([\d.]+) (\w+)", t)
     return float(r.group(1))*mul[r.group(2)]+float(w.group(1))*mul[w.group(2)]
-out={"icm_m8_n1000000_ils32": {"bytes": grab('/tmp/m_icm8.txt'), "kernel": "icm_warp_kernel<8,1,1>", "capture": "profiles/r2_icm_warp_kernel_m8_full_workload.txt", "what": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full"},
+def pct(path, name):
+    m = re.search(name + r"\s+([\d.]+)", open(path).read()); return round(float(m.group(1)), 1) if m else None
+out={"icm_m8_n1000000_ils32": {"bytes": grab('/tmp/m_icm8.txt'), "lts_throughput_pct": pct('/tmp/m_icm8.txt', 'lts__throughput.avg.pct_of_peak_sustained_elapsed'), "issue_active_pct": pct('/tmp/m_icm8.txt', 'smsp__issue_active.avg.pct_of_peak_sustained_active'), "kernel": "icm_warp_kernel<8,1,1>", "capture": "profiles/r2_icm_warp_kernel_m8_full_workload.txt", "what": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full"},
      "scan_m8_n1000000_nq10000_k1": {"bytes": grab('/tmp/m_scanx8.txt'), "kernel": "scanx_kernel<8,1,0,1> (pre-filter loop; main launch, 592 of 625 query tiles)", "capture": "profiles/r2_scanx8_kernel.txt", "what": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full"}}
 json.dump(out, open('profiles/ncu_traffic.json','w'), indent=1)
 PY
