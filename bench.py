@@ -429,14 +429,13 @@ def run_ours(args, cfg):
     steps_done, steps_total = core.last_icm_steps()
     steps_exact = core.last_icm_exact_steps()
     lib_ms = core.last_icm_timings()                        # the library's own CUDA-event phase timers (cross-check)
-    # bytes the kernel actually gathers: a 512 B quantised row per (step, other codebook) + the step's 1 KB unary row
-    # (m > 8), and the 1 KB fp32 rows again for the steps the pre-filter left undecided AND whose near-tie held more
+    # bytes the kernel actually gathers: a 512 B quantised row per (step, other codebook), and the 1 KB fp32 rows again for the steps the pre-filter left undecided AND whose near-tie held more
     # candidates than the windowed evaluation takes (steps_exact; the windowed near-ties read ~1 KB of sectors each and
     # are not counted); memoised steps read nothing
-    if m <= 8:   # the unaries are read once per vector (the warp keeps them in shared memory as 16-bit integers)
-        gather_bytes = float(steps_done) * (m - 1) * H * 2 + float(n) * m * H * 4 + float(steps_exact) * m * H * 4
-    else:
-        gather_bytes = float(steps_done) * ((m - 1) * H * 2 + H * 4) + float(steps_exact) * (m - 1) * H * 4
+    # the unaries are read once per vector (the warp keeps them in shared memory as 16-bit integers); m > 8 runs one
+    # uniform loop over all m rows (the diagonal one is a block of zero words)
+    rows = (m - 1) if m <= 8 else m
+    gather_bytes = float(steps_done) * rows * H * 2 + float(n) * m * H * 4 + float(steps_exact) * m * H * 4
     # SURVEY 8d algorithmic figure: every reference step gathers (m-1) fp32 rows of 256 entries
     gather_bytes_ref = float(n) * cfg["ilsiter"] * cfg["icmiter"] * m * (m - 1) * H * 4
     qerr = core.qerror(X, Bwork, C)
