@@ -361,7 +361,7 @@ def test_icm_prefilter_degenerate_inputs(rb, case):
     assert np.array_equal(bits(got["cost"][ok]), bits(want["cost"][ok]))
 
 
-@pytest.mark.parametrize("m", [5, 7, 8, 12, 16])
+@pytest.mark.parametrize("m", [4, 5, 6, 7, 8, 9, 12, 13, 16])
 @pytest.mark.parametrize("kind", ["ties", "wide_unaries", "gauss"])
 def test_icm_window_and_saturation_paths(rb, m, kind):
     """The three ways a step of the pre-filter kernels can end, for the m <= 8 (per-j row loops) and the m > 8 (uniform
