@@ -550,6 +550,9 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 #ifndef RYL_K3_LM3
 #define RYL_K3_LM3 0
 #endif
+#ifndef RYL_K3_DIAG0ROW
+#define RYL_K3_DIAG0ROW 1
+#endif
 #ifndef RYL_K3_LITE
 #define RYL_K3_LITE 1
 #endif
@@ -774,9 +777,18 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
                   // one copy of the code, at the price of one more 512 B row per step
                   constexpr int NG = (M + 3) / 4;                  // groups of <= 4 rows: no carry out of a 14-bit field sum
                   uint32_t G[NG][4];
+#if RYL_K3_DIAG0ROW
+                  // the diagonal row is always row 0 of block [j][j]: M hot rows in all that stay in L1, so the extra
+                  // row costs no L2 bandwidth (with the step's own code it was one of 256 M cold zero rows)
+                  Code nz = nb;
+                  if (M <= 8 || j < 8) nz.lo &= ~(0xFFull << (8 * (j & 7)));
+                  else nz.hi &= ~(0xFFull << (8 * (j & 7)));
+#else
+                  const Code nz = nb;
+#endif
 #pragma unroll
                   for (int k = 0; k < M; k++) {
-                    const uint32_t word = (uint32_t)((k < 8 ? nb.lo : nb.hi) >> (32 * ((k & 7) >> 2)));
+                    const uint32_t word = (uint32_t)((k < 8 ? nz.lo : nz.hi) >> (32 * ((k & 7) >> 2)));
                     const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
                     const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
                     if ((k & 3) == 0) { G[k >> 2][0] = x.x; G[k >> 2][1] = x.y; G[k >> 2][2] = x.z; G[k >> 2][3] = x.w; }
