@@ -551,7 +551,7 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 #define RYL_K3_LM3 0
 #endif
 #ifndef RYL_K3_DIAG0ROW
-#define RYL_K3_DIAG0ROW 1
+#define RYL_K3_DIAG0ROW 0
 #endif
 #ifndef RYL_K3_LITE
 #define RYL_K3_LITE 1
@@ -778,8 +778,8 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
                   constexpr int NG = (M + 3) / 4;                  // groups of <= 4 rows: no carry out of a 14-bit field sum
                   uint32_t G[NG][4];
 #if RYL_K3_DIAG0ROW
-                  // the diagonal row is always row 0 of block [j][j]: M hot rows in all that stay in L1, so the extra
-                  // row costs no L2 bandwidth (with the step's own code it was one of 256 M cold zero rows)
+                  // measured variant (off): the diagonal row is always row 0 of block [j][j] -- M hot rows that stay in L1
+                  // instead of one of 256 M zero rows in L2; no gain at m = 12 / 16, 3 % slower at m <= 8
                   Code nz = nb;
                   if (M <= 8 || j < 8) nz.lo &= ~(0xFFull << (8 * (j & 7)));
                   else nz.hi &= ~(0xFFull << (8 * (j & 7)));
