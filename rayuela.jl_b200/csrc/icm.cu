@@ -700,16 +700,16 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
         const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
         int q[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) q[i] = __float_as_int(fmaf(uu[i], inv, 12582912.0f)) - 0x4B400000;
+        for (int i = 0; i < 8; i++) q[i] = (int)(__float_as_uint(fmaf(uu[i], inv, 12582912.0f)) - 0x4B400000u);
         const int lm = min(min(min(q[0], q[1]), min(q[2], q[3])), min(min(q[4], q[5]), min(q[6], q[7])));
         const int lx = max(max(max(q[0], q[1]), max(q[2], q[3])), max(max(q[4], q[5]), max(q[6], q[7])));
         const int base = __reduce_min_sync(0xffffffffu, lm);
-        const bool sat = (uint32_t)(__reduce_max_sync(0xffffffffu, lx) - base) > 65535u;
+        const bool sat = (uint32_t)__reduce_max_sync(0xffffffffu, lx) - (uint32_t)base > 65535u;   // unsigned: garbage q may wrap
         if (lane == 0) pcw[j] = make_float2(inv, sat ? __int_as_float(0x7f800000) : pcj.y);
         uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; i++)
-          w[i] = min((uint32_t)(q[i] - base), 65535u) | (min((uint32_t)(q[4 + i] - base), 65535u) << 16);
+          w[i] = min((uint32_t)q[i] - (uint32_t)base, 65535u) | (min((uint32_t)q[4 + i] - (uint32_t)base, 65535u) << 16);
         uqw[j * 32] = make_uint4(w[0], w[1], w[2], w[3]);
       }
       __syncwarp();
