@@ -427,29 +427,34 @@ __global__ void __launch_bounds__(256) perturb_draws_kernel(unsigned long long* 
 
 // veccost for one vector, cooperatively by one warp; result uniform across the warp.
 // cb = ((0 + C_0[t,b_0]) + C_1[t,b_1]) + ... ; cost = sequential sum over t of (cb - x[t])^2, unfused.
-#ifndef RYL_K3_COSTSMALL
-#define RYL_K3_COSTSMALL 0
-#endif
 template <int M>
 __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const float* __restrict__ C, const Code code,
                                            int d, float* sq, int lane) {
-#if RYL_K3_COSTSMALL
-#pragma unroll 1
-#endif
-  for (int t = lane; t < d; t += 32) {
-    float cb = 0.f;
+  if ((d & 3) == 0) {   // four consecutive t per lane: one 16-byte load per codeword row (same arithmetic per element)
+    for (int t4 = lane * 4; t4 < d; t4 += 128) {
+      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < M; k++) cb = __fadd_rn(cb, __ldg(C + ((size_t)k * kH + code.get(k)) * d + t));
-    float df = __fsub_rn(cb, __ldg(x + t));
-    sq[t] = __fmul_rn(df, df);
+      for (int k = 0; k < M; k++) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(C + ((size_t)k * kH + code.get(k)) * d + t4));
+        cb.x = __fadd_rn(cb.x, c.x); cb.y = __fadd_rn(cb.y, c.y); cb.z = __fadd_rn(cb.z, c.z); cb.w = __fadd_rn(cb.w, c.w);
+      }
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + t4));
+      const float dx = __fsub_rn(cb.x, xv.x), dy = __fsub_rn(cb.y, xv.y), dz = __fsub_rn(cb.z, xv.z), dw = __fsub_rn(cb.w, xv.w);
+      *reinterpret_cast<float4*>(sq + t4) = make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
+    }
+  } else {
+    for (int t = lane; t < d; t += 32) {
+      float cb = 0.f;
+#pragma unroll
+      for (int k = 0; k < M; k++) cb = __fadd_rn(cb, __ldg(C + ((size_t)k * kH + code.get(k)) * d + t));
+      float df = __fsub_rn(cb, __ldg(x + t));
+      sq[t] = __fmul_rn(df, df);
+    }
   }
   __syncwarp();
   // sequential sum over t (every lane computes the same chain; 16-byte broadcast loads, same order of additions)
   float acc = 0.f;
   const int d4 = d & ~3;
-#if RYL_K3_COSTSMALL
-#pragma unroll 2
-#endif
   for (int t = 0; t < d4; t += 4) {
     const float4 v = *reinterpret_cast<const float4*>(sq + t);
     acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
