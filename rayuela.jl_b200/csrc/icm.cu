@@ -427,9 +427,16 @@ __global__ void __launch_bounds__(256) perturb_draws_kernel(unsigned long long* 
 
 // veccost for one vector, cooperatively by one warp; result uniform across the warp.
 // cb = ((0 + C_0[t,b_0]) + C_1[t,b_1]) + ... ; cost = sequential sum over t of (cb - x[t])^2, unfused.
+// `reject_above`: the caller only needs to know whether the cost is < or == that value (the ILS accept test, strict <).
+// The squares are first added as a tree (own values, then a 5-step butterfly: depth 8); both the tree sum and the
+// reference's sequential sum of the same n = d non-negative terms are within gamma_{n-1} resp. gamma_8 of the real sum, so
+// seq >= tree * (1 - gamma_{d-1}) / (1 + gamma_8): when tree > reject_above * (1 + 1.3e-7 * (d + 32)) (more than twice that
+// bound) the sequential sum is strictly above reject_above too and its 128 dependent adds are skipped -- the value returned
+// is then only known to compare greater.  NaN / inf on either side fail the test and take the exact chain.
 template <int M>
 __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const float* __restrict__ C, const Code code,
-                                           int d, float* sq, int lane) {
+                                           int d, float* sq, int lane, const float reject_above) {
+  float part = 0.f;
   if ((d & 3) == 0) {   // four consecutive t per lane: one 16-byte load per codeword row (same arithmetic per element)
     for (int t4 = lane * 4; t4 < d; t4 += 128) {
       float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -440,7 +447,9 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
       }
       const float4 xv = __ldg(reinterpret_cast<const float4*>(x + t4));
       const float dx = __fsub_rn(cb.x, xv.x), dy = __fsub_rn(cb.y, xv.y), dz = __fsub_rn(cb.z, xv.z), dw = __fsub_rn(cb.w, xv.w);
-      *reinterpret_cast<float4*>(sq + t4) = make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
+      const float4 o = make_float4(__fmul_rn(dx, dx), __fmul_rn(dy, dy), __fmul_rn(dz, dz), __fmul_rn(dw, dw));
+      *reinterpret_cast<float4*>(sq + t4) = o;
+      part = __fadd_rn(part, __fadd_rn(__fadd_rn(o.x, o.y), __fadd_rn(o.z, o.w)));
     }
   } else {
     for (int t = lane; t < d; t += 32) {
@@ -448,9 +457,15 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
 #pragma unroll
       for (int k = 0; k < M; k++) cb = __fadd_rn(cb, __ldg(C + ((size_t)k * kH + code.get(k)) * d + t));
       float df = __fsub_rn(cb, __ldg(x + t));
-      sq[t] = __fmul_rn(df, df);
+      const float o = __fmul_rn(df, df);
+      sq[t] = o;
+      part = __fadd_rn(part, o);
     }
   }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
+  // (the per-lane chain over chunks / strided t is at most d / 32 deep: covered by the d-proportional margin)
+  if (part > reject_above * (1.0f + 1.3e-7f * (float)(d + 32))) return part;   // strictly above: see the header
   __syncwarp();
   // sequential sum over t (every lane computes the same chain; 16-byte broadcast loads, same order of additions)
   float acc = 0.f;
@@ -471,8 +486,8 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
 #endif
 template <int M>
 __device__ __noinline__ float warp_cost_call(const float* __restrict__ x, const float* __restrict__ C, uint64_t lo,
-                                             uint64_t hi, int d, float* sq, int lane) {
-  return warp_cost<M>(x, C, Code{lo, hi}, d, sq, lane);
+                                             uint64_t hi, int d, float* sq, int lane, float reject_above) {
+  return warp_cost<M>(x, C, Code{lo, hi}, d, sq, lane, reject_above);
 }
 
 // L2 eviction-priority hints: with m = 16 the in-flight vectors' unaries (32 warps x 148 SMs x 16 KB = 78 MB) plus the
@@ -554,6 +569,9 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 #endif
 #ifndef RYL_K3_LM3
 #define RYL_K3_LM3 0
+#endif
+#ifndef RYL_K3_REJECT
+#define RYL_K3_REJECT 1
 #endif
 #ifndef RYL_K3_DIAG0ROW
 #define RYL_K3_DIAG0ROW 0
@@ -681,8 +699,8 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
     if (l >= p.nc) break;
     const float* x = p.X + (size_t)l * p.d;
     Code cur = load_code<M>(p.B + (size_t)l * M);
-    float curcost = RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, cur.lo, cur.hi, p.d, sq, lane)
-                                    : warp_cost<M>(x, p.C, cur, p.d, sq, lane);   // prevcost, src/LSQ.jl:201
+    float curcost = RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, cur.lo, cur.hi, p.d, sq, lane, __int_as_float(0x7f800000))
+                                    : warp_cost<M>(x, p.C, cur, p.d, sq, lane, __int_as_float(0x7f800000));   // prevcost, src/LSQ.jl:201
     const float4* Ul = reinterpret_cast<const float4*>(p.U + (size_t)l * M * kH);
     uint32_t vsteps = 0, vexact = 0;                            // this vector's step counters (32 bit in the hot loop)
     float slack = 0.f;                                          // 2.002 * 2^-20 * umax (PF)
@@ -994,8 +1012,8 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
       // undone -- the common case late in the search) the cost is the same arithmetic on the same inputs: reuse it.
       const bool same = nb.lo == cur.lo && nb.hi == cur.hi;
       const float newcost = same ? curcost
-                                 : (RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, nb.lo, nb.hi, p.d, sq, lane)
-                                                    : warp_cost<M>(x, p.C, nb, p.d, sq, lane));
+                                 : (RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, nb.lo, nb.hi, p.d, sq, lane, RYL_K3_REJECT ? curcost : __int_as_float(0x7f800000))
+                                                    : warp_cost<M>(x, p.C, nb, p.d, sq, lane, RYL_K3_REJECT ? curcost : __int_as_float(0x7f800000)));
       if (lane == 0) {
         if (newcost == curcost) atomicAdd(&stats_s[2 * it], 1);
         if (newcost < curcost) atomicAdd(&stats_s[2 * it + 1], 1);
@@ -1030,7 +1048,7 @@ __global__ void __launch_bounds__(256) veccost_kernel(const float* __restrict__ 
   float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * ((d + 3) & ~3);
   for (int64_t l = (int64_t)blockIdx.x * nwarps + warp; l < n; l += (int64_t)gridDim.x * nwarps) {
     Code c = load_code<M>(B + (size_t)l * M);
-    float v = warp_cost<M>(X + (size_t)l * d, C, c, d, sq, lane);
+    float v = warp_cost<M>(X + (size_t)l * d, C, c, d, sq, lane, __int_as_float(0x7f800000));
     if (lane == 0) cost[l] = v;
   }
 }
