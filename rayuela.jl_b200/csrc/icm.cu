@@ -427,6 +427,21 @@ __global__ void __launch_bounds__(256) perturb_draws_kernel(unsigned long long* 
 
 // veccost for one vector, cooperatively by one warp; result uniform across the warp.
 // cb = ((0 + C_0[t,b_0]) + C_1[t,b_1]) + ... ; cost = sequential sum over t of (cb - x[t])^2, unfused.
+// the reference's sequential sum of the d squares in sq[] (every lane computes the same chain; 16-byte broadcast loads)
+__device__ __forceinline__ float cost_seq(const float* sq, int d) {
+  __syncwarp();
+  float acc = 0.f;
+  const int d4 = d & ~3;
+  for (int t = 0; t < d4; t += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(sq + t);
+    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
+  }
+  for (int t = d4; t < d; t++) acc = __fadd_rn(acc, sq[t]);
+  __syncwarp();
+  return acc;
+}
+__device__ __noinline__ float cost_seq_call(const float* sq, int d) { return cost_seq(sq, d); }
+
 // `reject_above`: the caller only needs to know whether the cost is < or == that value (the ILS accept test, strict <).
 // The squares are first added as a tree (own values, then a 5-step butterfly: depth 8); both the tree sum and the
 // reference's sequential sum of the same n = d non-negative terms are within gamma_{n-1} resp. gamma_8 of the real sum, so
@@ -435,7 +450,8 @@ __global__ void __launch_bounds__(256) perturb_draws_kernel(unsigned long long* 
 // is then only known to compare greater.  NaN / inf on either side fail the test and take the exact chain.
 template <int M>
 __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const float* __restrict__ C, const Code code,
-                                           int d, float* sq, int lane, const float reject_above) {
+                                           int d, float* sq, int lane, const float reject_above,
+                                           const bool tree_only = false) {
   float part = 0.f;
   if ((d & 3) == 0) {   // four consecutive t per lane: one 16-byte load per codeword row (same arithmetic per element)
     for (int t4 = lane * 4; t4 < d; t4 += 128) {
@@ -465,18 +481,8 @@ __device__ __forceinline__ float warp_cost(const float* __restrict__ x, const fl
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(0xffffffffu, part, off));
   // (the per-lane chain over chunks / strided t is at most d / 32 deep: covered by the d-proportional margin)
-  if (part > reject_above * (1.0f + 1.3e-7f * (float)(d + 32))) return part;   // strictly above: see the header
-  __syncwarp();
-  // sequential sum over t (every lane computes the same chain; 16-byte broadcast loads, same order of additions)
-  float acc = 0.f;
-  const int d4 = d & ~3;
-  for (int t = 0; t < d4; t += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(sq + t);
-    acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, v.x), v.y), v.z), v.w);
-  }
-  for (int t = d4; t < d; t++) acc = __fadd_rn(acc, sq[t]);
-  __syncwarp();
-  return acc;
+  if (tree_only || part > reject_above * (1.0f + 1.3e-7f * (float)(d + 32))) return part;   // strictly above: see the header
+  return cost_seq(sq, d);
 }
 
 // one out-of-line copy for K3 (called at the start of a vector and once per ILS iteration): the kernel's hot instruction
@@ -1011,9 +1017,19 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
       // newcost, src/LSQ.jl:237.  When ICM led back to the codes the iteration started from (the perturbation was
       // undone -- the common case late in the search) the cost is the same arithmetic on the same inputs: reuse it.
       const bool same = nb.lo == cur.lo && nb.hi == cur.hi;
-      const float newcost = same ? curcost
-                                 : (RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, nb.lo, nb.hi, p.d, sq, lane, RYL_K3_REJECT ? curcost : __int_as_float(0x7f800000))
-                                                    : warp_cost<M>(x, p.C, nb, p.d, sq, lane, RYL_K3_REJECT ? curcost : __int_as_float(0x7f800000)));
+      // m <= 7: squares + tree sum inline (the common, rejected case ends there), the reference-order chain as a call;
+      // m = 8, whose hot loop sits at the instruction cache's capacity, calls the whole evaluation (measured: 176 vs 181 ms
+      // at m = 8, 142 vs 140 ms at m = 7)
+      float newcost = curcost;
+      if (!same) {
+        if constexpr (M <= 7 && RYL_K3_REJECT) {
+          newcost = warp_cost<M>(x, p.C, nb, p.d, sq, lane, curcost, true);
+          if (!(newcost > curcost * (1.0f + 1.3e-7f * (float)(p.d + 32)))) newcost = cost_seq_call(sq, p.d);
+        } else {
+          newcost = RYL_K3_COSTCALL ? warp_cost_call<M>(x, p.C, nb.lo, nb.hi, p.d, sq, lane, RYL_K3_REJECT ? curcost : __int_as_float(0x7f800000))
+                                    : warp_cost<M>(x, p.C, nb, p.d, sq, lane, RYL_K3_REJECT ? curcost : __int_as_float(0x7f800000));
+        }
+      }
       if (lane == 0) {
         if (newcost == curcost) atomicAdd(&stats_s[2 * it], 1);
         if (newcost < curcost) atomicAdd(&stats_s[2 * it + 1], 1);
