@@ -544,14 +544,15 @@ struct IcmParams {
 };
 
 // ---- K3: one warp per vector, all ILS iterations of that vector back to back ----------------------------
-// Lane owns candidates c = r*128 + lane*4 + e (r<2, e<4): every 1 KB row (unary or pairwise) is two
-// coalesced 512 B float4 loads per warp.  Unaries are re-read per step but a vector's 8 KB stay L2-resident
-// for its whole stay in the warp; the m*(m-1)*256 KB of tables live in L2.
-// The (M-1) quantised rows of one step with the conditioned codebook J as a LITERAL: no per-row predicate, no
-// predicated-off row.  sl = sum lo + (sum hi << 16) (mod 2^32), sh = sum hi.
-// The step is bound by the integer ALU pipe (IADD3 / LEA / LOP3 / SHF / ISETP issue at one warp-instruction per two
-// clocks; ncu: ~137 of a step's ~241 instructions, 76 % pipe utilisation), while the FMA pipe idles.  `one` is a kernel
-// parameter equal to 1 that the compiler cannot fold, so x * one + s is emitted as IMAD (FMA pipe) instead of IADD3.
+// Lane owns candidates c = r*128 + lane*4 + e (r<2, e<4): every row (unary or pairwise) is one (quantised, 512 B) or two
+// (fp32, 1 KB) coalesced 16-byte loads per lane.  The m*m*128 KB of quantised tables live in L2; the vector's unaries are
+// read once and kept by the warp in shared memory as 16-bit integers (see the kernel); the fp32 tables and unaries are
+// touched only by near-ties.  DESIGN.md 4 / 4d has the history and the measurements behind each choice.
+//
+// pf_rows: the row loop of the 16-bit-field build (RYL_K3_QBITS = 16; the shipped build uses pf_rows14 below).  The
+// (M-1) quantised rows of one step with the conditioned codebook J as a LITERAL: no per-row predicate, no predicated-off
+// row.  sl = sum lo + (sum hi << 16) (mod 2^32), sh = sum hi.  `one` is a kernel parameter equal to 1 that the compiler
+// cannot fold, so x * one + s is emitted as IMAD (FMA pipe) instead of IADD3 (that build was bound by the integer ALU pipe).
 template <int M, int J>
 __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_t (&sl)[4], uint32_t (&sh)[4],
                                         const uint32_t one) {
@@ -570,28 +571,21 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 // 14-bit fields (m <= 8): the rows of codebooks k < 4 and k >= 4 are summed as whole 32-bit words into A and B -- at most
 // four rows each, 4 * 16383 < 2^16, so neither 16-bit field carries -- and only the three words A, B and the unary are
 // split into their halves: 8 instead of 16 instructions per word and step.
-#ifndef RYL_K3_ADD
-#define RYL_K3_ADD 0
-#endif
-#ifndef RYL_K3_LM3
-#define RYL_K3_LM3 0
-#endif
-#ifndef RYL_K3_REJECT
-#define RYL_K3_REJECT 1
-#endif
-#ifndef RYL_K3_DIAG0ROW
-#define RYL_K3_DIAG0ROW 0
-#endif
+// compile-time variants kept for A/B builds (tools/build_variant.sh); the defaults are the measured optima
 #ifndef RYL_K3_LITE
-#define RYL_K3_LITE 1
+#define RYL_K3_LITE 1        // near-ties decided on the window's candidates
 #endif
 #ifndef RYL_K3_COLD
-#define RYL_K3_COLD 1
+#define RYL_K3_COLD 1        // whole-row exact step out of line
 #endif
-__device__ __forceinline__ uint32_t pf_add(uint32_t acc, uint32_t x, const uint32_t one, int r) {
-  if (RYL_K3_ADD == 1 || (RYL_K3_ADD == 2 && (r & 1))) return x * one + acc;   // IMAD (FMA pipe)
-  return acc + x;                                                              // IADD3 (ALU pipe; fuses two adds)
-}
+#ifndef RYL_K3_REJECT
+#define RYL_K3_REJECT 1      // certified early rejection in the cost evaluation
+#endif
+#ifndef RYL_K3_DIAG0ROW
+#define RYL_K3_DIAG0ROW 0    // uniform row loop: one L1-resident zero row instead of the diagonal block's
+#endif
+// (adds on the FMA pipe -- x * one + acc -- measured slower here than IADD3, which fuses two adds: 194 vs 187 ms)
+__device__ __forceinline__ uint32_t pf_add(uint32_t acc, uint32_t x, const uint32_t, int) { return acc + x; }
 template <int M, int J>
 __device__ __forceinline__ void pf_rows14(const char* tqj, const Code& nb, const uint4 xu, int (&S)[8],
                                           const uint32_t one) {
@@ -892,12 +886,7 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
               const int q0 = min(p0, p1), Q0 = min(min(max(p0, p1), P0), P1);
               const int q1 = min(p2, p3), Q1 = min(min(max(p2, p3), P2), P3);
               const int m2 = min(min(max(q0, q1), Q0), Q1);
-#if RYL_K3_LM3
-              // the smallest key by its own two-level tree: the warp reduction starts before the tournament is through
-              const int lm = min(min(min(min(K[0], K[1]), K[2]), min(min(K[3], K[4]), K[5])), min(K[6], K[7]));
-#else
               const int lm = min(q0, q1);
-#endif
               const int key = __reduce_min_sync(0xffffffffu, (lm << 5) | lane);      // |S| < 2^22
               const int thr8 = ((key >> 8) + (int)wf + 1) * 8;      // K < thr8  <=>  S <= min S + window
               const int wl = key & 31;

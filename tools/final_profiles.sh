@@ -17,4 +17,10 @@ timeout 300 python tools/configs01.py > gpurun_out/r2_configs01.json 2> gpurun_o
 timeout 400 python bench_rows.py > gpurun_out/r2_rows.json 2> gpurun_out/r2_rows.err
 timeout 300 python tools/scan_bench.py 1000000 10000 8,16 1,10,100,1000,4000 5 > gpurun_out/r2_scan_bench.txt 2>&1
 { echo '# RAYUELA_B200_SCAN_PREFILTER=0 (fp32 loop for every k)'; RAYUELA_B200_SCAN_PREFILTER=0 timeout 300 python tools/scan_bench.py 1000000 10000 8,16 1,10,100 5; } >> gpurun_out/r2_scan_bench.txt 2>&1
-cat gpurun_out/r2_pytest_gpu.txt; ls -la gpurun_out | grep r2_
+# gpurun copies back at most 64 MiB: summarise the captures here and keep only the K3 report itself
+for r in icm8 icm16 scanx8 scanx8_fp32 unary_tc unary_exact; do
+  [ -f gpurun_out/r2_$r.ncu-rep ] && python tools/ncu_metrics.py gpurun_out/r2_$r.ncu-rep > gpurun_out/m_$r.txt 2>/dev/null
+done
+[ -f gpurun_out/r2_icm8.ncu-rep ] && ncu -i gpurun_out/r2_icm8.ncu-rep --page source --csv > gpurun_out/icm8_source.csv 2>/dev/null
+rm -f gpurun_out/r2_icm16.ncu-rep gpurun_out/r2_scanx8.ncu-rep gpurun_out/r2_scanx8_fp32.ncu-rep gpurun_out/r2_unary_tc.ncu-rep gpurun_out/r2_unary_exact.ncu-rep
+cat gpurun_out/r2_pytest_gpu.txt; ls -la gpurun_out | grep "r2_\|m_" 
