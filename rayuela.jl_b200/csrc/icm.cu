@@ -581,6 +581,9 @@ __device__ __forceinline__ void pf_rows(const char* tqj, const Code& nb, uint32_
 #ifndef RYL_K3_REJECT
 #define RYL_K3_REJECT 1      // certified early rejection in the cost evaluation
 #endif
+#ifndef RYL_K3_HALF
+#define RYL_K3_HALF 0      // two register-indexed copies of the row loop instead of M literal ones
+#endif
 #ifndef RYL_K3_DIAG0ROW
 #define RYL_K3_DIAG0ROW 0    // uniform row loop: one L1-resident zero row instead of the diagonal block's
 #endif
@@ -611,6 +614,52 @@ __device__ __forceinline__ void pf_rows14(const char* tqj, const Code& nb, const
     uint32_t h = (xw[w] >> 16) + (A[w] >> 16);
     uint32_t t = pf_add(A[w], xw[w], one, 1);
     if (M > 4) { h += Bq[w] >> 16; t = pf_add(t, Bq[w], one, 0); }
+    S[w] = (int)(t - (h << 16));
+    S[4 + w] = (int)h;
+  }
+}
+
+// Two copies of the row loop instead of M (RYL_K3_HALF, 5 <= M <= 8): the conditioned codebook j only selects WHICH
+// three (or M-5) rows of its own group of four are read -- those rows take their codebook index from a register
+// (k = (j + r) & 3 resp. 4 + (j - 4 + r) % (M - 4)), the other group's rows are literals.  +2 instructions per
+// register-indexed row, but a quarter of the code of the per-j copies and a two-way branch instead of a jump table.
+template <int M, bool LOW>
+__device__ __forceinline__ void pf_rows14_half(const char* tqj, const Code& nb, const uint4 xu, int (&S)[8], const int j) {
+  constexpr int GB = M - 4;                                 // rows of the second group
+  uint32_t A[4] = {0, 0, 0, 0}, Bq[4] = {0, 0, 0, 0};
+  auto row_lit = [&](const int k, uint32_t (&G)[4], const bool first) {
+    const uint32_t word = (uint32_t)(nb.lo >> (32 * (k >> 2)));
+    const uint32_t code = __byte_perm(word, 0, 0x4440 | (k & 3));
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)k * (kH * 512) + (size_t)code * 512));
+    if (first) { G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; }
+    else { G[0] += x.x; G[1] += x.y; G[2] += x.z; G[3] += x.w; }
+  };
+  auto row_reg = [&](const int k, uint32_t (&G)[4], const bool first) {
+    const uint32_t code = (uint32_t)(nb.lo >> (8 * k)) & 255u;
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(tqj + (size_t)(k * kH + code) * 512));
+    if (first) { G[0] = x.x; G[1] = x.y; G[2] = x.z; G[3] = x.w; }
+    else { G[0] += x.x; G[1] += x.y; G[2] += x.z; G[3] += x.w; }
+  };
+  if (LOW) {                                                // j in 0..3
+#pragma unroll
+    for (int r = 1; r < 4; r++) row_reg((j + r) & 3, A, r == 1);
+#pragma unroll
+    for (int k = 4; k < M; k++) row_lit(k, Bq, k == 4);
+  } else {                                                  // j in 4..M-1
+#pragma unroll
+    for (int k = 0; k < 4; k++) row_lit(k, A, k == 0);
+#pragma unroll
+    for (int r = 1; r < GB; r++) {
+      int kk = j - 4 + r;
+      if (kk >= GB) kk -= GB;
+      row_reg(4 + kk, Bq, r == 1);
+    }
+  }
+  const uint32_t xw[4] = {xu.x, xu.y, xu.z, xu.w};
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    const uint32_t h = (xw[w] >> 16) + (A[w] >> 16) + (Bq[w] >> 16);
+    const uint32_t t = A[w] + xw[w] + Bq[w];
     S[w] = (int)(t - (h << 16));
     S[4 + w] = (int)h;
   }
@@ -784,7 +833,10 @@ __global__ void __launch_bounds__(256, (k3_blocks<M, PF>())) icm_warp_kernel(Icm
               int S[8];
               if constexpr (P14) {                                  // 14-bit fields: rows summed as whole words
                 const uint4 xu = uqw[j * 32];
-                if constexpr (JSPEC) {                              // one copy of the row loop per j (jump table)
+                if constexpr (JSPEC && RYL_K3_HALF && M >= 5) {     // two copies: j in its group of four
+                  if (j < 4) pf_rows14_half<M, true>(tqj, nb, xu, S, j);
+                  else pf_rows14_half<M, false>(tqj, nb, xu, S, j);
+                } else if constexpr (JSPEC) {                       // one copy of the row loop per j (jump table)
                   switch (j) {
                     case 0: pf_rows14<M, 0>(tqj, nb, xu, S, one); break;
                     case 1: pf_rows14<M, (M > 1 ? 1 : 0)>(tqj, nb, xu, S, one); break;
