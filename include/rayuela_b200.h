@@ -27,7 +27,8 @@ extern "C" {
 #define RAYUELA_ERR_OOM (-3)
 
 /* flags */
-#define RAYUELA_DEVICE_PTRS 1u /* all array arguments are device pointers on the current device */
+#define RAYUELA_DEVICE_PTRS 1u /* all array arguments are device pointers on the current device; X and C must be 16-byte
+                                * aligned when d % 4 == 0 (any cudaMalloc / CuArray / torch allocation is) */
 #define RAYUELA_FAST_UNARIES 2u /* rayuela_encode_icm / rayuela_get_unaries: OPT-IN tensor-core unaries.  The one dense
                                  * contraction of the path, -2*C'X (CUBLAS sgemm in the reference, src/LSQ_GPU.jl:74), runs as
                                  * a tcgen05 bf16x3 GEMM (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM) instead of the exact

@@ -1629,6 +1629,8 @@ static int encode_icm_single(const float* X, const float* C, uint8_t* B, int64_t
                              float* cost_out, int* stats, unsigned flags, cudaStream_t s) {
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
   const int mh = m * kH;
+  RYL_ARG(!dev || d % 4 != 0 || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+          "encode_icm: device arrays X and C must be 16-byte aligned when d % 4 == 0 (rows are read with 16-byte loads)");
 
   // chunking of the base set: the unary buffer (m KB per vector) stays within budget (nsplits of
   // src/LSQ_GPU.jl:226-255, done inside the library); gridDim.y of K1 caps a chunk at 65535 * 128 vectors; with HOST
@@ -2080,6 +2082,8 @@ extern "C" int rayuela_get_unaries(const float* X, const float* C, int64_t n, in
   RYL_ARG(X && C && U, "get_unaries: null array");
   RYL_ARG(n <= (int64_t)65535 * 128, "get_unaries: at most 8388480 vectors per call");
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  RYL_ARG(!dev || d % 4 != 0 || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+          "get_unaries: device arrays X and C must be 16-byte aligned when d % 4 == 0");
   const int mh = m * kH;
   InArg<float> x_in, c_in;
   RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
@@ -2107,6 +2111,8 @@ extern "C" int rayuela_veccost(const float* X, const uint8_t* B, const float* C,
   cudaStream_t s = (cudaStream_t)stream;
   RYL_ARG(h >= 1 && h <= kH && m >= 1 && m <= 16 && n >= 1 && d >= 1, "veccost: bad shape (h in 1..256, m in 1..16)");
   const bool dev = flags & RAYUELA_DEVICE_PTRS;
+  RYL_ARG(!dev || d % 4 != 0 || ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+          "veccost: device arrays X and C must be 16-byte aligned when d % 4 == 0");
   InArg<float> x_in, c_in;
   InArg<uint8_t> b_in;
   RYL_TRY(x_in.bind(X, (size_t)n * d, dev, s));
